@@ -1,0 +1,82 @@
+"""ctypes binding of ``liblcr_b200.so`` (the C ABI of include/lcr_b200.h).
+
+The library is the only compute path of this package: if it cannot be loaded, or CUDA is not
+available when an operator is called, a RuntimeError is raised (never a CPU fallback).
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'liblcr_b200.so')
+
+c_i32, c_i64, c_f32, c_sz, c_vp = ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_size_t, ctypes.c_void_p
+
+# name -> (restype, argtypes); must list every symbol include/lcr_b200.h declares
+SIGNATURES = {
+    'lcr_last_error': (ctypes.c_char_p, []),
+    'lcr_abi_version': (c_i32, []),
+    'lcr_grid_subsample_ws_bytes': (c_sz, [c_i64, c_i32]),
+    'lcr_grid_subsample': (c_i32, [c_vp, c_i64, c_vp, c_i32, c_f32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    'lcr_radius_neighbors_ws_bytes': (c_sz, [c_i64, c_i64, c_i32]),
+    'lcr_radius_neighbors': (c_i32, [c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_i32, c_f32, c_i32, c_vp, c_i32, c_vp,
+                                     c_vp, c_vp, c_vp, c_sz, c_vp]),
+}
+
+_lib = None
+
+
+def lib():
+    """The loaded library (loads on first use; raises if it has not been built)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError('%s is missing: run `python -c "import __graft_entry__ as g; g.build()"` '
+                               '(there is no CPU fallback)' % LIB_PATH)
+        l = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(l, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = l
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise RuntimeError('lcr_b200 error %d: %s' % (rc, lib().lcr_last_error().decode()))
+
+
+def require_cuda(*tensors):
+    if not torch.cuda.is_available():
+        raise RuntimeError('lcrnet_b200 needs a CUDA device (sm_100a); there is no CPU fallback')
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError('expected a CUDA tensor')
+
+
+def ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def stream_ptr(device=None):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+class _Workspace:
+    """Grow-only scratch buffers, one per (device, slot)."""
+
+    def __init__(self):
+        self._buf = {}
+
+    def get(self, nbytes, device, slot=0):
+        key = (device.index if device.index is not None else torch.cuda.current_device(), slot)
+        b = self._buf.get(key)
+        if b is None or b.numel() < nbytes:
+            b = torch.empty(max(int(nbytes * 1.25), 1 << 20), dtype=torch.uint8, device=device)
+            self._buf[key] = b
+        return b
+
+
+workspace = _Workspace()
