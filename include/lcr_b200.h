@@ -75,6 +75,71 @@ int lcr_radius_neighbors(const float* q_points, int64_t nq_total, const float* s
                          int width, void* out_idx, int idx_is64, int32_t* out_counts,
                          int32_t* out_max_count, int32_t* out_status, void* ws, size_t ws_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * a4. KPConv forward.  Replaces KPConv.forward (experiments/lcrnet/modules/kpconv/kpconv.py:79-122).
+ * s_feats[n_support, c_in], q_points[m_query,3], s_points[n_support,3], idx int32 [m_query, ld_idx]
+ * (first H columns used, pad = n_support), kernel_points[15,3], weights[15, c_in, c_out],
+ * bias[c_out] or NULL -> out[m_query, c_out].  s_flags[n_support] (u8, optional): 1 where the
+ * feature row sum is > 0 (the reference's neighbour_num counts only those rows, :113-116);
+ * NULL counts every valid neighbour.  c_in in {1, 32, 64, 128, 256}.
+ * ---------------------------------------------------------------------------------------- */
+size_t lcr_kpconv_ws_bytes(int64_t m_query, int c_in);
+int lcr_kpconv(const float* s_feats, const uint8_t* s_flags, int64_t n_support, const float* q_points,
+               int64_t m_query, const float* s_points, const int32_t* idx, int ld_idx, int H,
+               const float* kernel_points, float sigma, const float* weights, const float* bias, int c_in,
+               int c_out, float* out, void* ws, size_t ws_bytes, void* stream);
+/* flags[r] = (sum_c x[r, c] > 0) */
+int lcr_row_flags(const float* x, int64_t rows, int channels, uint8_t* flags, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a5. Linear, GroupNorm, LeakyReLU, residual add, neighbour max-pool.  Replace nn.Linear +
+ * GroupNorm wrapper + UnaryBlock / ResidualBlock glue (modules/kpconv/modules.py:33-225) and
+ * maxpool (modules/kpconv/functional.py:54-67).
+ * lcr_linear: out[n_rows, c_out] = x[n_rows, c_in] . weight_t[c_in, c_out] + bias  (weight_t is the
+ *   TRANSPOSE of nn.Linear.weight, prepared once at load time).
+ * lcr_group_norm_stats: per (stack, group) mean and 1/sqrt(var+eps) over (channels/groups) x (all
+ *   rows of the stack) (biased variance), stats_out f32 [n_stacks, groups, 2].
+ * lcr_group_norm_apply: y = act(gn(x) + other) with other = nothing (x2 NULL), a raw tensor
+ *   (x2, stats2 NULL) or gn(x2; stats2, gamma2, beta2); act = LeakyReLU(slope) if leaky.
+ *   row_flags (optional) receives (sum_c y[r, c] > 0) for the following KPConv.
+ * ---------------------------------------------------------------------------------------- */
+int lcr_linear(const float* x, int64_t n_rows, int c_in, const float* weight_t, int c_out, const float* bias,
+               float* out, void* stream);
+size_t lcr_group_norm_ws_bytes(int64_t max_stack_rows, int n_stacks, int groups);
+int lcr_group_norm_stats(const float* x, int64_t rows, int channels, int groups, const int64_t* stack_off,
+                         int n_stacks, int64_t max_stack_rows, float eps, float* stats_out, void* ws,
+                         size_t ws_bytes, void* stream);
+int lcr_group_norm_apply(const float* x, const float* stats, const float* gamma, const float* beta,
+                         const float* x2, const float* stats2, const float* gamma2, const float* beta2,
+                         int64_t rows, int channels, int groups, const int64_t* stack_off, int n_stacks,
+                         int leaky, float slope, float* y, uint8_t* row_flags, void* stream);
+int lcr_maxpool(const float* x, int64_t n_support, const int32_t* idx, int ld_idx, int H, int64_t m_query,
+                int channels, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a8. NetVLAD global-descriptor head (eval mode), batched over scans.  Replaces
+ * F.normalize + NetVLADLoupe2.forward + GatingContext + F.normalize
+ * (modules/netvlad/NetVlad.py:49-87,189-201; model_family/LCRNet_GlobalDescrition.py:34-38).
+ * feats[rows, 1024] with scan_off[n_scans+1] row offsets -> out[n_scans, 256] (unit L2 norm).
+ * bn1 / bn2 / gating_bn: weight, bias, running_mean, running_var concatenated (4 x C floats).
+ * ---------------------------------------------------------------------------------------- */
+size_t lcr_netvlad_ws_bytes(int64_t rows, int n_scans);
+int lcr_netvlad(const float* feats, int64_t rows, const int64_t* scan_off, int n_scans,
+                const float* cluster_weights, const float* cluster_weights2, const float* hidden1_weights,
+                const float* bn1, const float* bn2, const float* gating_weights, const float* gating_bn, float* out,
+                void* ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a15. Exact squared-L2 top-k descriptor retrieval.  Replaces the faiss IndexIVFFlat(nlist=1)
+ * loop of experiments/loop_detection/eval_loop_detection_overlap_dataset.py:183-214 and
+ * experiments/inference/infer_loop_detection_find_top1.py:79-104.
+ * queries[n_queries, 256], db[n_db, 256]; valid_counts[n_queries] (i32, optional): query i only
+ * searches db rows [0, valid_counts[i]).  out_d2 / out_idx [n_queries, k] ascending (d2, index);
+ * missing entries are (+inf, -1).  k <= 64.
+ * ---------------------------------------------------------------------------------------- */
+int lcr_l2_topk(const float* queries, int64_t n_queries, const float* db, int64_t n_db, int dim, int k,
+                const int32_t* valid_counts, float* out_d2, int64_t* out_idx, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

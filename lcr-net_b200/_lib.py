@@ -22,6 +22,20 @@ SIGNATURES = {
     'lcr_radius_neighbors_ws_bytes': (c_sz, [c_i64, c_i64, c_i32]),
     'lcr_radius_neighbors': (c_i32, [c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_i32, c_f32, c_i32, c_vp, c_i32, c_vp,
                                      c_vp, c_vp, c_vp, c_sz, c_vp]),
+    'lcr_kpconv_ws_bytes': (c_sz, [c_i64, c_i32]),
+    'lcr_kpconv': (c_i32, [c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_i32, c_i32, c_vp, c_f32, c_vp, c_vp, c_i32,
+                           c_i32, c_vp, c_vp, c_sz, c_vp]),
+    'lcr_row_flags': (c_i32, [c_vp, c_i64, c_i32, c_vp, c_vp]),
+    'lcr_linear': (c_i32, [c_vp, c_i64, c_i32, c_vp, c_i32, c_vp, c_vp, c_vp]),
+    'lcr_group_norm_ws_bytes': (c_sz, [c_i64, c_i32, c_i32]),
+    'lcr_group_norm_stats': (c_i32, [c_vp, c_i64, c_i32, c_i32, c_vp, c_i32, c_i64, c_f32, c_vp, c_vp, c_sz, c_vp]),
+    'lcr_group_norm_apply': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_vp,
+                                     c_i32, c_i32, c_f32, c_vp, c_vp, c_vp]),
+    'lcr_maxpool': (c_i32, [c_vp, c_i64, c_vp, c_i32, c_i32, c_i64, c_i32, c_vp, c_vp]),
+    'lcr_netvlad_ws_bytes': (c_sz, [c_i64, c_i32]),
+    'lcr_netvlad': (c_i32, [c_vp, c_i64, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_sz,
+                            c_vp]),
+    'lcr_l2_topk': (c_i32, [c_vp, c_i64, c_vp, c_i64, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp]),
 }
 
 _lib = None

@@ -1,0 +1,416 @@
+// encoder.cu -- a4/a5/a6: KPConv, GroupNorm (+LeakyReLU, residual), max-pool for the KPConv
+// encoder (reference: experiments/lcrnet/modules/kpconv/kpconv.py:79-122,
+// modules/kpconv/modules.py:33-225, modules/kpconv/functional.py:54-67, backbone4.py:11-89).
+//
+// Data layout in HBM: features row-major f32 [rows, C]; points f32 [rows, 3]; neighbour tables
+// int32 [M, ld_idx] with pad value = number of support rows (the int64 tables of the reference
+// boundary are narrowed once on entry).  Several "stacks" (the unit of one reference forward:
+// one scan, or the two scans of a pair) are concatenated along rows; GroupNorm statistics are
+// per stack (stack_off[S+1] row offsets), everything else is oblivious to stack boundaries
+// because neighbour indices never cross clouds.
+//
+// KPConv is split into
+//   (A) kpconv_gather_kernel: irregular gather, one warp per query point.  Lanes compute the 15
+//       kernel-point influences of 32 neighbours at a time into shared memory, then every lane
+//       owns C/32 channels and accumulates wf[k][c] = sum_h w[k,h] * feat[idx[h], c] in registers
+//       with coalesced 128 B feature-row loads.  Output wf[M, 15*C] and 1/neighbour_num.
+//   (B) the fp32 GEMM of gemm.cu: [M, 15C] x [15C, O] with the 1/num row scale and bias fused.
+#include "common.cuh"
+
+int lcr_gemm_f32(const float* A, int lda, const float* B, int ldb, float* C, int ldc, int M, int N, int K,
+                 const float* rowscale, const float* bias, cudaStream_t stream);
+
+namespace {
+
+constexpr int KP = 15;  // kernel points (config_model.py:35)
+
+// ------------------------------------------------------------------ KPConv gather
+template <int CPL>  // channels per lane: C = 32 * CPL
+__global__ void __launch_bounds__(128)
+kpconv_gather_kernel(const float* __restrict__ s_feats, const float* __restrict__ q_pts,
+                     const float* __restrict__ s_pts, const int32_t* __restrict__ idx, int ld_idx, int H,
+                     const float* __restrict__ kpts, float sigma, const uint8_t* __restrict__ flags, int M,
+                     int N, float* __restrict__ wf, float* __restrict__ rowscale) {
+  constexpr int C = 32 * CPL;
+  __shared__ float s_w[4][KP][32];
+  __shared__ int s_j[4][32];
+  __shared__ float s_kp[KP * 3];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x < KP * 3) s_kp[threadIdx.x] = kpts[threadIdx.x];
+  __syncthreads();
+  const int m = blockIdx.x * 4 + warp;
+  if (m >= M) return;
+  const float qx = q_pts[3 * m], qy = q_pts[3 * m + 1], qz = q_pts[3 * m + 2];
+  float acc[KP][CPL];
+#pragma unroll
+  for (int k = 0; k < KP; k++)
+#pragma unroll
+    for (int i = 0; i < CPL; i++) acc[k][i] = 0.f;
+  int cnt = 0;
+  const int32_t* row = idx + (size_t)m * ld_idx;
+  for (int h0 = 0; h0 < H; h0 += 32) {
+    const int h = h0 + lane;
+    const int j = h < H ? row[h] : N;
+    const bool valid = j < N;
+    if (valid) {
+      const float rx = s_pts[3 * (size_t)j] - qx, ry = s_pts[3 * (size_t)j + 1] - qy,
+                  rz = s_pts[3 * (size_t)j + 2] - qz;
+#pragma unroll
+      for (int k = 0; k < KP; k++) {
+        const float dx = rx - s_kp[3 * k], dy = ry - s_kp[3 * k + 1], dz = rz - s_kp[3 * k + 2];
+        const float d2 = dx * dx + dy * dy + dz * dz;
+        s_w[warp][k][lane] = fmaxf(1.f - __fdiv_rn(sqrtf(d2), sigma), 0.f);
+      }
+      cnt += flags ? (int)flags[j] : 1;
+    }
+    s_j[warp][lane] = j;
+    const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+    __syncwarp();
+    // rows are sorted by distance with the pads last, but tolerate holes: iterate set bits
+    unsigned rem = vmask;
+    while (rem) {
+      const int hh = __ffs(rem) - 1;
+      rem &= rem - 1;
+      const float* f = s_feats + (size_t)s_j[warp][hh] * C + lane;
+      float fv[CPL];
+#pragma unroll
+      for (int i = 0; i < CPL; i++) fv[i] = f[32 * i];
+#pragma unroll
+      for (int k = 0; k < KP; k++) {
+        const float w = s_w[warp][k][hh];
+#pragma unroll
+        for (int i = 0; i < CPL; i++) acc[k][i] = fmaf(w, fv[i], acc[k][i]);
+      }
+    }
+    __syncwarp();
+  }
+  cnt = lcr_warp_sum(cnt);
+  float* o = wf + (size_t)m * (KP * C) + lane;
+#pragma unroll
+  for (int k = 0; k < KP; k++)
+#pragma unroll
+    for (int i = 0; i < CPL; i++) o[k * C + 32 * i] = acc[k][i];
+  if (lane == 0) rowscale[m] = 1.f / (float)max(cnt, 1);
+}
+
+// C_in = 1 (encoder1_1): lanes over neighbours, 15 warp-reduced sums, then O outputs per query.
+__global__ void __launch_bounds__(128)
+kpconv_c1_kernel(const float* __restrict__ s_feats, const float* __restrict__ q_pts, const float* __restrict__ s_pts,
+                 const int32_t* __restrict__ idx, int ld_idx, int H, const float* __restrict__ kpts, float sigma,
+                 const float* __restrict__ weights /*[15,1,O]*/, const float* __restrict__ bias, int O, int M, int N,
+                 float* __restrict__ out) {
+  __shared__ float s_kp[KP * 3];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x < KP * 3) s_kp[threadIdx.x] = kpts[threadIdx.x];
+  __syncthreads();
+  const int m = blockIdx.x * 4 + warp;
+  if (m >= M) return;
+  const float qx = q_pts[3 * m], qy = q_pts[3 * m + 1], qz = q_pts[3 * m + 2];
+  float ws[KP];
+#pragma unroll
+  for (int k = 0; k < KP; k++) ws[k] = 0.f;
+  int cnt = 0;
+  const int32_t* row = idx + (size_t)m * ld_idx;
+  for (int h = lane; h < H; h += 32) {
+    const int j = row[h];
+    if (j < N) {
+      const float f = s_feats[j];
+      const float rx = s_pts[3 * (size_t)j] - qx, ry = s_pts[3 * (size_t)j + 1] - qy,
+                  rz = s_pts[3 * (size_t)j + 2] - qz;
+#pragma unroll
+      for (int k = 0; k < KP; k++) {
+        const float dx = rx - s_kp[3 * k], dy = ry - s_kp[3 * k + 1], dz = rz - s_kp[3 * k + 2];
+        const float d2 = dx * dx + dy * dy + dz * dz;
+        ws[k] = fmaf(fmaxf(1.f - __fdiv_rn(sqrtf(d2), sigma), 0.f), f, ws[k]);
+      }
+      cnt += f > 0.f;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < KP; k++) ws[k] = lcr_warp_sum(ws[k]);
+  cnt = lcr_warp_sum(cnt);
+  const float num = (float)max(cnt, 1);
+  for (int o = lane; o < O; o += 32) {
+    float a = 0.f;
+#pragma unroll
+    for (int k = 0; k < KP; k++) a = fmaf(ws[k], weights[k * O + o], a);
+    a = __fdiv_rn(a, num);
+    out[(size_t)m * O + o] = bias ? a + bias[o] : a;
+  }
+}
+
+// ------------------------------------------------------------------ GroupNorm statistics
+// partial[(s * n_chunks + chunk) * G + g] = (sum, sumsq) over rows of the chunk x channels of g.
+constexpr int kGnRows = 64;
+
+__global__ void __launch_bounds__(256)
+gn_partial_kernel(const float* __restrict__ x, int C, int G, const int64_t* __restrict__ stack_off, int n_chunks,
+                  double2* __restrict__ partial) {
+  // per-column partial sums of this chunk's rows go through shared memory, then one thread per
+  // group adds its columns in a fixed order (deterministic; no float atomics)
+  __shared__ float s_sum[1024], s_sq[1024];
+  const int s = blockIdx.y, chunk = blockIdx.x;
+  const int64_t r0 = stack_off[s] + (int64_t)chunk * kGnRows;
+  const int64_t r1 = min(r0 + kGnRows, stack_off[s + 1]);
+  int slots;  // number of shared-memory slots per column group layout
+  if (C >= 256) {
+    for (int c = threadIdx.x; c < C; c += 256) {
+      float a = 0.f, b = 0.f;
+      for (int64_t r = r0; r < r1; r++) {
+        const float v = x[r * C + c];
+        a += v;
+        b = fmaf(v, v, b);
+      }
+      s_sum[c] = a;
+      s_sq[c] = b;
+    }
+    slots = 1;
+  } else {
+    const int rl = 256 / C, c = threadIdx.x % C, rlane = threadIdx.x / C;  // 256/C row lanes
+    float a = 0.f, b = 0.f;
+    for (int64_t r = r0 + rlane; r < r1; r += rl) {
+      const float v = x[r * C + c];
+      a += v;
+      b = fmaf(v, v, b);
+    }
+    s_sum[rlane * C + c] = a;
+    s_sq[rlane * C + c] = b;
+    slots = rl;
+  }
+  __syncthreads();
+  if (threadIdx.x < G) {
+    const int cpg = C / G;
+    double a = 0.0, b = 0.0;
+    for (int r = 0; r < slots; r++)
+      for (int cc = 0; cc < cpg; cc++) {
+        a += (double)s_sum[r * C + threadIdx.x * cpg + cc];
+        b += (double)s_sq[r * C + threadIdx.x * cpg + cc];
+      }
+    partial[((size_t)s * n_chunks + chunk) * G + threadIdx.x] = make_double2(a, b);
+  }
+}
+
+// one warp per (stack, group): fixed-order reduction over chunks -> mean, rstd
+__global__ void gn_finalize_kernel(const double2* __restrict__ partial, int G, int C,
+                                   const int64_t* __restrict__ stack_off, int n_chunks, int S, float eps,
+                                   float2* __restrict__ stats) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= S * G) return;
+  const int s = w / G, g = w % G;
+  const int64_t rows = stack_off[s + 1] - stack_off[s];
+  const int used = (int)((rows + kGnRows - 1) / kGnRows);
+  double a = 0.0, b = 0.0;
+  for (int ch = lane; ch < used; ch += 32) {
+    const double2 p = partial[((size_t)s * n_chunks + ch) * G + g];
+    a += p.x;
+    b += p.y;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+  }
+  if (lane == 0) {
+    const double n = (double)rows * (double)(C / G);
+    const double mean = n > 0 ? a / n : 0.0;
+    const double var = n > 0 ? fmax(b / n - mean * mean, 0.0) : 0.0;
+    stats[w] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
+  }
+}
+
+// ------------------------------------------------------------------ GroupNorm apply (+add, +LeakyReLU, +row flags)
+// y = act( gn(x; stats, gamma, beta) + other ),  other = none | raw tensor | gn(x2; stats2, gamma2, beta2)
+struct GnApplyArgs {
+  const float* x; const float2* stats; const float* gamma; const float* beta;
+  const float* x2; const float2* stats2; const float* gamma2; const float* beta2;
+  float* y; uint8_t* flags;
+  const int64_t* stack_off; int S; int64_t rows; int C; int G; float slope; int act;
+};
+
+__global__ void __launch_bounds__(256) gn_apply_kernel(GnApplyArgs a) {
+  const int lpr = min(32, a.C / 4);          // lanes per row
+  const int rpw = 32 / lpr;                  // rows per warp
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t r = warp * rpw + lane / lpr;
+  const int sub = lane % lpr;
+  const bool active = r < a.rows;
+  float rowsum = 0.f;
+  if (active) {
+    const int s = lcr_find_segment(a.stack_off, a.S, r);
+    const int cpg = a.C / a.G;
+    for (int c = sub * 4; c < a.C; c += lpr * 4) {
+      float4 v = *reinterpret_cast<const float4*>(a.x + r * a.C + c);
+      float o[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const float2 st = a.stats[s * a.G + (c + i) / cpg];
+        o[i] = (o[i] - st.x) * st.y * a.gamma[c + i] + a.beta[c + i];
+      }
+      if (a.x2) {
+        const float4 w = *reinterpret_cast<const float4*>(a.x2 + r * a.C + c);
+        float p[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          if (a.stats2) {
+            const float2 st = a.stats2[s * a.G + (c + i) / cpg];
+            p[i] = (p[i] - st.x) * st.y * a.gamma2[c + i] + a.beta2[c + i];
+          }
+          o[i] += p[i];
+        }
+      }
+      if (a.act) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) o[i] = o[i] > 0.f ? o[i] : o[i] * a.slope;
+      }
+      rowsum += (o[0] + o[1]) + (o[2] + o[3]);
+      *reinterpret_cast<float4*>(a.y + r * a.C + c) = make_float4(o[0], o[1], o[2], o[3]);
+    }
+  }
+  if (a.flags) {
+    for (int o = lpr >> 1; o > 0; o >>= 1) rowsum += __shfl_xor_sync(0xffffffffu, rowsum, o);
+    if (active && sub == 0) a.flags[r] = rowsum > 0.f;
+  }
+}
+
+// ------------------------------------------------------------------ max-pool over neighbours
+__global__ void __launch_bounds__(256)
+maxpool_kernel(const float* __restrict__ x, const int32_t* __restrict__ idx, int ld_idx, int H, int M, int N, int C,
+               float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int m = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (m >= M) return;
+  const int32_t* row = idx + (size_t)m * ld_idx;
+  for (int c = lane * 4; c < C; c += 128) {
+    float4 best = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    for (int h = 0; h < H; h++) {
+      const int j = row[h];
+      // the pad row of the reference is a row of zeros appended to x (functional.py:64)
+      const float4 v = j < N ? *reinterpret_cast<const float4*>(x + (size_t)j * C + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      best.x = fmaxf(best.x, v.x);
+      best.y = fmaxf(best.y, v.y);
+      best.z = fmaxf(best.z, v.z);
+      best.w = fmaxf(best.w, v.w);
+    }
+    *reinterpret_cast<float4*>(out + (size_t)m * C + c) = best;
+  }
+}
+
+__global__ void rowflag_kernel(const float* __restrict__ x, int64_t rows, int C, uint8_t* __restrict__ flags) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (r >= rows) return;
+  float s = 0.f;
+  for (int c = lane; c < C; c += 32) s += x[r * C + c];
+  s = lcr_warp_sum(s);
+  if (lane == 0) flags[r] = s > 0.f;
+}
+
+}  // namespace
+
+// ================================================================== C ABI
+extern "C" size_t lcr_kpconv_ws_bytes(int64_t m_rows, int c_in) {
+  return lcr_align_up((size_t)m_rows * KP * c_in * sizeof(float)) + lcr_align_up((size_t)m_rows * sizeof(float)) + 256;
+}
+
+extern "C" int lcr_kpconv(const float* s_feats, const uint8_t* s_flags, int64_t n_support, const float* q_points,
+                          int64_t m_query, const float* s_points, const int32_t* idx, int ld_idx, int H,
+                          const float* kernel_points, float sigma, const float* weights, const float* bias, int c_in,
+                          int c_out, float* out, void* ws, size_t ws_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  LCR_REQUIRE(m_query >= 0 && n_support >= 0 && m_query < (1ll << 31) && n_support < (1ll << 31), "kpconv: sizes");
+  LCR_REQUIRE(H >= 1 && ld_idx >= H, "kpconv: bad neighbour table width");
+  LCR_REQUIRE(c_in == 1 || c_in == 32 || c_in == 64 || c_in == 128 || c_in == 256,
+              "kpconv: c_in must be 1, 32, 64, 128 or 256");
+  LCR_REQUIRE(c_out % 32 == 0, "kpconv: c_out must be a multiple of 32");
+  if (m_query == 0) return LCR_OK;
+  const int M = (int)m_query, N = (int)n_support;
+  const unsigned grid = (unsigned)((M + 3) / 4);
+  if (c_in == 1) {
+    kpconv_c1_kernel<<<grid, 128, 0, stream>>>(s_feats, q_points, s_points, idx, ld_idx, H, kernel_points, sigma,
+                                               weights, bias, c_out, M, N, out);
+    LCR_CUDA_CHECK_LAUNCH();
+    return LCR_OK;
+  }
+  LCR_REQUIRE(ws && ws_bytes >= lcr_kpconv_ws_bytes(m_query, c_in), "kpconv: workspace too small");
+  LcrArena a(ws, ws_bytes);
+  float* wf = a.take<float>((size_t)M * KP * c_in);
+  float* rowscale = a.take<float>(M);
+#define LCR_GATHER(CPL)                                                                                        \
+  kpconv_gather_kernel<CPL><<<grid, 128, 0, stream>>>(s_feats, q_points, s_points, idx, ld_idx, H, kernel_points, \
+                                                      sigma, s_flags, M, N, wf, rowscale)
+  switch (c_in) {
+    case 32: LCR_GATHER(1); break;
+    case 64: LCR_GATHER(2); break;
+    case 128: LCR_GATHER(4); break;
+    default: LCR_GATHER(8); break;
+  }
+#undef LCR_GATHER
+  LCR_CUDA_CHECK_LAUNCH();
+  return lcr_gemm_f32(wf, KP * c_in, weights, c_out, out, c_out, M, c_out, KP * c_in, rowscale, bias, stream);
+}
+
+extern "C" size_t lcr_group_norm_ws_bytes(int64_t max_stack_rows, int n_stacks, int groups) {
+  const size_t chunks = (size_t)((max_stack_rows + kGnRows - 1) / kGnRows) + 1;
+  return lcr_align_up(chunks * n_stacks * groups * sizeof(double2)) + 256;
+}
+
+extern "C" int lcr_group_norm_stats(const float* x, int64_t rows, int channels, int groups, const int64_t* stack_off,
+                                    int n_stacks, int64_t max_stack_rows, float eps, float* stats_out, void* ws,
+                                    size_t ws_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  LCR_REQUIRE(channels % groups == 0 && groups <= 32 && channels % 4 == 0, "group_norm: bad channel/group count");
+  LCR_REQUIRE(channels <= 256 ? (256 % channels == 0) : (channels % 256 == 0 && channels <= 1024),
+              "group_norm: channels must divide 256 or be a multiple of 256 (<= 1024)");
+  LCR_REQUIRE(n_stacks >= 1 && ws && ws_bytes >= lcr_group_norm_ws_bytes(max_stack_rows, n_stacks, groups),
+              "group_norm: workspace too small");
+  if (rows == 0) return LCR_OK;
+  const int n_chunks = (int)((max_stack_rows + kGnRows - 1) / kGnRows) + 1;
+  double2* partial = (double2*)ws;
+  dim3 grid(n_chunks, n_stacks);
+  gn_partial_kernel<<<grid, 256, 0, stream>>>(x, channels, groups, stack_off, n_chunks, partial);
+  const int warps = n_stacks * groups;
+  gn_finalize_kernel<<<(warps * 32 + 255) / 256, 256, 0, stream>>>(partial, groups, channels, stack_off, n_chunks,
+                                                                   n_stacks, eps, (float2*)stats_out);
+  LCR_CUDA_CHECK_LAUNCH();
+  return LCR_OK;
+}
+
+extern "C" int lcr_group_norm_apply(const float* x, const float* stats, const float* gamma, const float* beta,
+                                    const float* x2, const float* stats2, const float* gamma2, const float* beta2,
+                                    int64_t rows, int channels, int groups, const int64_t* stack_off, int n_stacks,
+                                    int leaky, float slope, float* y, uint8_t* row_flags, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  LCR_REQUIRE(channels % 32 == 0 && channels % groups == 0, "group_norm_apply: bad channel count");
+  if (rows == 0) return LCR_OK;
+  GnApplyArgs a;
+  a.x = x; a.stats = (const float2*)stats; a.gamma = gamma; a.beta = beta;
+  a.x2 = x2; a.stats2 = (const float2*)stats2; a.gamma2 = gamma2; a.beta2 = beta2;
+  a.y = y; a.flags = row_flags; a.stack_off = stack_off; a.S = n_stacks; a.rows = rows; a.C = channels;
+  a.G = groups; a.slope = slope; a.act = leaky;
+  const int lpr = channels / 4 < 32 ? channels / 4 : 32;
+  const int rpw = 32 / lpr;
+  const int64_t warps = (rows + rpw - 1) / rpw;
+  gn_apply_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, stream>>>(a);
+  LCR_CUDA_CHECK_LAUNCH();
+  return LCR_OK;
+}
+
+extern "C" int lcr_maxpool(const float* x, int64_t n_support, const int32_t* idx, int ld_idx, int H, int64_t m_query,
+                           int channels, float* out, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  LCR_REQUIRE(channels % 4 == 0 && H >= 1 && ld_idx >= H, "maxpool: bad shape");
+  if (m_query == 0) return LCR_OK;
+  maxpool_kernel<<<(unsigned)((m_query * 32 + 255) / 256), 256, 0, stream>>>(x, idx, ld_idx, H, (int)m_query,
+                                                                            (int)n_support, channels, out);
+  LCR_CUDA_CHECK_LAUNCH();
+  return LCR_OK;
+}
+
+extern "C" int lcr_row_flags(const float* x, int64_t rows, int channels, uint8_t* flags, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (rows == 0) return LCR_OK;
+  rowflag_kernel<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, stream>>>(x, rows, channels, flags);
+  LCR_CUDA_CHECK_LAUNCH();
+  return LCR_OK;
+}

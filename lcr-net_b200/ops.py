@@ -1,0 +1,144 @@
+"""Host-side operator layer: the reference's ``experiments/lcrnet/modules/ops`` wrappers
+(grid_subsample.py:7-22, radius_search.py:7-27) plus thin torch-tensor wrappers over the C ABI
+for the model kernels.  All tensors are CUDA tensors; nothing here computes on the CPU."""
+import torch
+
+from . import _lib, ext
+
+GROUPS = 32
+
+
+def grid_subsample(points, lengths, voxel_size, order='reference'):
+    """ops/grid_subsample.py:7-22."""
+    s_points, s_lengths = ext.grid_subsampling(points, lengths, voxel_size, order=order)
+    return s_points, s_lengths
+
+
+def radius_search(q_points, s_points, q_lengths, s_lengths, radius, neighbor_limit, int32=False):
+    """ops/radius_search.py:7-27 (the ``[:, :neighbor_limit]`` cut is fused into the kernel)."""
+    return ext.radius_neighbors(q_points, s_points, q_lengths, s_lengths, radius,
+                                limit=neighbor_limit if neighbor_limit and neighbor_limit > 0 else 0, int32=int32)
+
+
+def _f32c(t):
+    assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous(), 'expected a contiguous CUDA float tensor'
+    return t
+
+
+def as_index32(idx):
+    """Neighbour tables are int32 inside the kernels; the reference's int64 tables are narrowed."""
+    if idx.dtype != torch.int32:
+        idx = idx.to(torch.int32)
+    if idx.stride(-1) != 1:
+        idx = idx.contiguous()
+    return idx
+
+
+def row_flags(x):
+    _lib.require_cuda(x)
+    flags = torch.empty(x.shape[0], dtype=torch.uint8, device=x.device)
+    _lib.check(_lib.lib().lcr_row_flags(_lib.ptr(_f32c(x)), x.shape[0], x.shape[1], _lib.ptr(flags),
+                                        _lib.stream_ptr(x.device)))
+    return flags
+
+
+def kpconv(s_feats, q_points, s_points, idx, kernel_points, sigma, weights, bias, s_flags=None):
+    """KPConv.forward (kpconv.py:79-122).  ``s_flags``: row-sum>0 flags of s_feats (computed if None)."""
+    _lib.require_cuda(s_feats, q_points, s_points, idx)
+    L = _lib.lib()
+    idx = as_index32(idx)
+    m, n = q_points.shape[0], s_points.shape[0]
+    c_in, c_out = weights.shape[1], weights.shape[2]
+    if s_flags is None and c_in > 1:
+        s_flags = row_flags(s_feats)
+    out = torch.empty((m, c_out), dtype=torch.float32, device=s_feats.device)
+    ws_bytes = L.lcr_kpconv_ws_bytes(m, c_in)
+    ws = _lib.workspace.get(ws_bytes, s_feats.device, slot=1)
+    _lib.check(L.lcr_kpconv(_lib.ptr(_f32c(s_feats)), _lib.ptr(s_flags), n, _lib.ptr(_f32c(q_points)), m,
+                            _lib.ptr(_f32c(s_points)), _lib.ptr(idx), idx.stride(0), idx.shape[1],
+                            _lib.ptr(_f32c(kernel_points)), float(sigma), _lib.ptr(_f32c(weights)), _lib.ptr(bias),
+                            c_in, c_out, _lib.ptr(out), _lib.ptr(ws), ws.numel(), _lib.stream_ptr(s_feats.device)))
+    return out
+
+
+def linear(x, weight_t, bias):
+    """nn.Linear with the weight pre-transposed to [c_in, c_out]."""
+    _lib.require_cuda(x)
+    out = torch.empty((x.shape[0], weight_t.shape[1]), dtype=torch.float32, device=x.device)
+    _lib.check(_lib.lib().lcr_linear(_lib.ptr(_f32c(x)), x.shape[0], x.shape[1], _lib.ptr(_f32c(weight_t)),
+                                     weight_t.shape[1], _lib.ptr(bias), _lib.ptr(out), _lib.stream_ptr(x.device)))
+    return out
+
+
+class Stacks:
+    """Row offsets of the stacks (units of one reference forward) at one pyramid level."""
+
+    def __init__(self, lengths_host, device):
+        import itertools
+        off = [0] + list(itertools.accumulate(int(x) for x in lengths_host))
+        self.n = len(off) - 1
+        self.rows = off[-1]
+        self.max_rows = max([b - a for a, b in zip(off[:-1], off[1:])] + [1])
+        self.off = torch.tensor(off, dtype=torch.int64, device=device)
+
+
+def group_norm_stats(x, stacks, eps=1e-5, groups=GROUPS):
+    L = _lib.lib()
+    stats = torch.empty((stacks.n, groups, 2), dtype=torch.float32, device=x.device)
+    ws_bytes = L.lcr_group_norm_ws_bytes(stacks.max_rows, stacks.n, groups)
+    ws = _lib.workspace.get(ws_bytes, x.device, slot=2)
+    _lib.check(L.lcr_group_norm_stats(_lib.ptr(_f32c(x)), x.shape[0], x.shape[1], groups, _lib.ptr(stacks.off),
+                                      stacks.n, stacks.max_rows, eps, _lib.ptr(stats), _lib.ptr(ws), ws.numel(),
+                                      _lib.stream_ptr(x.device)))
+    return stats
+
+
+def group_norm_apply(x, stats, gamma, beta, stacks, leaky=True, other=None, other_norm=None, want_flags=False,
+                     groups=GROUPS, slope=0.1):
+    """y = act(gn(x) + other); other_norm = (stats2, gamma2, beta2) normalises ``other`` first."""
+    y = torch.empty_like(x)
+    flags = torch.empty(x.shape[0], dtype=torch.uint8, device=x.device) if want_flags else None
+    s2, g2, b2 = other_norm if other_norm is not None else (None, None, None)
+    _lib.check(_lib.lib().lcr_group_norm_apply(
+        _lib.ptr(_f32c(x)), _lib.ptr(stats), _lib.ptr(gamma), _lib.ptr(beta), _lib.ptr(other), _lib.ptr(s2),
+        _lib.ptr(g2), _lib.ptr(b2), x.shape[0], x.shape[1], groups, _lib.ptr(stacks.off), stacks.n,
+        1 if leaky else 0, slope, _lib.ptr(y), _lib.ptr(flags), _lib.stream_ptr(x.device)))
+    return (y, flags) if want_flags else y
+
+
+def maxpool(x, idx):
+    """functional.py:54-67."""
+    idx = as_index32(idx)
+    out = torch.empty((idx.shape[0], x.shape[1]), dtype=torch.float32, device=x.device)
+    _lib.check(_lib.lib().lcr_maxpool(_lib.ptr(_f32c(x)), x.shape[0], _lib.ptr(idx), idx.stride(0), idx.shape[1],
+                                      idx.shape[0], x.shape[1], _lib.ptr(out), _lib.stream_ptr(x.device)))
+    return out
+
+
+def netvlad(feats, scan_off, n_scans, cluster_weights, cluster_weights2, hidden1_weights, bn1, bn2, gating_weights,
+            gating_bn):
+    L = _lib.lib()
+    out = torch.empty((n_scans, 256), dtype=torch.float32, device=feats.device)
+    ws_bytes = L.lcr_netvlad_ws_bytes(feats.shape[0], n_scans)
+    ws = _lib.workspace.get(ws_bytes, feats.device, slot=3)
+    _lib.check(L.lcr_netvlad(_lib.ptr(_f32c(feats)), feats.shape[0], _lib.ptr(scan_off), n_scans,
+                             _lib.ptr(_f32c(cluster_weights)), _lib.ptr(_f32c(cluster_weights2)),
+                             _lib.ptr(_f32c(hidden1_weights)), _lib.ptr(bn1), _lib.ptr(bn2),
+                             _lib.ptr(_f32c(gating_weights)), _lib.ptr(gating_bn), _lib.ptr(out), _lib.ptr(ws),
+                             ws.numel(), _lib.stream_ptr(feats.device)))
+    return out
+
+
+def l2_topk(queries, db, k, valid_counts=None):
+    """Exact squared-L2 top-k (eval_loop_detection_overlap_dataset.py:183-214).  Returns
+    (d2 [nq,k] f32, idx [nq,k] i64), ascending; missing entries (+inf, -1)."""
+    _lib.require_cuda(queries, db)
+    nq = queries.shape[0]
+    d2 = torch.empty((nq, k), dtype=torch.float32, device=queries.device)
+    idx = torch.empty((nq, k), dtype=torch.int64, device=queries.device)
+    if valid_counts is not None:
+        valid_counts = valid_counts.to(device=queries.device, dtype=torch.int32).contiguous()
+    _lib.check(_lib.lib().lcr_l2_topk(_lib.ptr(_f32c(queries)), nq, _lib.ptr(_f32c(db)), db.shape[0],
+                                      queries.shape[1], k, _lib.ptr(valid_counts), _lib.ptr(d2), _lib.ptr(idx),
+                                      _lib.stream_ptr(queries.device)))
+    return d2, idx
