@@ -79,7 +79,7 @@ def test_kpconv_vs_oracle(c_in, c_out):
 def test_unary_groupnorm_vs_oracle(c):
     from lcrnet_b200 import ops
     rng = np.random.default_rng(c)
-    rows = [300, 1, 517]
+    rows = [300, 2, 517]
     x = (rng.standard_normal((sum(rows), 64)) * 2 + 0.5).astype(np.float32)
     w = (rng.standard_normal((c, 64)) * 0.2).astype(np.float32)
     b = rng.standard_normal(c).astype(np.float32)
