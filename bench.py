@@ -1,0 +1,380 @@
+#!/usr/bin/env python
+"""bench.py -- scan-pairs/sec of the LCR-Net descriptor hot path on B200.
+
+Workload (BASELINE.json configs[1], "single-scan encoder+global-descriptor forward, 64k
+synthetic pts"): every step processes a batch of P scan pairs (2P synthetic 65 536-point
+KITTI-shaped scans) through raw points -> 0.3 m voxel pre-pass -> 3-level voxel pyramid ->
+7 radius-neighbour tables -> 11-block KPConv encoder -> NetVLAD descriptor, one descriptor per
+scan, plus the squared-L2 descriptor distance of every pair (the loop-detection score).
+
+  value : pairs/s with the raw scans already resident in HBM (CUDA events, L2 flushed
+          between timed steps, max over ranks).
+  e2e   : the same through the public API from pinned HOST buffers (H2D of the raw scans and
+          D2H of descriptors + distances inside the timed region).
+  roofline / cpu_baseline : see DESIGN.md "Measurement".
+
+Launch: `python bench.py --gpus 1` or
+`python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N` (weak scaling: every
+rank runs its own P pairs, no data-path collective: independent units).
+`--impl reference` times the CPU path (reference C++ operators from oracle/_ref when shipped +
+the torch-CPU oracle port of the model) on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+NUM_STAGES, VOXEL, RADIUS = 4, 0.3, 4.25 * 0.3
+METRIC, UNIT = 'scan_pairs_per_sec_64k_descriptor_path', 'pairs/s'
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--pairs', type=int, default=16, help='scan pairs per step per GPU')
+    ap.add_argument('--cpu-pairs', type=int, default=1, help='pairs in the CPU baseline sample')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--kernel-times', action='store_true', help='also print per-kernel-group event timings')
+    return ap.parse_args()
+
+
+def make_scans(n_pairs, rank=0):
+    from lcrnet_b200 import synth
+    scans = []
+    for i in range(n_pairs):
+        ref, src, _ = synth.make_pair(scene_seed=1000 * rank + i, seed=7351 + i)
+        scans += [ref, src]
+    return scans
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(',')]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax = float(f[2])
+            except ValueError:
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[5:9]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': smax, 'reasons': sorted(reasons),
+                'samples': len(sm)}
+
+
+# ----------------------------------------------------------------------------- CPU path
+def cpu_pair_pipeline(scans, sd, limits, use_ref_ops):
+    """The reference's CPU path on the same scans: collate (C++ operators) + torch-CPU model."""
+    import torch
+    from oracle import model_oracle as mo
+    from oracle import native as on
+    descs = []
+    for s in scans:
+        lens = np.array([len(s)], dtype=np.int64)
+        if use_ref_ops:
+            p0, l0 = on.ref_grid_subsample(s, lens, VOXEL)
+            pts, ls = [p0], [l0]
+            v = VOXEL
+            for _ in range(1, NUM_STAGES):
+                v *= 2
+                p, l = on.ref_grid_subsample(pts[-1], ls[-1], v)
+                pts.append(p)
+                ls.append(l)
+            nb, sub, r = [], [], RADIUS
+            for i in range(NUM_STAGES):
+                nb.append(on.ref_radius_neighbors(pts[i], pts[i], ls[i], ls[i], r, limits[i]))
+                if i < NUM_STAGES - 1:
+                    sub.append(on.ref_radius_neighbors(pts[i + 1], pts[i], ls[i + 1], ls[i], r, limits[i]))
+                r *= 2
+            t = torch.from_numpy
+            data = {'points': [t(x) for x in pts], 'neighbors': [t(x) for x in nb], 'subsampling': [t(x) for x in sub]}
+        else:
+            p0, l0 = on.grid_subsample(s, lens, VOXEL)
+            data = mo.precompute_pyramid(p0, l0, NUM_STAGES, VOXEL, RADIUS, limits)
+        with torch.no_grad():
+            descs.append(mo.global_descriptor(sd, data))
+    d = torch.cat(descs)
+    return d, ((d[0::2] - d[1::2]) ** 2).sum(1)
+
+
+def time_cpu(scans, sd, limits, steps=1, warmup=0):
+    import torch
+    from oracle import native as on
+    on.build()
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    use_ref = on.ref_lib() is not None
+    for _ in range(warmup):
+        cpu_pair_pipeline(scans, sd, limits, use_ref)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_pair_pipeline(scans, sd, limits, use_ref)
+    dt = (time.perf_counter() - t0) / steps
+    n_pairs = len(scans) // 2
+    kind_ops = 'reference C++ operators (oracle/_ref)' if use_ref else 'C oracle operators'
+    return {'value': n_pairs / dt, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+            'sample': '%d pair(s) = %d scans of 65536 pts per step; collate single-threaded (%s), model = torch-CPU '
+                      'oracle port with %d threads; %.2f s per step' % (n_pairs, len(scans), kind_ops, cores, dt)}, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    from lcrnet_b200 import checkpoint
+    sd = checkpoint.random_state_dict('global_descriptor', 7351)
+    scans = make_scans(args.cpu_pairs)
+    limits = calibrated_limits_cpu(scans[:2])
+    base, dt = time_cpu(scans, sd, limits, steps=max(1, args.steps), warmup=min(args.warmup, 1))
+    line = {'impl': 'reference', 'metric': METRIC, 'value': base['value'], 'unit': UNIT, 'n_gpus': args.gpus,
+            'steps': args.steps, 'warmup': min(args.warmup, 1), 'ms_per_step': dt * 1e3, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': workload_config(args.cpu_pairs, limits), 'cpu_baseline': base,
+            'e2e': {'value': base['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(line))
+
+
+def calibrated_limits_cpu(scans):
+    """calibrate_neighbors_stack_mode (data.py:408-433) with the C oracle: 80 % quantile."""
+    from oracle import native as on
+    hist_n = int(np.ceil(4 / 3 * np.pi * (RADIUS / VOXEL + 1) ** 3))
+    hists = np.zeros((NUM_STAGES, hist_n), dtype=np.int64)
+    for s in scans:
+        p, l = on.grid_subsample(s, np.array([len(s)], dtype=np.int64), VOXEL)
+        v, r = VOXEL, RADIUS
+        for i in range(NUM_STAGES):
+            if i > 0:
+                v *= 2
+                p, l = on.grid_subsample(p, l, v)
+            _, counts, _ = on.radius_neighbors(p, p, l, l, r, limit=1, return_counts=True)
+            hists[i] += np.bincount(np.minimum(counts, hist_n - 1), minlength=hist_n)[:hist_n]
+            r *= 2
+        if hists.sum(1).min() > 2000:
+            break
+    cum = np.cumsum(hists.T, axis=0)
+    return [int(x) for x in np.sum(cum < 0.8 * cum[hist_n - 1, :], axis=0)]
+
+
+def workload_config(pairs, limits):
+    return {'workload': 'configs[1]: descriptor path (0.3 m pre-voxel -> pyramid -> radius tables -> KPConv encoder '
+                        '-> NetVLAD) on synthetic 64k-point scans, %d pairs (%d scans) per step per GPU, + pair '
+                        'descriptor distance' % (pairs, 2 * pairs),
+            'pairs_per_step_per_gpu': pairs, 'points_per_scan': 65536, 'neighbor_limits': limits,
+            'weights': 'seeded random (checkpoint.random_state_dict(7351))', 'cache': 'L2 flushed between timed steps'}
+
+
+# ----------------------------------------------------------------------------- GPU path
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from lcrnet_b200 import _lib, checkpoint, model
+    from lcrnet_b200 import data as gdata
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    L = _lib.lib()
+    net = model.create_model(model.default_cfg()).eval()
+    sd = checkpoint.random_state_dict('global_descriptor', 7351)
+    net.load_state_dict(sd, strict=True)
+    net = net.to(dev)
+
+    scans = make_scans(args.pairs, rank)
+    limits = gdata.calibrate_neighbors_stack_mode(scans[:2], NUM_STAGES, VOXEL, RADIUS, device=dev)
+    host_pts = torch.from_numpy(np.concatenate(scans, 0)).pin_memory()
+    host_len = torch.tensor([len(s) for s in scans], dtype=torch.int64).pin_memory()
+    dev_pts, dev_len = host_pts.to(dev), host_len.to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    out_desc = torch.empty((2 * args.pairs, 256), dtype=torch.float32).pin_memory()
+    out_dist = torch.empty(args.pairs, dtype=torch.float32).pin_memory()
+
+    def step(points, lengths):
+        d = gdata.device_collate(points, lengths, NUM_STAGES, VOXEL, RADIUS, limits, pre_voxel=VOXEL, stack_size=1,
+                                 int32=True, upsampling=False)
+        desc = net(d)['anc_global']
+        diff = desc[0::2] - desc[1::2]
+        return desc, (diff * diff).sum(1)
+
+    def step_e2e():
+        p = host_pts.to(dev, non_blocking=True)
+        l = host_len.to(dev, non_blocking=True)
+        desc, dd = step(p, l)
+        out_desc.copy_(desc, non_blocking=True)
+        out_dist.copy_(dd, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        evs = []
+        for _ in range(steps):
+            flush.fill_(1)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            evs.append((a, b))
+        torch.cuda.synchronize()
+        return [a.elapsed_time(b) for a, b in evs]
+
+    for _ in range(max(args.warmup, 3)):
+        step(dev_pts, dev_len)
+        step_e2e()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    n0 = L.lcr_launch_count()
+    barrier()
+    ms = timed(lambda: step(dev_pts, dev_len), args.steps)
+    barrier()
+    launches = (L.lcr_launch_count() - n0) // args.steps
+    ms_e2e = timed(step_e2e, args.steps)
+    barrier()
+    clocks = sampler.stop() if sampler else None
+
+    total, total_e2e = sum(ms), sum(ms_e2e)
+    if world > 1:
+        t = torch.tensor([total, total_e2e], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total, total_e2e = t.tolist()
+    pairs_all = args.pairs * world * args.steps
+    value = pairs_all / (total * 1e-3)
+    e2e_value = pairs_all / (total_e2e * 1e-3)
+
+    # parity spot check of the benchmarked configuration is in tests/; here only sanity
+    desc, dd = step(dev_pts, dev_len)
+    assert torch.isfinite(desc).all() and abs(float(desc.norm(dim=1).mean()) - 1.0) < 1e-4
+
+    roof = dominant_kernel_roofline(step, dev_pts, dev_len, flush) if rank == 0 else None
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+            'warmup': max(args.warmup, 3), 'ms_per_step': total / args.steps, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': workload_config(args.pairs, limits),
+            'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(host_pts.numel() * 4 + host_len.numel() * 8),
+                    'd2h_bytes_per_step': int(out_desc.numel() * 4 + out_dist.numel() * 4),
+                    'ms_per_step': total_e2e / args.steps},
+            'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roof}
+    if world == 1 and not args.no_cpu_baseline:
+        cpu_scans = scans[:2 * args.cpu_pairs]
+        base, _ = time_cpu(cpu_scans, sd, limits)
+        line['cpu_baseline'] = base
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def dominant_kernel_roofline(step, pts, lens, flush):
+    """Roofline entry for the dominant kernel of the step (the fp32 tile GEMM, gemm.cu, which
+    carries the KPConv contraction and the unary layers): algorithmic FLOPs of all its launches in
+    one step / their summed device time, measured live with CUDA events around every launch via
+    the library's own per-kernel timing hook.  See DESIGN.md "Measurement"."""
+    import torch
+    from lcrnet_b200 import _lib
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(REPO, 'MEASURED_PEAKS.json')))
+    except Exception:
+        pass
+    L = _lib.lib()
+    if not hasattr(L, 'lcr_profile_begin'):
+        return None
+    L.lcr_profile_begin()
+    flush.fill_(1)
+    step(pts, lens)
+    torch.cuda.synchronize()
+    import ctypes
+    n = L.lcr_profile_end()
+    rows = []
+    for i in range(n):
+        name = ctypes.create_string_buffer(64)
+        ms, flops, bytes_ = ctypes.c_double(), ctypes.c_double(), ctypes.c_double()
+        L.lcr_profile_get(i, name, 64, ctypes.byref(ms), ctypes.byref(flops), ctypes.byref(bytes_))
+        rows.append((name.value.decode(), ms.value, flops.value, bytes_.value))
+    agg = {}
+    for name, ms, fl, by in rows:
+        a = agg.setdefault(name, [0.0, 0.0, 0.0, 0])
+        a[0] += ms
+        a[1] += fl
+        a[2] += by
+        a[3] += 1
+    if not agg:
+        return None
+    leaf = {k: v for k, v in agg.items() if not k.endswith('_total')}
+    nested = ('radius_query', 'netvlad_hidden')          # already inside a *_total group
+    total_ms = sum(v[0] for k, v in agg.items() if k not in nested)
+    top = max(leaf.items(), key=lambda kv: kv[1][0])
+    name, (ms, fl, by, cnt) = top
+    hbm_peak = peaks.get('hbm_gbs', 6650.0)
+    tens_peak = peaks.get('bf16_tflops', 1590.0)
+    src = 'measured (MEASURED_PEAKS.json)' if peaks else 'fallback (B200_PROFILING.md)'
+    groups = {k: {'ms': round(v[0], 4), 'launches': v[3], 'share': round(v[0] / total_ms, 4),
+                  'gflops': round(v[1] / 1e9, 3), 'mbytes': round(v[2] / 1e6, 3)} for k, v in agg.items()}
+    if fl > 0 and name.startswith('gemm'):
+        ach = fl / (ms * 1e-3) / 1e12
+        return {'kernel': name, 'bound': 'tensor', 'achieved': ach, 'peak': tens_peak, 'unit': 'TFLOP/s',
+                'frac': ach / tens_peak, 'traffic': None, 'peak_source': src,
+                'note': 'fp32 SIMT GEMM (no fp32 MMA on tensor cores); fraction is against the dense bf16 tensor peak',
+                'launches_per_step': cnt, 'ms_per_step': ms, 'share_of_step': ms / total_ms, 'kernel_groups': groups}
+    ach = by / (ms * 1e-3) / 1e9
+    return {'kernel': name, 'bound': 'hbm', 'achieved': ach, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': ach / hbm_peak,
+            'traffic': None, 'peak_source': src, 'launches_per_step': cnt, 'ms_per_step': ms,
+            'share_of_step': ms / total_ms, 'kernel_groups': groups}
+
+
+if __name__ == '__main__':
+    a = parse()
+    if a.impl == 'reference':
+        run_reference(a)
+    else:
+        run_b200(a)

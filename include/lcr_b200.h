@@ -35,6 +35,14 @@ extern "C" {
 
 const char* lcr_last_error(void);
 int lcr_abi_version(void);
+/* number of CUDA kernels this library has launched in this process (for benchmark reports) */
+int64_t lcr_launch_count(void);
+/* Per-kernel-group device timing for benchmark reports: between begin and end every kernel group
+ * is bracketed by CUDA events on its launching stream; get(i) returns its name, elapsed ms and
+ * the algorithmic flops / bytes it was credited with. */
+void lcr_profile_begin(void);
+int lcr_profile_end(void);
+int lcr_profile_get(int i, char* name, int name_cap, double* ms, double* flops, double* bytes);
 
 /* ------------------------------------------------------------------------------------------
  * a1. Voxel-grid subsampling.

@@ -17,6 +17,11 @@ c_i32, c_i64, c_f32, c_sz, c_vp = ctypes.c_int, ctypes.c_int64, ctypes.c_float, 
 SIGNATURES = {
     'lcr_last_error': (ctypes.c_char_p, []),
     'lcr_abi_version': (c_i32, []),
+    'lcr_launch_count': (c_i64, []),
+    'lcr_profile_begin': (None, []),
+    'lcr_profile_end': (c_i32, []),
+    'lcr_profile_get': (c_i32, [c_i32, ctypes.c_char_p, c_i32, ctypes.POINTER(ctypes.c_double),
+                                ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]),
     'lcr_grid_subsample_ws_bytes': (c_sz, [c_i64, c_i32]),
     'lcr_grid_subsample': (c_i32, [c_vp, c_i64, c_vp, c_i32, c_f32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
     'lcr_radius_neighbors_ws_bytes': (c_sz, [c_i64, c_i64, c_i32]),

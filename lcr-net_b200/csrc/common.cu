@@ -12,6 +12,75 @@ void lcr_set_error(const char* msg, const char* file, int line) {
 extern "C" const char* lcr_last_error(void) { return g_err; }
 extern "C" int lcr_abi_version(void) { return 1; }
 
+#include <atomic>
+static std::atomic<long long> g_launches{0};
+void lcr_count_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+extern "C" int64_t lcr_launch_count(void) { return (int64_t)g_launches.load(std::memory_order_relaxed); }
+
+// ------------------------------------------------------------------ per-kernel-group profiling
+#include <mutex>
+#include <vector>
+namespace {
+struct ProfRec {
+  const char* name;
+  cudaEvent_t a, b;
+  double flops, bytes;
+};
+bool g_prof_on = false;
+std::vector<ProfRec> g_prof;
+std::vector<float> g_prof_ms;
+std::mutex g_prof_mu;
+}  // namespace
+
+LcrProfScope::LcrProfScope(const char* name, double flops, double bytes, cudaStream_t s) : slot(-1), stream(s) {
+  if (!g_prof_on) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  ProfRec r;
+  r.name = name;
+  r.flops = flops;
+  r.bytes = bytes;
+  if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
+  cudaEventRecord(r.a, s);
+  g_prof.push_back(r);
+  slot = (int)g_prof.size() - 1;
+}
+LcrProfScope::~LcrProfScope() {
+  if (slot < 0) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  cudaEventRecord(g_prof[slot].b, stream);
+}
+
+extern "C" void lcr_profile_begin(void) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (auto& r : g_prof) {
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  g_prof.clear();
+  g_prof_ms.clear();
+  g_prof_on = true;
+}
+// Stops recording, waits for the recorded work and returns the number of records.
+extern "C" int lcr_profile_end(void) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof_on = false;
+  g_prof_ms.assign(g_prof.size(), 0.f);
+  for (size_t i = 0; i < g_prof.size(); i++) {
+    cudaEventSynchronize(g_prof[i].b);
+    cudaEventElapsedTime(&g_prof_ms[i], g_prof[i].a, g_prof[i].b);
+  }
+  return (int)g_prof.size();
+}
+extern "C" int lcr_profile_get(int i, char* name, int name_cap, double* ms, double* flops, double* bytes) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (i < 0 || i >= (int)g_prof.size() || name_cap < 1) return LCR_ERR_INVALID;
+  snprintf(name, (size_t)name_cap, "%s", g_prof[i].name);
+  *ms = (double)g_prof_ms[i];
+  *flops = g_prof[i].flops;
+  *bytes = g_prof[i].bytes;
+  return LCR_OK;
+}
+
 // ------------------------------------------------------------------ scan
 // Layout: up to 1024 blocks, each block owns a contiguous chunk of `chunk` elements
 // (chunk is a multiple of the block size); phase 1 reduces chunks, phase 2 scans the <=1024
@@ -105,6 +174,7 @@ int scan_impl(const T* in, T* out, int64_t n, T* total_out, T* partials, cudaStr
   scan_reduce_kernel<T><<<nblocks, kScanThreads, 0, stream>>>(in, n, chunk, partials);
   scan_partials_kernel<T><<<1, kScanThreads, 0, stream>>>(partials, nblocks, total_out);
   scan_down_kernel<T><<<nblocks, kScanThreads, 0, stream>>>(in, out, n, chunk, partials);
+  LCR_LAUNCHED(3);
   LCR_CUDA_CHECK_LAUNCH();
   return LCR_OK;
 }
@@ -193,10 +263,12 @@ __global__ void bbox_kernel(const float* __restrict__ pts, int64_t n, const int6
 
 void lcr_offsets_launch(const int64_t* lengths, int batch, int64_t* off, cudaStream_t stream) {
   offsets_kernel<<<1, 32, 0, stream>>>(lengths, batch, off);
+  LCR_LAUNCHED(1);
 }
 
 void lcr_bbox_launch(const float* pts, int64_t n, const int64_t* off, int batch, unsigned* bbox, cudaStream_t stream) {
   const int T = 256;
   bbox_init_kernel<<<(batch * 6 + T - 1) / T, T, 0, stream>>>(bbox, batch);
   if (n > 0) bbox_kernel<<<(unsigned)((n + T - 1) / T), T, 0, stream>>>(pts, n, off, batch, bbox);
+  LCR_LAUNCHED(n > 0 ? 2 : 1);
 }

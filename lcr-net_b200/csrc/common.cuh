@@ -35,6 +35,19 @@
   } while (0)
 
 void lcr_set_error(const char* msg, const char* file, int line);
+// Kernel-launch accounting (bench.py reports it as "gpu_launches").
+void lcr_count_launches(int n);
+#define LCR_LAUNCHED(n) lcr_count_launches(n)
+
+// Optional per-kernel-group timing (lcr_profile_begin/end/get in the C ABI): when enabled, a
+// scope records CUDA events on the launching stream around the launches it brackets, together
+// with the group's ALGORITHMIC flops and bytes (the compulsory work).
+struct LcrProfScope {
+  int slot;
+  cudaStream_t stream;
+  LcrProfScope(const char* name, double flops, double bytes, cudaStream_t s);
+  ~LcrProfScope();
+};
 
 static inline size_t lcr_align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 

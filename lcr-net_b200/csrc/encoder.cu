@@ -327,8 +327,10 @@ extern "C" int lcr_kpconv(const float* s_feats, const uint8_t* s_flags, int64_t 
   const int M = (int)m_query, N = (int)n_support;
   const unsigned grid = (unsigned)((M + 3) / 4);
   if (c_in == 1) {
+    LcrProfScope prof("kpconv_c1", 2.0 * M * KP * (H + c_out), 4.0 * M * H + 16.0 * (M + N) + 4.0 * M * c_out, stream);
     kpconv_c1_kernel<<<grid, 128, 0, stream>>>(s_feats, q_points, s_points, idx, ld_idx, H, kernel_points, sigma,
                                                weights, bias, c_out, M, N, out);
+    LCR_LAUNCHED(1);
     LCR_CUDA_CHECK_LAUNCH();
     return LCR_OK;
   }
@@ -336,6 +338,9 @@ extern "C" int lcr_kpconv(const float* s_feats, const uint8_t* s_flags, int64_t 
   LcrArena a(ws, ws_bytes);
   float* wf = a.take<float>((size_t)M * KP * c_in);
   float* rowscale = a.take<float>(M);
+  {
+  LcrProfScope prof("kpconv_gather", 2.0 * M * KP * (double)H * c_in,
+                    4.0 * M * H + 4.0 * (double)N * c_in + 12.0 * (M + N) + 4.0 * (double)M * KP * c_in, stream);
 #define LCR_GATHER(CPL)                                                                                        \
   kpconv_gather_kernel<CPL><<<grid, 128, 0, stream>>>(s_feats, q_points, s_points, idx, ld_idx, H, kernel_points, \
                                                       sigma, s_flags, M, N, wf, rowscale)
@@ -346,6 +351,8 @@ extern "C" int lcr_kpconv(const float* s_feats, const uint8_t* s_flags, int64_t 
     default: LCR_GATHER(8); break;
   }
 #undef LCR_GATHER
+  }
+  LCR_LAUNCHED(1);
   LCR_CUDA_CHECK_LAUNCH();
   return lcr_gemm_f32(wf, KP * c_in, weights, c_out, out, c_out, M, c_out, KP * c_in, rowscale, bias, stream);
 }
@@ -367,11 +374,13 @@ extern "C" int lcr_group_norm_stats(const float* x, int64_t rows, int channels, 
   if (rows == 0) return LCR_OK;
   const int n_chunks = (int)((max_stack_rows + kGnRows - 1) / kGnRows) + 1;
   double2* partial = (double2*)ws;
+  LcrProfScope prof("group_norm_stats", 3.0 * rows * channels, 4.0 * rows * channels, stream);
   dim3 grid(n_chunks, n_stacks);
   gn_partial_kernel<<<grid, 256, 0, stream>>>(x, channels, groups, stack_off, n_chunks, partial);
   const int warps = n_stacks * groups;
   gn_finalize_kernel<<<(warps * 32 + 255) / 256, 256, 0, stream>>>(partial, groups, channels, stack_off, n_chunks,
                                                                    n_stacks, eps, (float2*)stats_out);
+  LCR_LAUNCHED(2);
   LCR_CUDA_CHECK_LAUNCH();
   return LCR_OK;
 }
@@ -391,7 +400,9 @@ extern "C" int lcr_group_norm_apply(const float* x, const float* stats, const fl
   const int lpr = channels / 4 < 32 ? channels / 4 : 32;
   const int rpw = 32 / lpr;
   const int64_t warps = (rows + rpw - 1) / rpw;
+  LcrProfScope prof("group_norm_apply", 6.0 * rows * channels, 4.0 * rows * channels * (x2 ? 3.0 : 2.0), stream);
   gn_apply_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, stream>>>(a);
+  LCR_LAUNCHED(1);
   LCR_CUDA_CHECK_LAUNCH();
   return LCR_OK;
 }
@@ -401,8 +412,11 @@ extern "C" int lcr_maxpool(const float* x, int64_t n_support, const int32_t* idx
   cudaStream_t stream = (cudaStream_t)stream_;
   LCR_REQUIRE(channels % 4 == 0 && H >= 1 && ld_idx >= H, "maxpool: bad shape");
   if (m_query == 0) return LCR_OK;
+  LcrProfScope prof("maxpool", (double)m_query * H * channels,
+                    4.0 * m_query * H + 4.0 * (double)n_support * channels + 4.0 * (double)m_query * channels, stream);
   maxpool_kernel<<<(unsigned)((m_query * 32 + 255) / 256), 256, 0, stream>>>(x, idx, ld_idx, H, (int)m_query,
                                                                             (int)n_support, channels, out);
+  LCR_LAUNCHED(1);
   LCR_CUDA_CHECK_LAUNCH();
   return LCR_OK;
 }
@@ -411,6 +425,7 @@ extern "C" int lcr_row_flags(const float* x, int64_t rows, int channels, uint8_t
   cudaStream_t stream = (cudaStream_t)stream_;
   if (rows == 0) return LCR_OK;
   rowflag_kernel<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, stream>>>(x, rows, channels, flags);
+  LCR_LAUNCHED(1);
   LCR_CUDA_CHECK_LAUNCH();
   return LCR_OK;
 }

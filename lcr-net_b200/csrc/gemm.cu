@@ -148,6 +148,7 @@ int lcr_gemm_f32(const float* A, int lda, const float* B, int ldb, float* C, int
   LCR_REQUIRE((((uintptr_t)A | (uintptr_t)B | (uintptr_t)C | (uintptr_t)bias) & 15) == 0,
               "gemm: pointers must be 16-byte aligned");
   if (M == 0) return LCR_OK;
+  LcrProfScope prof("gemm_f32", 2.0 * M * N * K, 4.0 * ((double)M * K + (double)K * N + (double)M * N), stream);
   // tile choice: keep >= ~1 wave of CTAs on 148 SMs when the problem allows it
   const long ctas_128 = (long)((M + 127) / 128) * ((N + 127) / 128);
   if (N <= 32) {
@@ -160,6 +161,7 @@ int lcr_gemm_f32(const float* A, int lda, const float* B, int ldb, float* C, int
   } else {
     launch<128, 128, 8, 8>(A, lda, B, ldb, C, ldc, M, N, K, rowscale, bias, stream);
   }
+  LCR_LAUNCHED(1);
   LCR_CUDA_CHECK_LAUNCH();
   return LCR_OK;
 }

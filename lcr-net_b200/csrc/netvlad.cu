@@ -225,6 +225,7 @@ extern "C" int lcr_netvlad(const float* feats, int64_t rows, const int64_t* scan
   const BnParams p1{bn1, bn1 + KC, bn1 + 2 * KC, bn1 + 3 * KC};
   const BnParams p2{bn2, bn2 + OD, bn2 + 2 * OD, bn2 + 3 * OD};
   const BnParams pg{gating_bn, gating_bn + OD, gating_bn + 2 * OD, gating_bn + 3 * OD};
+  LcrProfScope prof_all("netvlad_total", 0.0, 0.0, stream);
   if (rows > 0) {
     const unsigned gw = (unsigned)((rows * 32 + 255) / 256);
     row_normalize_kernel<<<gw, 256, 0, stream>>>(feats, rows, xn);
@@ -234,9 +235,14 @@ extern "C" int lcr_netvlad(const float* feats, int64_t rows, const int64_t* scan
   }
   vlad_kernel<<<dim3(F / 64, n_scans), 256, 0, stream>>>(xn, act, scan_off, cluster_weights2, vlad);
   vlad_normalize_kernel<<<n_scans, 256, 0, stream>>>(vlad);
+  {
+  LcrProfScope prof("netvlad_hidden", 2.0 * n_scans * (double)F * KC * OD,
+                    4.0 * (double)F * KC * OD * ((n_scans + HS - 1) / HS) + 4.0 * (double)n_scans * F * KC, stream);
   hidden_partial_kernel<<<dim3(n_chunks, (n_scans + HS - 1) / HS), OD, 0, stream>>>(vlad, hidden1_weights, n_scans,
                                                                                    partial);
+  }
   head_tail_kernel<<<n_scans, OD, 0, stream>>>(partial, n_chunks, p2, gating_weights, pg, out);
+  LCR_LAUNCHED(4 + (rows > 0 ? 2 : 0));  // + the GEMM, which counts itself
   LCR_CUDA_CHECK_LAUNCH();
   return LCR_OK;
 }

@@ -348,6 +348,8 @@ extern "C" int lcr_radius_neighbors(const float* q_points, int64_t nq_total, con
   const float cell = radius * 1.001f;
   const float inv_cell = 1.0f / cell;
   const float r2 = radius * radius;  // radius_neighbors_cpu.cpp:12 (fp32 product)
+  const double idx_bytes = out_idx ? (idx_is64 ? 8.0 : 4.0) * (double)nq_total * width : 0.0;
+  LcrProfScope prof_all("radius_total", 0.0, 12.0 * (nq_total + ns_total) + idx_bytes, stream);
   lcr_offsets_launch(q_lengths, batch, w.q_off, stream);
   lcr_offsets_launch(s_lengths, batch, w.s_off, stream);
   lcr_bbox_launch(s_points, ns_total, w.s_off, batch, w.bbox, stream);
@@ -365,6 +367,7 @@ extern "C" int lcr_radius_neighbors(const float* q_points, int64_t nq_total, con
     if (rc != LCR_OK) return rc;
     cell_scatter_kernel<<<gridS, T, 0, stream>>>(s_points, ns_total, w.slot_of, w.tstart, w.tcursor, w.sorted);
   }
+  LcrProfScope prof("radius_query", 0.0, 12.0 * (nq_total + ns_total) + idx_bytes, stream);
   const unsigned gridQ = (unsigned)((nq_total + kWarpsPerCta - 1) / kWarpsPerCta);
   const size_t spill_smem = sizeof(unsigned long long) * kSpillCap;
   if (idx_is64) {
@@ -398,6 +401,7 @@ extern "C" int lcr_radius_neighbors(const float* q_points, int64_t nq_total, con
           ns_total, (int32_t*)out_idx, w.spill_list, w.spill_n, err);
     }
   }
+  LCR_LAUNCHED(2 + (ns_total > 0 ? 2 : 0) + (out_idx ? 1 : 0));  // geom, query, insert, scatter, spill
   LCR_CUDA_CHECK_LAUNCH();
   return LCR_OK;
 }

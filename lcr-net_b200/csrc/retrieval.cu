@@ -151,8 +151,11 @@ extern "C" int lcr_l2_topk(const float* queries, int64_t n_queries, const float*
   LCR_REQUIRE(k >= 1 && k <= KMAX, "l2_topk: k must be in [1, 64]");
   LCR_REQUIRE(n_queries >= 0 && n_db >= 0 && n_queries < (1ll << 31) && n_db < (1ll << 31), "l2_topk: sizes");
   if (n_queries == 0) return LCR_OK;
+  LcrProfScope prof("l2_topk", 3.0 * n_queries * (double)n_db * D, 4.0 * D * (double)(n_queries + n_db) + 12.0 * n_queries * k,
+                    stream);
   l2_topk_kernel<<<(unsigned)((n_queries + QT - 1) / QT), 256, 0, stream>>>(queries, (int)n_queries, db, (int)n_db,
                                                                           valid_counts, k, out_d2, out_idx);
+  LCR_LAUNCHED(1);
   LCR_CUDA_CHECK_LAUNCH();
   return LCR_OK;
 }

@@ -368,6 +368,7 @@ extern "C" int lcr_grid_subsample(const float* points, int64_t n_total, const in
     lcr_set_error("grid_subsample: workspace too small", __FILE__, __LINE__);
     return LCR_ERR_WORKSPACE;
   }
+  LcrProfScope prof("grid_subsample", 0.0, 24.0 * n_total + 8.0 * batch, stream);
   const int T = 256;
   const unsigned gridN = (unsigned)((n_total + T - 1) / T);
   lcr_offsets_launch(lengths, batch, w.off, stream);
@@ -393,6 +394,7 @@ extern "C" int lcr_grid_subsample(const float* points, int64_t n_total, const in
   }
   centroid_kernel<<<gridN, T, 0, stream>>>(points, w.scan_total, w.members, w.vstart, w.vcnt, w.vbase, batch,
                                            order_mode == 1 ? w.pos : nullptr, out_points);
+  LCR_LAUNCHED(order_mode == 1 ? 7 : 6);
   LCR_CUDA_CHECK_LAUNCH();
   return LCR_OK;
 }
