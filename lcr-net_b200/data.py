@@ -79,7 +79,7 @@ def device_collate(points, lengths, num_stages, voxel_size, search_radius, neigh
 
 
 def calibrate_neighbors_stack_mode(scans, num_stages, voxel_size, search_radius, keep_ratio=0.8,
-                                   sample_threshold=2000, device='cuda'):
+                                   sample_threshold=2000, pre_voxel=None, device='cuda'):
     """data.py:408-433: histogram of neighbourhood sizes per level (table limit 'hist_n' = the
     number of points in a ball of the search radius at unit voxel density), keep the
     ``keep_ratio`` quantile.  Runs the counting pass of the radius kernel only."""
@@ -87,8 +87,8 @@ def calibrate_neighbors_stack_mode(scans, num_stages, voxel_size, search_radius,
     hists = np.zeros((num_stages, hist_n), dtype=np.int64)
     max_limits = [hist_n] * num_stages
     for scan in scans:
-        d = scans_collate_fn_stack_mode([scan], num_stages, voxel_size, search_radius, max_limits, int32=True,
-                                        upsampling=False, device=device)
+        d = scans_collate_fn_stack_mode([scan], num_stages, voxel_size, search_radius, max_limits,
+                                        pre_voxel=pre_voxel, int32=True, upsampling=False, device=device)
         counts = [(nb < nb.shape[0]).sum(1).cpu().numpy() for nb in d['neighbors']]
         hists += np.stack([np.bincount(c, minlength=hist_n)[:hist_n] for c in counts])
         if np.min(np.sum(hists, axis=1)) > sample_threshold:
