@@ -73,9 +73,65 @@ def netvlad_spec(prefix='netvlad.', feature=1024, clusters=64, out=256):
             + [(prefix + 'context_gating.gating_weights', (out, out))] + _bn_spec(prefix + 'context_gating.bn1.', out))
 
 
+def _res_spec(p, cin, cout):
+    mid = cout // 4
+    spec = []
+    if cin != mid:
+        spec += _unary_spec(p + 'unary1.', cin, mid)
+    spec += _kpconv_spec(p + 'KPConv.', mid, mid)
+    spec += [(p + 'norm_conv.norm.weight', (mid,)), (p + 'norm_conv.norm.bias', (mid,))]
+    spec += _unary_spec(p + 'unary2.', mid, cout)
+    if cin != cout:
+        spec += _unary_spec(p + 'unary_shortcut.', cin, cout)
+    return spec
+
+
+def _linear_spec(p, cin, cout):
+    return [(p + 'weight', (cout, cin)), (p + 'bias', (cout,))]
+
+
+def _ln_spec(p, c):
+    return [(p + 'weight', (c,)), (p + 'bias', (c,))]
+
+
+def vote_encoder_spec(prefix='vote_encoder.', d=INIT_DIM):
+    """backbone4.py:92-119 + modules/vote/vote.py:112-147 (input_feats_dim 256, MLP 512/256)."""
+    v = prefix + 'vote.'
+    spec = (_linear_spec(v + 'mlp_modules.0.', 256, 512) + _ln_spec(v + 'mlp_modules.1.', 512)
+            + _linear_spec(v + 'mlp_modules.3.', 512, 256) + _ln_spec(v + 'mlp_modules.4.', 256)
+            + _linear_spec(v + 'ctr_reg.', 256, 3))
+    spec += _res_spec(prefix + 'encoder6_1.', 4 * d, 4 * d)
+    spec += _res_spec(prefix + 'encoder6_2.', 4 * d, 8 * d)
+    spec += _res_spec(prefix + 'encoder6_3.', 8 * d, 8 * d)
+    return spec
+
+
+def transformer_spec(prefix='transformer.', d_in=1024, d=128, d_out=256, layers=8):
+    """thdroformer_linear.py:12-48, rpetransformer.py:57-220, vanilla_transformer.py:13-144."""
+    spec = (_linear_spec(prefix + 'embedding.encoder.', 3, d) + _linear_spec(prefix + 'embedding.encoder2.', d, d // 2)
+            + _linear_spec(prefix + 'in_proj.', d_in, d))
+    for i in range(layers):
+        p = prefix + 'transformer.layers.%d.' % i
+        for n in ('proj_q.', 'proj_k.', 'proj_v.'):
+            spec += _linear_spec(p + 'attention.attention.' + n, d, d)
+        spec += _linear_spec(p + 'attention.linear.', d, d) + _ln_spec(p + 'attention.norm.', d)
+        spec += (_linear_spec(p + 'output.expand.', d, 2 * d) + _linear_spec(p + 'output.squeeze.', 2 * d, d)
+                 + _ln_spec(p + 'output.norm.', d))
+    return spec + _linear_spec(prefix + 'out_proj.', d, d_out)
+
+
+def kpdecoder_spec(prefix='kpdecoder.', d=INIT_DIM):
+    return (_unary_spec(prefix + 'decoder3.', 12 * d, 8 * d) + _unary_spec(prefix + 'decoder2.', 12 * d, 4 * d)
+            + _linear_spec(prefix + 'decoder1.mlp.', 6 * d, 2 * d))
+
+
 def state_dict_spec(kind='global_descriptor'):
     if kind == 'global_descriptor':
         return encoder_spec() + netvlad_spec()
+    if kind == 'lcrnet':  # model_family/LCRNet.py:25-112 (373 tensors, 25 093 190 parameters)
+        return (encoder_spec() + vote_encoder_spec() + _linear_spec('proj_node_overlap_score.', 512, 1)
+                + transformer_spec() + kpdecoder_spec()
+                + [('node_optimal_transport.alpha', ()), ('optimal_transport.alpha', ())] + netvlad_spec())
     raise ValueError(kind)
 
 
@@ -97,6 +153,8 @@ def random_state_dict(kind='global_descriptor', seed=7351):
     radius = {}
     for name, _, _, _, stage, _ in encoder_blocks():
         radius['encoder.' + name + '.KPConv.kernel_points'] = INIT_RADIUS * 2 ** stage
+    for name, stage in (('encoder6_1', 3), ('encoder6_2', 4), ('encoder6_3', 4)):
+        radius['vote_encoder.' + name + '.KPConv.kernel_points'] = INIT_RADIUS * 2 ** stage
     sd = OrderedDict()
     for name, shape in state_dict_spec(kind):
         leaf = name.rsplit('.', 1)[-1]
@@ -110,6 +168,12 @@ def random_state_dict(kind='global_descriptor', seed=7351):
             t = torch.from_numpy((0.1 * rng.standard_normal(shape)).astype(np.float32))
         elif name.endswith('norm.weight') or (leaf == 'weight' and len(shape) == 1):
             t = torch.from_numpy((1.0 + 0.1 * rng.standard_normal(shape)).astype(np.float32))
+        elif leaf == 'alpha':
+            t = torch.tensor(1.0 + 0.25 * rng.standard_normal(), dtype=torch.float32)
+        elif name.startswith('transformer.embedding.'):
+            # angles theta = A p + b must stay O(1) over a +-80 m scene
+            scale = {'encoder.weight': 0.05, 'encoder.bias': 0.1, 'encoder2.weight': 0.06, 'encoder2.bias': 0.1}
+            t = torch.from_numpy((scale[name.split('embedding.')[1]] * rng.standard_normal(shape)).astype(np.float32))
         elif leaf == 'bias':
             t = torch.from_numpy((0.05 * rng.standard_normal(shape)).astype(np.float32))
         elif leaf == 'weights':  # KPConv [K, Cin, Cout]

@@ -1,0 +1,131 @@
+"""CPU: the registration-path oracle (oracle/pair_oracle.py) against the fixture generated from the
+UNMODIFIED reference ``LCRNet`` and, when /root/reference is present, against the reference live
+(stage by stage)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from lcrnet_b200 import checkpoint
+from oracle import model_oracle as mo
+from oracle import native
+from oracle import pair_oracle as po
+from util import GOLDEN, REF_PRESENT
+
+sys.path.insert(0, GOLDEN)
+G = np.load(os.path.join(GOLDEN, 'pair_golden.npz'))
+LIMITS = [int(x) for x in G['limits']]
+
+
+def _pair_data():
+    from make_pair_golden import make_pair_data
+    raw_ref, raw_src, _ = make_pair_data(*(int(x) for x in G['case']))
+    pts = np.concatenate([raw_ref, raw_src], 0)
+    p0, l0 = native.grid_subsample(pts, np.array([len(raw_ref), len(raw_src)], dtype=np.int64), 0.3)
+    return raw_ref, raw_src, mo.precompute_pyramid(p0, l0, limits=LIMITS)
+
+
+@pytest.fixture(scope='module')
+def run():
+    sd = checkpoint.random_state_dict('lcrnet', int(G['weight_seed']))
+    raw_ref, raw_src, data = _pair_data()
+    with torch.no_grad():
+        out = po.lcrnet_forward(sd, data, LIMITS, stages=True)
+    return sd, raw_ref, raw_src, data, out
+
+
+def test_layout_lcrnet():
+    spec = checkpoint.state_dict_spec('lcrnet')
+    assert len(spec) == 373
+    skip = ('num_batches_tracked', 'kernel_points', 'running_mean', 'running_var')
+    assert sum(int(np.prod(s)) for n, s in spec if not n.endswith(skip)) == 25093190
+
+
+def test_oracle_matches_reference_fixture(run):
+    sd, _, _, data, out = run
+    assert np.array_equal(torch.stack(data['lengths']).numpy(), G['lengths'])
+    st = out['_stages']
+    n_c0 = int(G['lengths'][-1][0])
+    assert np.abs(st['enhanced'][:8].numpy() - G['enhanced_pos_head']).max() < 2e-4
+    assert np.abs(st['enhanced'][n_c0:n_c0 + 8].numpy() - G['enhanced_anc_head']).max() < 2e-4
+    assert list(out['length']) == list(G['node_counts'])
+    assert np.abs(out['pos_points_c'].numpy() - G['pos_points_c']).max() < 1e-3
+    assert np.abs(out['anc_points_c'].numpy() - G['anc_points_c']).max() < 1e-3
+    assert np.abs(st['feats_f'][:8].numpy() - G['feats_f_head']).max() < 5e-4
+    for k in ('pos_feature_global', 'anc_feature_global'):
+        assert np.linalg.norm(out[k].numpy() - G[k]) < 1e-4
+    assert np.abs(st['node_ot'].diagonal().numpy() - G['node_ot_diag']).max() < 5e-3
+    # discrete stages: identical node correspondences and correspondence count
+    assert np.array_equal(out['pos_node_corr_indices'].numpy(), G['pos_node_corr_indices'])
+    assert np.array_equal(out['anc_node_corr_indices'].numpy(), G['anc_node_corr_indices'])
+    assert out['corr_scores'].shape[0] == int(G['n_corr'])
+    T, Tref = out['estimated_transform'].numpy(), G['estimated_transform']
+    assert np.abs(T - Tref).max() < 1e-3 * max(1.0, np.abs(Tref).max())
+
+
+@pytest.mark.skipif(not REF_PRESENT, reason='reference tree not present')
+def test_oracle_matches_reference_live(run):
+    from make_pair_golden import reference_pair_forward
+    sd, raw_ref, raw_src, data, out = run
+    rdata, rout, taps = reference_pair_forward(raw_ref, raw_src, sd, LIMITS)
+    for a, b in zip(data['points'], rdata['points']):
+        assert torch.equal(a, b)
+    # neighbour tables: identical up to the order inside exact-distance tie classes (the reference's
+    # std::sort is unstable; the oracle orders ties by ascending index)
+    from util import canonical_rows
+    P = [p.numpy() for p in data['points']]
+    for k, qs in (('neighbors', [(i, i) for i in range(4)]), ('subsampling', [(i + 1, i) for i in range(3)]),
+                  ('upsampling', [(i, i + 1) for i in range(3)])):
+        for (qi, si), a, b in zip(qs, data[k], rdata[k]):
+            a, b = a.numpy(), b.numpy()
+            assert a.shape == b.shape
+            db = native.neighbor_d2(P[qi], P[si], b)
+            assert np.array_equal(native.neighbor_d2(P[qi], P[si], a), db), k
+            assert np.array_equal(canonical_rows(b, db)[0], a), k
+    st = out['_stages']
+    n_c0 = int(rdata['lengths'][-1][0])
+    enh = torch.cat([taps['transformer'][0][0], taps['transformer'][1][0]], 0)
+    assert float((st['enhanced'] - enh).abs().max()) < 2e-4
+    assert float((st['vote']['shifted'][:n_c0] - rout['shifted_pos_points_c']).abs().max()) < 1e-4
+    assert float((out['pos_feats_c'] - rout['pos_feats_c']).abs().max()) < 1e-3
+    assert float((st['feats_f'] - taps['kpdecoder'][0]).abs().max()) < 1e-3
+    assert torch.equal(st['pos_knn'].sort(1)[0], rout['pos_node_knn_indices'][0].sort(1)[0])
+    assert float((st['node_ot'] - taps['node_ot'][0]).abs().max()) < 1e-2
+    # per-patch point lists agree as sets; torch.topk orders near-equal distances differently in a
+    # few patches (SURVEY trap 5), which permutes rows/cols of those patches' OT matrices: compare
+    # the patches whose order is identical
+    same = ((st['pos_knn'] == rout['pos_node_knn_indices'][0]).all(1)[out['pos_node_corr_indices']]
+            & (st['anc_knn'] == rout['anc_node_knn_indices'][0]).all(1)[out['anc_node_corr_indices']])
+    assert float(same.float().mean()) > 0.8
+    valid = taps['point_ot'][same] > -1e11
+    assert float(((st['point_ot'][same] - taps['point_ot'][same]).abs() * valid).max()) < 1e-2
+    assert torch.equal(out['pos_node_corr_indices'], rout['pos_node_corr_indices'])
+    assert float((out['pos_corr_points'] - rout['pos_corr_points']).abs().max()) == 0.0
+    assert float((out['estimated_transform'] - rout['estimated_transform']).abs().max()) < 1e-3
+
+
+def test_sinkhorn_properties():
+    """Sinkhorn output rows/cols are log-marginals (size-independent property)."""
+    rng = torch.Generator().manual_seed(0)
+    s = torch.randn(3, 20, 17, generator=rng)
+    rm, cm = torch.ones(3, 20, dtype=torch.bool), torch.ones(3, 17, dtype=torch.bool)
+    rm[1, 5:9] = False
+    cm[2, :3] = False
+    out = po.sinkhorn(s, rm, cm, torch.tensor(1.0))
+    p = torch.exp(out)
+    assert np.allclose(p[0, :20].sum(1).numpy(), 1.0, atol=1e-3)        # valid rows carry unit mass
+    assert np.allclose(p[0, :, :17].sum(0).numpy(), 1.0, atol=1e-3)
+    assert float(p[1, 5:9, :17].abs().max()) < 1e-6                      # masked rows carry nothing
+
+
+def test_procrustes_recovers_rigid_motion():
+    rng = np.random.default_rng(0)
+    src = torch.from_numpy(rng.standard_normal((50, 3)).astype(np.float32))
+    a = 0.7
+    R = torch.tensor([[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1]], dtype=torch.float32)
+    t = torch.tensor([1.0, -2.0, 0.5])
+    ref = src @ R.t() + t
+    T = po.weighted_procrustes(src, ref, torch.ones(50))
+    assert float((T[:3, :3] - R).abs().max()) < 1e-4 and float((T[:3, 3] - t).abs().max()) < 1e-3
