@@ -148,6 +148,102 @@ int lcr_netvlad(const float* feats, int64_t rows, const int64_t* scan_off, int n
 int lcr_l2_topk(const float* queries, int64_t n_queries, const float* db, int64_t n_db, int dim, int k,
                 const int32_t* valid_counts, float* out_d2, int64_t* out_idx, void* stream);
 
+/* out = act(rowscale[m] * (x . weight_t) + bias): lcr_linear with leading dimensions, an optional
+ * per-row scale and act in {0: none, 1: ReLU} (FFN of vanilla_transformer.py:22-28, vote MLP). */
+int lcr_linear_ex(const float* x, int64_t n_rows, int c_in, int ld_x, const float* weight_t, int c_out,
+                  const float* bias, const float* rowscale, int act, float* out, int ld_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a7. 3D-RoFormer pieces (experiments/lcrnet/modules/thdroformer/*).
+ * lcr_layer_norm: y = act(LayerNorm(x + residual) * gamma + beta), residual optional, relu flag
+ *   (post-LN residual of rpetransformer.py:139-142 / vanilla_transformer.py:22-28,98-101; LN+ReLU of
+ *   modules/vote/vote.py:124-128).
+ * lcr_rope: in-place rotary embedding of the first 128 columns (4 heads x 32) of x with per-point
+ *   angles theta[rows, 64] (RotaryPositionalEmbedding, rpetransformer.py:41-54).
+ * lcr_attention: out = softmax(q k^T / sqrt(32)) v per head, batched over problems given by row
+ *   offsets (problem p: queries q_off[p]..q_off[p+1], keys/values k_off[p]..k_off[p+1])
+ *   (dynamic_attention with k=None, rpetransformer.py:19-24; MultiHeadAttention,
+ *   vanilla_transformer.py:58-72).  q/k/v/out hold heads*32 columns at their leading dimensions.
+ * ---------------------------------------------------------------------------------------- */
+int lcr_layer_norm(const float* x, const float* residual, const float* gamma, const float* beta, int64_t rows,
+                   int channels, float eps, int relu, float* y, void* stream);
+int lcr_rope(float* x, int ld, const float* theta, int64_t rows, void* stream);
+int lcr_attention(const float* q, int ld_q, const float* k, int ld_k, const float* v, int ld_v,
+                  const int64_t* q_off, const int64_t* k_off, int n_problems, int64_t max_q_rows, int heads,
+                  int head_dim, float* out, int ld_out, double flops_hint, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a9. Vote layer tail, greedy NMS, node centres (modules/vote/vote.py:13-70,166-172;
+ * backbone4.py:140-176).
+ * lcr_vote_shift: out = points + offsets[:, :3] * min(1, max_range / |offset|).
+ * lcr_nms_greedy: per cloud, sequential greedy suppression: point i is kept iff its
+ *   nn.PairwiseDistance (eps 1e-6) to ALL previously kept points is > radius; the first point is
+ *   always kept.  keep[n] (u8), counts[n_clouds], kept_idx: per cloud, the kept point indices
+ *   compacted at the cloud's row offset.
+ * lcr_neighbor_mean: out[m] = mean of points[idx[m, h]] over valid entries (idx < n_points).
+ * ---------------------------------------------------------------------------------------- */
+int lcr_vote_shift(const float* points, const float* offsets, int ld_offsets, float max_range, int64_t n, float* out,
+                   void* stream);
+int lcr_nms_greedy(const float* points, const int64_t* cloud_off, int n_clouds, int64_t max_cloud_rows, float radius,
+                   uint8_t* keep, int32_t* counts, int32_t* kept_idx, void* stream);
+int lcr_neighbor_mean(const float* points, int64_t n_points, const int32_t* idx, int ld_idx, int H, int64_t m_rows,
+                      float* out, void* stream);
+/* decoder gather: out[i] = concat(coarse[up_idx[i, 0]] or zeros, fine[i])
+ * (nearest_upsample, modules/kpconv/functional.py:6-22; KPDecoder, backbone4.py:355-368) */
+int lcr_upsample_concat(const float* coarse, int64_t n_coarse, int c_coarse, const int32_t* up_idx, int ld_up,
+                        const float* fine, int c_fine, int64_t n_fine, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a10. Point-to-node partition (modules/ops/pointcloud_partition.py:61-107): nearest node per point
+ * (matmul-form squared distance, first minimum), per-node k nearest OWNED points ascending
+ * (ties: ascending point index), pad index = n_points, knn_mask 1 where valid.
+ * ---------------------------------------------------------------------------------------- */
+size_t lcr_point_to_node_ws_bytes(int64_t n_points, int64_t n_nodes);
+int lcr_point_to_node(const float* points, int64_t n_points, const float* nodes, int64_t n_nodes, int k,
+                      int32_t* point_to_node, uint8_t* node_mask, void* knn_idx, int idx_is64, uint8_t* knn_mask,
+                      int32_t* out_status, void* ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a11. Log-domain Sinkhorn with a learnable dustbin (modules/sinkhorn/learnable_sinkhorn.py:13-66).
+ * scores[batch, rows, cols], masks u8 (1 = valid, NULL = all valid), alpha device scalar ->
+ * out[batch, rows+1, cols+1].
+ * a12. Coarse correspondences (modules/geotransformer/superpoint_matching.py:129-160): from the
+ * (rows+1) x (cols+1) log scores, row-major list of (i, j, exp score); *out_count on the device;
+ * capacity rows + cols.
+ * ---------------------------------------------------------------------------------------- */
+int lcr_sinkhorn(const float* scores, int batch, int rows, int cols, const uint8_t* row_mask, const uint8_t* col_mask,
+                 const float* alpha, int iters, float* out, void* stream);
+size_t lcr_coarse_matching_ws_bytes(int rows, int cols);
+int lcr_coarse_matching(const float* log_scores, int rows, int cols, int32_t* out_i, int32_t* out_j,
+                        float* out_scores, int32_t* out_count, void* ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a13. Dense matching and local-to-global registration (model_family/LCRNet.py:218-262;
+ * modules/geotransformer/local_global_registration.py:49-246; modules/registration/procrustes.py:6-73).
+ * lcr_patch_scores: out[p] = F_a[knn_a[node_a[p]]] . F_b[knn_b[node_b[p]]]^T / sqrt(128), [128 x 128].
+ * lcr_fine_correspondences: from the Sinkhorn output [n_pairs, 129, 129]: (i, j) kept iff row- or
+ *   column-top-1 beating the dustbin, both points valid; row-major per pair; pair_off = exclusive
+ *   scan of the per-pair counts (pair_off[n_pairs] = total); outputs have capacity n_pairs * 256.
+ * lcr_corr_points: the 3-D points of the correspondences.
+ * lcr_local_global_registration: per-pair weighted Procrustes (pairs with >= min_corr
+ *   correspondences), hypothesis with most inliers (< radius) over all correspondences, then
+ *   `steps` rounds of inlier-reweighted global Procrustes -> out_T[16] (row-major 4x4, src -> ref).
+ * ---------------------------------------------------------------------------------------- */
+int lcr_patch_scores(const float* feats_a, int64_t n_a, const int32_t* knn_a, const int32_t* node_a,
+                     const float* feats_b, int64_t n_b, const int32_t* knn_b, const int32_t* node_b, int n_pairs,
+                     int k, int channels, float* out, void* stream);
+int lcr_fine_correspondences(const float* log_scores, int n_pairs, const uint8_t* knn_mask_a, const int32_t* node_a,
+                             const uint8_t* knn_mask_b, const int32_t* node_b, int32_t* pair_cnt, int32_t* pair_off,
+                             int32_t* out_pair, int32_t* out_i, int32_t* out_j, float* out_scores, void* stream);
+int lcr_corr_points(const int32_t* c_pair, const int32_t* c_i, const int32_t* c_j, const int32_t* n_corr,
+                    int64_t capacity, const float* pts_a, const int32_t* knn_a, const int32_t* node_a,
+                    const float* pts_b, const int32_t* knn_b, const int32_t* node_b, float* ref, float* src,
+                    void* stream);
+size_t lcr_lgr_ws_bytes(int n_pairs, int64_t capacity);
+int lcr_local_global_registration(const float* ref, const float* src, const float* scores, const int32_t* pair_off,
+                                  int n_pairs, int64_t capacity, float radius, int min_corr, int steps, float* out_T,
+                                  void* ws, size_t ws_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -40,6 +40,28 @@ SIGNATURES = {
     'lcr_netvlad_ws_bytes': (c_sz, [c_i64, c_i32]),
     'lcr_netvlad': (c_i32, [c_vp, c_i64, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_sz,
                             c_vp]),
+    'lcr_linear_ex': (c_i32, [c_vp, c_i64, c_i32, c_i32, c_vp, c_i32, c_vp, c_vp, c_i32, c_vp, c_i32, c_vp]),
+    'lcr_layer_norm': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_f32, c_i32, c_vp, c_vp]),
+    'lcr_rope': (c_i32, [c_vp, c_i32, c_vp, c_i64, c_vp]),
+    'lcr_attention': (c_i32, [c_vp, c_i32, c_vp, c_i32, c_vp, c_i32, c_vp, c_vp, c_i32, c_i64, c_i32, c_i32, c_vp,
+                              c_i32, ctypes.c_double, c_vp]),
+    'lcr_vote_shift': (c_i32, [c_vp, c_vp, c_i32, c_f32, c_i64, c_vp, c_vp]),
+    'lcr_nms_greedy': (c_i32, [c_vp, c_vp, c_i32, c_i64, c_f32, c_vp, c_vp, c_vp, c_vp]),
+    'lcr_neighbor_mean': (c_i32, [c_vp, c_i64, c_vp, c_i32, c_i32, c_i64, c_vp, c_vp]),
+    'lcr_upsample_concat': (c_i32, [c_vp, c_i64, c_i32, c_vp, c_i32, c_vp, c_i32, c_i64, c_vp, c_vp]),
+    'lcr_point_to_node_ws_bytes': (c_sz, [c_i64, c_i64]),
+    'lcr_point_to_node': (c_i32, [c_vp, c_i64, c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp, c_sz,
+                                  c_vp]),
+    'lcr_sinkhorn': (c_i32, [c_vp, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_i32, c_vp, c_vp]),
+    'lcr_coarse_matching_ws_bytes': (c_sz, [c_i32, c_i32]),
+    'lcr_coarse_matching': (c_i32, [c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    'lcr_patch_scores': (c_i32, [c_vp, c_i64, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp]),
+    'lcr_fine_correspondences': (c_i32, [c_vp, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,
+                                         c_vp]),
+    'lcr_corr_points': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    'lcr_lgr_ws_bytes': (c_sz, [c_i32, c_i64]),
+    'lcr_local_global_registration': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i64, c_f32, c_i32, c_i32, c_vp, c_vp,
+                                              c_sz, c_vp]),
     'lcr_l2_topk': (c_i32, [c_vp, c_i64, c_vp, c_i64, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp]),
 }
 

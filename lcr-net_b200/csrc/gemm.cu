@@ -17,7 +17,7 @@ constexpr int APAD = 4;
 template <int BM, int BN, int TM, int TN>
 __global__ void __launch_bounds__(256)
 gemm_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb, float* __restrict__ C, int ldc,
-            int M, int N, int K, const float* __restrict__ rowscale, const float* __restrict__ bias) {
+            int M, int N, int K, const float* __restrict__ rowscale, const float* __restrict__ bias, int relu) {
   constexpr int CT = BN / TN;        // threads along N
   constexpr int RT = BM / TM;        // threads along M
   static_assert(CT * RT == 256, "256 threads per CTA");
@@ -125,6 +125,9 @@ gemm_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B, i
           const float4 bv = *reinterpret_cast<const float4*>(bias + gn);
           v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
         }
+        if (relu) {
+          v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+        }
         *reinterpret_cast<float4*>(C + (size_t)gm * ldc + gn) = v;
       }
     }
@@ -132,16 +135,16 @@ gemm_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B, i
 
 template <int BM, int BN, int TM, int TN>
 void launch(const float* A, int lda, const float* B, int ldb, float* C, int ldc, int M, int N, int K,
-            const float* rowscale, const float* bias, cudaStream_t stream) {
+            const float* rowscale, const float* bias, int relu, cudaStream_t stream) {
   dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
-  gemm_kernel<BM, BN, TM, TN><<<grid, 256, 0, stream>>>(A, lda, B, ldb, C, ldc, M, N, K, rowscale, bias);
+  gemm_kernel<BM, BN, TM, TN><<<grid, 256, 0, stream>>>(A, lda, B, ldb, C, ldc, M, N, K, rowscale, bias, relu);
 }
 
 }  // namespace
 
 // Internal entry (also used by encoder.cu / netvlad.cu).
-int lcr_gemm_f32(const float* A, int lda, const float* B, int ldb, float* C, int ldc, int M, int N, int K,
-                 const float* rowscale, const float* bias, cudaStream_t stream) {
+int lcr_gemm_f32_act(const float* A, int lda, const float* B, int ldb, float* C, int ldc, int M, int N, int K,
+                     const float* rowscale, const float* bias, int relu, cudaStream_t stream) {
   LCR_REQUIRE(M >= 0 && N > 0 && K > 0, "gemm: bad shape");
   LCR_REQUIRE((N % 4) == 0 && (K % 4) == 0 && (lda % 4) == 0 && (ldb % 4) == 0 && (ldc % 4) == 0,
               "gemm: N, K and leading dimensions must be multiples of 4");
@@ -152,18 +155,31 @@ int lcr_gemm_f32(const float* A, int lda, const float* B, int ldb, float* C, int
   // tile choice: keep >= ~1 wave of CTAs on 148 SMs when the problem allows it
   const long ctas_128 = (long)((M + 127) / 128) * ((N + 127) / 128);
   if (N <= 32) {
-    launch<256, 32, 8, 4>(A, lda, B, ldb, C, ldc, M, N, K, rowscale, bias, stream);
+    launch<256, 32, 8, 4>(A, lda, B, ldb, C, ldc, M, N, K, rowscale, bias, relu, stream);
   } else if (N <= 64 || ctas_128 < LCR_SM_COUNT) {
     if ((long)((M + 127) / 128) * ((N + 63) / 64) < LCR_SM_COUNT)
-      launch<64, 64, 4, 4>(A, lda, B, ldb, C, ldc, M, N, K, rowscale, bias, stream);
+      launch<64, 64, 4, 4>(A, lda, B, ldb, C, ldc, M, N, K, rowscale, bias, relu, stream);
     else
-      launch<128, 64, 8, 4>(A, lda, B, ldb, C, ldc, M, N, K, rowscale, bias, stream);
+      launch<128, 64, 8, 4>(A, lda, B, ldb, C, ldc, M, N, K, rowscale, bias, relu, stream);
   } else {
-    launch<128, 128, 8, 8>(A, lda, B, ldb, C, ldc, M, N, K, rowscale, bias, stream);
+    launch<128, 128, 8, 8>(A, lda, B, ldb, C, ldc, M, N, K, rowscale, bias, relu, stream);
   }
   LCR_LAUNCHED(1);
   LCR_CUDA_CHECK_LAUNCH();
   return LCR_OK;
+}
+
+int lcr_gemm_f32(const float* A, int lda, const float* B, int ldb, float* C, int ldc, int M, int N, int K,
+                 const float* rowscale, const float* bias, cudaStream_t stream) {
+  return lcr_gemm_f32_act(A, lda, B, ldb, C, ldc, M, N, K, rowscale, bias, 0, stream);
+}
+
+// out = act(x . weight_t + bias), act: 0 none, 1 ReLU; optional per-row scale applied before the bias
+extern "C" int lcr_linear_ex(const float* x, int64_t n_rows, int c_in, int ld_x, const float* weight_t, int c_out,
+                             const float* bias, const float* rowscale, int act, float* out, int ld_out, void* stream) {
+  LCR_REQUIRE(n_rows >= 0 && n_rows < (1ll << 31), "linear: n_rows out of range");
+  return lcr_gemm_f32_act(x, ld_x, weight_t, c_out, out, ld_out, (int)n_rows, c_out, c_in, rowscale, bias, act,
+                          (cudaStream_t)stream);
 }
 
 extern "C" int lcr_linear(const float* x, int64_t n_rows, int c_in, const float* weight_t, int c_out,

@@ -1,0 +1,913 @@
+// matching.cu -- a10-a13 of the registration path:
+//   point -> node partition            modules/ops/pointcloud_partition.py:61-107, pairwise_distance.py:4-31
+//   log-domain Sinkhorn with dustbin   modules/sinkhorn/learnable_sinkhorn.py:13-66
+//   coarse (node) correspondences      modules/geotransformer/superpoint_matching.py:129-160
+//   patch score matrices               model_family/LCRNet.py:231-249
+//   fine correspondences               modules/geotransformer/local_global_registration.py:49-92
+//   local-to-global registration       local_global_registration.py:140-202, registration/procrustes.py:6-73
+// SFU / latency-bound small problems: one CTA per problem, everything stays on the device.
+#include "common.cuh"
+
+namespace {
+
+constexpr unsigned long long kEmptyKey = 0xFFFFFFFFFFFFFFFFull;
+
+// ================================================================== point -> node partition
+// owner[j] = argmin_i clamp(|n_i|^2 - 2 n_i.p_j + |p_j|^2, 1e-12)   (first minimum), d2 kept for the sort
+__global__ void __launch_bounds__(256)
+owner_kernel(const float* __restrict__ pts, int N, const float* __restrict__ nodes, int M,
+             int32_t* __restrict__ owner, float* __restrict__ owner_d2, uint32_t* __restrict__ node_count) {
+  extern __shared__ float4 s_nodes[];  // x, y, z, |n|^2
+  for (int i = threadIdx.x; i < M; i += blockDim.x) {
+    const float x = nodes[3 * i], y = nodes[3 * i + 1], z = nodes[3 * i + 2];
+    s_nodes[i] = make_float4(x, y, z, x * x + y * y + z * z);
+  }
+  __syncthreads();
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= N) return;
+  const float px = pts[3 * j], py = pts[3 * j + 1], pz = pts[3 * j + 2];
+  const float p2 = px * px + py * py + pz * pz;
+  float best = INFINITY;
+  int bi = 0;
+  for (int i = 0; i < M; i++) {
+    const float4 n = s_nodes[i];
+    const float xy = n.x * px + n.y * py + n.z * pz;
+    const float d = fmaxf(n.w - 2.f * xy + p2, 1e-12f);
+    if (d < best) {
+      best = d;
+      bi = i;
+    }
+  }
+  owner[j] = bi;
+  owner_d2[j] = best;
+  atomicAdd(&node_count[bi], 1u);
+}
+
+__global__ void node_scan_kernel(const uint32_t* __restrict__ node_count, int M, uint32_t* __restrict__ node_start,
+                                 uint8_t* __restrict__ node_mask) {
+  // single CTA, M is a few hundred to a few thousand
+  __shared__ uint32_t carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < M; base += blockDim.x) {
+    const int i = base + threadIdx.x;
+    const uint32_t v = i < M ? node_count[i] : 0u;
+    // block inclusive scan via warp scans
+    __shared__ uint32_t wsum[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      uint32_t w = lane < (blockDim.x >> 5) ? wsum[lane] : 0u, wi = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, wi, o);
+        if (lane >= o) wi += t;
+      }
+      wsum[lane] = wi - w;
+    }
+    __syncthreads();
+    const uint32_t ex = incl - v + wsum[warp] + carry;
+    if (i < M) {
+      node_start[i] = ex;
+      node_mask[i] = v > 0;
+    }
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) carry = ex + v;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) node_start[M] = carry;
+}
+
+__global__ void node_scatter_kernel(const int32_t* __restrict__ owner, const float* __restrict__ owner_d2, int N,
+                                    const uint32_t* __restrict__ node_start, uint32_t* __restrict__ node_cursor,
+                                    unsigned long long* __restrict__ keys) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= N) return;
+  const int o = owner[j];
+  const uint32_t pos = node_start[o] + atomicAdd(&node_cursor[o], 1u);
+  keys[pos] = ((unsigned long long)__float_as_uint(owner_d2[j]) << 32) | (unsigned)j;
+}
+
+// one CTA per node: sort its owned points by (d2, index), emit the first K
+constexpr int kNodeCap = 4096;
+__global__ void __launch_bounds__(256)
+node_topk_kernel(const unsigned long long* __restrict__ keys, const uint32_t* __restrict__ node_start, int N, int K,
+                 int idx_is64, void* __restrict__ knn_idx, uint8_t* __restrict__ knn_mask, int* __restrict__ err) {
+  __shared__ unsigned long long s[kNodeCap];
+  const int node = blockIdx.x;
+  const uint32_t st = node_start[node];
+  int cnt = (int)(node_start[node + 1] - st);
+  if (cnt > kNodeCap) {
+    if (threadIdx.x == 0) *err = LCR_ERR_OVERFLOW;
+    cnt = kNodeCap;
+  }
+  int n = 32;
+  while (n < cnt) n <<= 1;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s[i] = i < cnt ? keys[st + i] : kEmptyKey;
+  __syncthreads();
+  for (int k = 2; k <= n; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const unsigned long long a = s[i], b = s[ixj];
+          if ((a > b) == ((i & k) == 0)) {
+            s[i] = b;
+            s[ixj] = a;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  for (int t = threadIdx.x; t < K; t += blockDim.x) {
+    const bool ok = t < cnt;
+    const long long v = ok ? (long long)(unsigned)(s[t] & 0xFFFFFFFFull) : (long long)N;
+    if (idx_is64) ((int64_t*)knn_idx)[(size_t)node * K + t] = v;
+    else ((int32_t*)knn_idx)[(size_t)node * K + t] = (int32_t)v;
+    knn_mask[(size_t)node * K + t] = ok;
+  }
+}
+
+// ================================================================== Sinkhorn
+// One CTA per problem.  S = padded score matrix [(M+1) x (N+1)] lives in `out` (global, L2
+// resident) or, when it fits, in shared memory; u, v, log_mu, log_nu in shared memory.
+struct SinkhornArgs {
+  const float* scores;       // [B, M, N]
+  const uint8_t* row_mask;   // [B, M] (1 = valid) or NULL
+  const uint8_t* col_mask;   // [B, N] or NULL
+  const float* alpha;        // device scalar
+  float* out;                // [B, M+1, N+1]
+  int M, N, iters;
+};
+
+template <bool kSmem>
+__global__ void __launch_bounds__(512) sinkhorn_kernel(SinkhornArgs a) {
+  extern __shared__ float sm[];
+  const int R = a.M + 1, C = a.N + 1;
+  float* u = sm;
+  float* v = u + R;
+  float* log_mu = v + C;
+  float* log_nu = log_mu + R;
+  float* S = kSmem ? log_nu + C : a.out + (size_t)blockIdx.x * R * C;
+  __shared__ float s_norm;
+  __shared__ int s_cnt[2];
+  const int b = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+  const int lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+  const float inf = 1e12f;
+  const float alpha = *a.alpha;
+  const uint8_t* rm = a.row_mask ? a.row_mask + (size_t)b * a.M : nullptr;
+  const uint8_t* cm = a.col_mask ? a.col_mask + (size_t)b * a.N : nullptr;
+  if (tid < 2) s_cnt[tid] = 0;
+  __syncthreads();
+  int c0 = 0, c1 = 0;
+  for (int i = tid; i < a.M; i += nt) c0 += rm ? rm[i] : 1;
+  for (int j = tid; j < a.N; j += nt) c1 += cm ? cm[j] : 1;
+  c0 = lcr_warp_sum(c0);
+  c1 = lcr_warp_sum(c1);
+  if (lane == 0) {
+    atomicAdd(&s_cnt[0], c0);
+    atomicAdd(&s_cnt[1], c1);
+  }
+  __syncthreads();
+  const float nvr = (float)s_cnt[0], nvc = (float)s_cnt[1];
+  if (tid == 0) s_norm = -logf(nvr + nvc);
+  __syncthreads();
+  const float norm = s_norm;
+  for (int i = tid; i < R; i += nt) {
+    const bool masked = i < a.M && rm && !rm[i];
+    log_mu[i] = masked ? -inf : (i < a.M ? norm : logf(nvc) + norm);
+    u[i] = 0.f;
+  }
+  for (int j = tid; j < C; j += nt) {
+    const bool masked = j < a.N && cm && !cm[j];
+    log_nu[j] = masked ? -inf : (j < a.N ? norm : logf(nvr) + norm);
+    v[j] = 0.f;
+  }
+  const float* src = a.scores + (size_t)b * a.M * a.N;
+  for (int e = tid; e < R * C; e += nt) {
+    const int i = e / C, j = e % C;
+    float val = (i < a.M && j < a.N) ? src[(size_t)i * a.N + j] : alpha;
+    const bool masked = (i < a.M && rm && !rm[i]) || (j < a.N && cm && !cm[j]);
+    S[e] = masked ? -inf : val;
+  }
+  __syncthreads();
+  for (int it = 0; it < a.iters; it++) {
+    // u = log_mu - logsumexp_j(S + v)
+    for (int i = warp; i < R; i += nw) {
+      const float* row = S + (size_t)i * C;
+      float mx = -INFINITY;
+      for (int j = lane; j < C; j += 32) mx = fmaxf(mx, row[j] + v[j]);
+      mx = lcr_warp_max(mx);
+      float sum = 0.f;
+      for (int j = lane; j < C; j += 32) sum += expf(row[j] + v[j] - mx);
+      sum = lcr_warp_sum(sum);
+      if (lane == 0) u[i] = log_mu[i] - (mx + logf(sum));
+    }
+    __syncthreads();
+    // v = log_nu - logsumexp_i(S + u)
+    if (kSmem) {
+      for (int j = warp; j < C; j += nw) {
+        float mx = -INFINITY;
+        for (int i = lane; i < R; i += 32) mx = fmaxf(mx, S[(size_t)i * C + j] + u[i]);
+        mx = lcr_warp_max(mx);
+        float sum = 0.f;
+        for (int i = lane; i < R; i += 32) sum += expf(S[(size_t)i * C + j] + u[i] - mx);
+        sum = lcr_warp_sum(sum);
+        if (lane == 0) v[j] = log_nu[j] - (mx + logf(sum));
+      }
+    } else {
+      for (int j = tid; j < C; j += nt) {  // adjacent threads read adjacent columns: coalesced
+        float mx = -INFINITY;
+        for (int i = 0; i < R; i++) mx = fmaxf(mx, S[(size_t)i * C + j] + u[i]);
+        float sum = 0.f;
+        for (int i = 0; i < R; i++) sum += expf(S[(size_t)i * C + j] + u[i] - mx);
+        v[j] = log_nu[j] - (mx + logf(sum));
+      }
+    }
+    __syncthreads();
+  }
+  float* dst = a.out + (size_t)b * R * C;
+  for (int e = tid; e < R * C; e += nt) {
+    const int i = e / C, j = e % C;
+    dst[e] = S[e] + u[i] + v[j] - norm;
+  }
+}
+
+// ================================================================== coarse correspondences
+// log_scores [(M+1) x (N+1)]: (i,j) kept iff it is the column-argmax and beats the dustbin row, or
+// the row-argmax and beats the dustbin column (exp domain, strict >); listed row-major.
+__global__ void __launch_bounds__(1024)
+coarse_match_kernel(const float* __restrict__ ls, int M, int N, int32_t* __restrict__ out_i,
+                    int32_t* __restrict__ out_j, float* __restrict__ out_s, int32_t* __restrict__ out_n,
+                    int32_t* __restrict__ row_best, int32_t* __restrict__ col_best, int32_t* __restrict__ row_cnt) {
+  const int R = M + 1, C = N + 1;
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+  // exp() is monotone, so arg-maxima are taken on exp(ls) exactly like the reference (ties: first)
+  for (int i = warp; i < R; i += nw) {
+    float best = -INFINITY;
+    int bj = 0x7fffffff;
+    for (int j = lane; j < C; j += 32) {
+      const float e = expf(ls[(size_t)i * C + j]);
+      if (e > best) { best = e; bj = j; }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oj = __shfl_xor_sync(0xffffffffu, bj, o);
+      if (ob > best || (ob == best && oj < bj)) { best = ob; bj = oj; }
+    }
+    if (lane == 0) row_best[i] = bj;
+  }
+  for (int j = tid; j < C; j += nt) {
+    float best = -INFINITY;
+    int bi = 0;
+    for (int i = 0; i < R; i++) {
+      const float e = expf(ls[(size_t)i * C + j]);
+      if (e > best) { best = e; bi = i; }
+    }
+    col_best[j] = bi;
+  }
+  __syncthreads();
+  auto kept = [&](int i, int j) -> bool {
+    const float e = expf(ls[(size_t)i * C + j]);
+    const bool by_col = col_best[j] == i && e > expf(ls[(size_t)M * C + j]);
+    const bool by_row = row_best[i] == j && e > expf(ls[(size_t)i * C + N]);
+    return by_col || by_row;
+  };
+  for (int i = warp; i < M; i += nw) {
+    int c = 0;
+    for (int j = lane; j < N; j += 32) c += kept(i, j);
+    c = lcr_warp_sum(c);
+    if (lane == 0) row_cnt[i] = c;
+  }
+  __syncthreads();
+  if (tid == 0) {  // M is a few hundred: serial exclusive scan
+    int acc = 0;
+    for (int i = 0; i < M; i++) {
+      const int c = row_cnt[i];
+      row_cnt[i] = acc;
+      acc += c;
+    }
+    *out_n = acc;
+  }
+  __syncthreads();
+  for (int i = warp; i < M; i += nw) {
+    int base = row_cnt[i];
+    for (int j0 = 0; j0 < N; j0 += 32) {
+      const int j = j0 + lane;
+      const bool k = j < N && kept(i, j);
+      const unsigned m = __ballot_sync(0xffffffffu, k);
+      if (k) {
+        const int pos = base + __popc(m & ((1u << lane) - 1u));
+        out_i[pos] = i;
+        out_j[pos] = j;
+        out_s[pos] = expf(ls[(size_t)i * C + j]);
+      }
+      base += __popc(m);
+    }
+  }
+}
+
+// ================================================================== patch score matrices
+// out[p, a, b] = <fa[knn_a[p, a]], fb[knn_b[p, b]]> / sqrt(C)  (pad index -> zero row); K = 128, C = 128
+constexpr int PK = 128, PC = 128;
+__global__ void __launch_bounds__(256)
+patch_scores_kernel(const float* __restrict__ fa, int na, const int32_t* __restrict__ knn_a,
+                    const int32_t* __restrict__ node_a, const float* __restrict__ fb, int nb,
+                    const int32_t* __restrict__ knn_b, const int32_t* __restrict__ node_b, float div,
+                    float* __restrict__ out) {
+  extern __shared__ float sp[];  // A^T [PC][PK+4], B^T [PC][PK+4]
+  float(*sa)[PK + 4] = reinterpret_cast<float(*)[PK + 4]>(sp);
+  float(*sb)[PK + 4] = reinterpret_cast<float(*)[PK + 4]>(sp + PC * (PK + 4));
+  const int p = blockIdx.x, tid = threadIdx.x;
+  const int32_t* ka = knn_a + (size_t)node_a[p] * PK;
+  const int32_t* kb = knn_b + (size_t)node_b[p] * PK;
+  for (int e = tid; e < PK * (PC / 4); e += 256) {
+    const int r = e / (PC / 4), c4 = e % (PC / 4);
+    const int ia = ka[r], ib = kb[r];
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 va = ia < na ? *reinterpret_cast<const float4*>(fa + (size_t)ia * PC + c4 * 4) : z;
+    const float4 vb = ib < nb ? *reinterpret_cast<const float4*>(fb + (size_t)ib * PC + c4 * 4) : z;
+    sa[c4 * 4 + 0][r] = va.x; sa[c4 * 4 + 1][r] = va.y; sa[c4 * 4 + 2][r] = va.z; sa[c4 * 4 + 3][r] = va.w;
+    sb[c4 * 4 + 0][r] = vb.x; sb[c4 * 4 + 1][r] = vb.y; sb[c4 * 4 + 2][r] = vb.z; sb[c4 * 4 + 3][r] = vb.w;
+  }
+  __syncthreads();
+  const int tx = tid & 15, ty = tid >> 4;
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; i++)
+#pragma unroll
+    for (int j = 0; j < 8; j++) acc[i][j] = 0.f;
+#pragma unroll 4
+  for (int c = 0; c < PC; c++) {
+    float a[8], b[8];
+    *reinterpret_cast<float4*>(a) = *reinterpret_cast<const float4*>(&sa[c][ty * 4]);
+    *reinterpret_cast<float4*>(a + 4) = *reinterpret_cast<const float4*>(&sa[c][64 + ty * 4]);
+    *reinterpret_cast<float4*>(b) = *reinterpret_cast<const float4*>(&sb[c][tx * 4]);
+    *reinterpret_cast<float4*>(b + 4) = *reinterpret_cast<const float4*>(&sb[c][64 + tx * 4]);
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+      for (int j = 0; j < 8; j++) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+  }
+  float* o = out + (size_t)p * PK * PK;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const int r = (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      const int cidx = h * 64 + tx * 4;
+      *reinterpret_cast<float4*>(o + (size_t)r * PK + cidx) =
+          make_float4(acc[i][h * 4 + 0] / div, acc[i][h * 4 + 1] / div, acc[i][h * 4 + 2] / div, acc[i][h * 4 + 3] / div);
+    }
+  }
+}
+
+// ================================================================== fine correspondences
+// per pair p: log scores [129 x 129]; (i,j), i,j < 128, kept iff (row-argmax and > dustbin col) or
+// (col-argmax and > dustbin row) in the exp domain, and both points valid.  Two passes: count, emit.
+__global__ void __launch_bounds__(256)
+fine_corr_kernel(const float* __restrict__ ls, const uint8_t* __restrict__ mask_a, const int32_t* __restrict__ node_a,
+                 const uint8_t* __restrict__ mask_b, const int32_t* __restrict__ node_b,
+                 const int32_t* __restrict__ pair_off /* NULL in the counting pass */, int32_t* __restrict__ pair_cnt,
+                 int32_t* __restrict__ out_pair, int32_t* __restrict__ out_i, int32_t* __restrict__ out_j,
+                 float* __restrict__ out_s) {
+  constexpr int R = PK + 1;
+  __shared__ int row_best[R], col_best[R], row_cnt[PK];
+  const int p = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* S = ls + (size_t)p * R * R;
+  const uint8_t* ma = mask_a + (size_t)node_a[p] * PK;
+  const uint8_t* mb = mask_b + (size_t)node_b[p] * PK;
+  for (int i = warp; i < R; i += 8) {
+    float best = -INFINITY;
+    int bj = 0x7fffffff;
+    for (int j = lane; j < R; j += 32) {
+      const float e = expf(S[i * R + j]);
+      if (e > best) { best = e; bj = j; }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oj = __shfl_xor_sync(0xffffffffu, bj, o);
+      if (ob > best || (ob == best && oj < bj)) { best = ob; bj = oj; }
+    }
+    if (lane == 0) row_best[i] = bj;
+  }
+  for (int j = tid; j < R; j += 256) {
+    float best = -INFINITY;
+    int bi = 0;
+    for (int i = 0; i < R; i++) {
+      const float e = expf(S[i * R + j]);
+      if (e > best) { best = e; bi = i; }
+    }
+    col_best[j] = bi;
+  }
+  __syncthreads();
+  auto kept = [&](int i, int j) -> bool {
+    if (!ma[i] || !mb[j]) return false;
+    const float e = expf(S[i * R + j]);
+    return (row_best[i] == j && e > expf(S[i * R + PK])) || (col_best[j] == i && e > expf(S[PK * R + j]));
+  };
+  for (int i = warp; i < PK; i += 8) {
+    int c = 0;
+    for (int j = lane; j < PK; j += 32) c += kept(i, j);
+    c = lcr_warp_sum(c);
+    if (lane == 0) row_cnt[i] = c;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int acc = 0;
+    for (int i = 0; i < PK; i++) {
+      const int c = row_cnt[i];
+      row_cnt[i] = acc;
+      acc += c;
+    }
+    if (!pair_off) pair_cnt[p] = acc;
+  }
+  __syncthreads();
+  if (!pair_off) return;
+  const int base0 = pair_off[p];
+  for (int i = warp; i < PK; i += 8) {
+    int base = base0 + row_cnt[i];
+    for (int j0 = 0; j0 < PK; j0 += 32) {
+      const int j = j0 + lane;
+      const bool k = kept(i, j);
+      const unsigned m = __ballot_sync(0xffffffffu, k);
+      if (k) {
+        const int pos = base + __popc(m & ((1u << lane) - 1u));
+        out_pair[pos] = p;
+        out_i[pos] = i;
+        out_j[pos] = j;
+        out_s[pos] = expf(S[i * R + j]);
+      }
+      base += __popc(m);
+    }
+  }
+}
+
+__global__ void exclusive_scan_i32_kernel(const int32_t* __restrict__ in, int n, int32_t* __restrict__ out) {
+  // single CTA of 1024 threads, chunked
+  __shared__ int wsum[32];
+  __shared__ int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int base = 0; base < n; base += blockDim.x) {
+    const int i = base + threadIdx.x;
+    const int v = i < n ? in[i] : 0;
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      int w = lane < (blockDim.x >> 5) ? wsum[lane] : 0, wi = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, wi, o);
+        if (lane >= o) wi += t;
+      }
+      wsum[lane] = wi - w;
+    }
+    __syncthreads();
+    const int ex = incl - v + wsum[warp] + carry;
+    if (i < n) out[i] = ex;
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) carry = ex + v;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[n] = carry;
+}
+
+// gather correspondence points: ref = pts_a[knn_a[node_a[pair], i]], src = pts_b[knn_b[node_b[pair], j]]
+__global__ void corr_points_kernel(const int32_t* __restrict__ c_pair, const int32_t* __restrict__ c_i,
+                                   const int32_t* __restrict__ c_j, const int32_t* __restrict__ n_corr,
+                                   const float* __restrict__ pts_a, const int32_t* __restrict__ knn_a,
+                                   const int32_t* __restrict__ node_a, const float* __restrict__ pts_b,
+                                   const int32_t* __restrict__ knn_b, const int32_t* __restrict__ node_b,
+                                   float* __restrict__ ref, float* __restrict__ src) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= *n_corr) return;
+  const int p = c_pair[t];
+  const int ia = knn_a[(size_t)node_a[p] * PK + c_i[t]], ib = knn_b[(size_t)node_b[p] * PK + c_j[t]];
+#pragma unroll
+  for (int d = 0; d < 3; d++) {
+    ref[3 * t + d] = pts_a[3 * (size_t)ia + d];
+    src[3 * t + d] = pts_b[3 * (size_t)ib + d];
+  }
+}
+
+// ================================================================== weighted Procrustes
+// 3x3 SVD by one-sided Jacobi in double precision; R = V diag(1,1,det(V U^T)) U^T.
+__device__ void kabsch_rotation(const double H[3][3], double R[3][3]) {
+  double A[3][3], V[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) A[i][j] = H[i][j];
+  for (int sweep = 0; sweep < 30; sweep++) {
+    double off = 0.0;
+    for (int p = 0; p < 2; p++)
+      for (int q = p + 1; q < 3; q++) {
+        double alpha = 0, beta = 0, gamma = 0;
+        for (int i = 0; i < 3; i++) {
+          alpha += A[i][p] * A[i][p];
+          beta += A[i][q] * A[i][q];
+          gamma += A[i][p] * A[i][q];
+        }
+        off = fmax(off, fabs(gamma) / sqrt(fmax(alpha * beta, 1e-300)));
+        if (fabs(gamma) < 1e-300) continue;
+        const double zeta = (beta - alpha) / (2.0 * gamma);
+        const double t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+        const double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
+        for (int i = 0; i < 3; i++) {
+          const double ap = A[i][p], aq = A[i][q];
+          A[i][p] = c * ap - s * aq;
+          A[i][q] = s * ap + c * aq;
+          const double vp = V[i][p], vq = V[i][q];
+          V[i][p] = c * vp - s * vq;
+          V[i][q] = s * vp + c * vq;
+        }
+      }
+    if (off < 1e-15) break;
+  }
+  // singular values = column norms; order descending so the det correction hits the smallest
+  double sv[3];
+  int ord[3] = {0, 1, 2};
+  for (int j = 0; j < 3; j++) sv[j] = sqrt(A[0][j] * A[0][j] + A[1][j] * A[1][j] + A[2][j] * A[2][j]);
+  for (int a = 0; a < 2; a++)
+    for (int b = a + 1; b < 3; b++)
+      if (sv[ord[b]] > sv[ord[a]]) { const int t = ord[a]; ord[a] = ord[b]; ord[b] = t; }
+  double U[3][3], Vs[3][3];
+  for (int j = 0; j < 3; j++) {
+    const int o = ord[j];
+    for (int i = 0; i < 3; i++) {
+      Vs[i][j] = V[i][o];
+      U[i][j] = sv[o] > 1e-30 ? A[i][o] / sv[o] : 0.0;
+    }
+  }
+  // complete degenerate columns of U to an orthonormal basis
+  auto norm3 = [](double* x) { return sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]); };
+  if (sv[ord[0]] <= 1e-30) { U[0][0] = 1; U[1][0] = 0; U[2][0] = 0; }
+  if (sv[ord[1]] <= 1e-30) {
+    double e[3] = {0, 0, 0};
+    int m = fabs(U[0][0]) < fabs(U[1][0]) ? (fabs(U[0][0]) < fabs(U[2][0]) ? 0 : 2) : (fabs(U[1][0]) < fabs(U[2][0]) ? 1 : 2);
+    e[m] = 1.0;
+    const double dp = e[0] * U[0][0] + e[1] * U[1][0] + e[2] * U[2][0];
+    double w[3] = {e[0] - dp * U[0][0], e[1] - dp * U[1][0], e[2] - dp * U[2][0]};
+    const double nw = norm3(w);
+    for (int i = 0; i < 3; i++) U[i][1] = w[i] / nw;
+  }
+  if (sv[ord[2]] <= 1e-30 * fmax(sv[ord[0]], 1.0) || sv[ord[2]] <= 1e-30) {
+    U[0][2] = U[1][0] * U[2][1] - U[2][0] * U[1][1];
+    U[1][2] = U[2][0] * U[0][1] - U[0][0] * U[2][1];
+    U[2][2] = U[0][0] * U[1][1] - U[1][0] * U[0][1];
+  }
+  // M = V U^T, d = sign(det M)
+  double M[3][3];
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) M[i][j] = Vs[i][0] * U[j][0] + Vs[i][1] * U[j][1] + Vs[i][2] * U[j][2];
+  const double det = M[0][0] * (M[1][1] * M[2][2] - M[1][2] * M[2][1]) - M[0][1] * (M[1][0] * M[2][2] - M[1][2] * M[2][0]) +
+                     M[0][2] * (M[1][0] * M[2][1] - M[1][1] * M[2][0]);
+  const double d = det > 0 ? 1.0 : (det < 0 ? -1.0 : 0.0);
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) R[i][j] = Vs[i][0] * U[j][0] + Vs[i][1] * U[j][1] + d * Vs[i][2] * U[j][2];
+}
+
+// One CTA per segment [seg_off[s], seg_off[s+1]) of the correspondence arrays (or the whole range
+// when seg_off == NULL).  weights = w[t] (>= 0 enforced), normalised by (sum + 1e-5).
+// Segments shorter than min_count are skipped (valid[s] = 0).
+__global__ void __launch_bounds__(256)
+procrustes_kernel(const float* __restrict__ src, const float* __restrict__ ref, const float* __restrict__ w,
+                  const int32_t* __restrict__ seg_off, const int32_t* __restrict__ n_total, int min_count,
+                  float* __restrict__ T_out /*[S,16]*/, int32_t* __restrict__ valid) {
+  __shared__ double red[8][13];
+  __shared__ double tot[13];
+  const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int t0 = seg_off ? seg_off[s] : 0, t1 = seg_off ? seg_off[s + 1] : *n_total;
+  if (t1 - t0 < min_count) {
+    if (tid == 0 && valid) valid[s] = 0;
+    return;
+  }
+  auto block_sum = [&](double* vals, int n) {
+    for (int k = 0; k < n; k++) {
+      double x = vals[k];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+      if (lane == 0) red[warp][k] = x;
+    }
+    __syncthreads();
+    if (tid < n) {
+      double x = 0;
+      for (int ww = 0; ww < 8; ww++) x += red[ww][tid];
+      tot[tid] = x;
+    }
+    __syncthreads();
+  };
+  // pass 1: sum of weights, weighted sums of src and ref
+  double v[13];
+  for (int k = 0; k < 13; k++) v[k] = 0;
+  for (int t = t0 + tid; t < t1; t += 256) {
+    const double ww = fmax((double)w[t], 0.0);
+    v[0] += ww;
+    for (int d = 0; d < 3; d++) {
+      v[1 + d] += ww * (double)src[3 * t + d];
+      v[4 + d] += ww * (double)ref[3 * t + d];
+    }
+  }
+  block_sum(v, 7);
+  const double wsum = tot[0] + 1e-5;
+  double sc[3], rc[3];
+  for (int d = 0; d < 3; d++) {
+    sc[d] = tot[1 + d] / wsum;
+    rc[d] = tot[4 + d] / wsum;
+  }
+  __syncthreads();
+  // pass 2: H = sum w/wsum * (src - sc)(ref - rc)^T
+  for (int k = 0; k < 13; k++) v[k] = 0;
+  for (int t = t0 + tid; t < t1; t += 256) {
+    const double ww = fmax((double)w[t], 0.0) / wsum;
+    double a[3], b[3];
+    for (int d = 0; d < 3; d++) {
+      a[d] = (double)src[3 * t + d] - sc[d];
+      b[d] = (double)ref[3 * t + d] - rc[d];
+    }
+    for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++) v[3 * i + j] += ww * a[i] * b[j];
+  }
+  block_sum(v, 9);
+  if (tid == 0) {
+    double H[3][3], R[3][3];
+    for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++) H[i][j] = tot[3 * i + j];
+    kabsch_rotation(H, R);
+    float* T = T_out + (size_t)s * 16;
+    for (int i = 0; i < 3; i++) {
+      for (int j = 0; j < 3; j++) T[4 * i + j] = (float)R[i][j];
+      T[4 * i + 3] = (float)(rc[i] - (R[i][0] * sc[0] + R[i][1] * sc[1] + R[i][2] * sc[2]));
+    }
+    T[12] = T[13] = T[14] = 0.f;
+    T[15] = 1.f;
+    if (valid) valid[s] = 1;
+  }
+}
+
+__device__ __forceinline__ bool is_inlier(const float* T, const float* src, const float* ref, int t, float radius) {
+  const float x = src[3 * t], y = src[3 * t + 1], z = src[3 * t + 2];
+  const float ax = T[0] * x + T[1] * y + T[2] * z + T[3], ay = T[4] * x + T[5] * y + T[6] * z + T[7],
+              az = T[8] * x + T[9] * y + T[10] * z + T[11];
+  const float dx = ref[3 * t] - ax, dy = ref[3 * t + 1] - ay, dz = ref[3 * t + 2] - az;
+  return sqrtf(dx * dx + dy * dy + dz * dz) < radius;
+}
+
+// inlier count of every local transform over ALL correspondences; one CTA per segment
+__global__ void __launch_bounds__(256)
+inlier_count_kernel(const float* __restrict__ T, const int32_t* __restrict__ valid, const float* __restrict__ src,
+                    const float* __restrict__ ref, const int32_t* __restrict__ n_total, float radius,
+                    int32_t* __restrict__ counts) {
+  __shared__ int s_c[8];
+  const int s = blockIdx.x;
+  if (!valid[s]) {
+    if (threadIdx.x == 0) counts[s] = -1;
+    return;
+  }
+  const float* Ts = T + (size_t)s * 16;
+  int c = 0;
+  const int n = *n_total;
+  for (int t = threadIdx.x; t < n; t += 256) c += is_inlier(Ts, src, ref, t, radius);
+  c = lcr_warp_sum(c);
+  if ((threadIdx.x & 31) == 0) s_c[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int tot = 0;
+    for (int w = 0; w < 8; w++) tot += s_c[w];
+    counts[s] = tot;
+  }
+}
+
+// best = first argmax of counts (>= 0); copies T[best] to T_cur, or flags "no local transform"
+__global__ void pick_best_kernel(const int32_t* __restrict__ counts, int S, const float* __restrict__ T,
+                                 float* __restrict__ T_cur, int32_t* __restrict__ have_local) {
+  __shared__ int s_best[32], s_idx[32];
+  int best = -1, bi = 0x7fffffff;
+  for (int s = threadIdx.x; s < S; s += blockDim.x)
+    if (counts[s] > best) { best = counts[s]; bi = s; }
+  for (int o = 16; o > 0; o >>= 1) {
+    const int ob = __shfl_xor_sync(0xffffffffu, best, o), oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+  }
+  if ((threadIdx.x & 31) == 0) { s_best[threadIdx.x >> 5] = best; s_idx[threadIdx.x >> 5] = bi; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); w++)
+      if (s_best[w] > best || (s_best[w] == best && s_idx[w] < bi)) { best = s_best[w]; bi = s_idx[w]; }
+    *have_local = best >= 0;
+    if (best >= 0)
+      for (int k = 0; k < 16; k++) T_cur[k] = T[(size_t)bi * 16 + k];
+  }
+}
+
+// w_cur[t] = score[t] * inlier(T), T = (*select != 0) ? T_a : T_b   (select == NULL -> T_a)
+__global__ void reweight_kernel(const float* __restrict__ T_a, const float* __restrict__ T_b,
+                                const int32_t* __restrict__ select, const float* __restrict__ src,
+                                const float* __restrict__ ref, const float* __restrict__ score,
+                                const int32_t* __restrict__ n_total, float radius, float* __restrict__ w_cur) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= *n_total) return;
+  const float* T = (!select || *select != 0) ? T_a : T_b;
+  w_cur[t] = is_inlier(T, src, ref, t, radius) ? score[t] : 0.f;
+}
+
+}  // namespace
+
+// ================================================================== C ABI
+extern "C" size_t lcr_point_to_node_ws_bytes(int64_t n_points, int64_t n_nodes) {
+  return lcr_align_up(n_points * 4) * 2 + lcr_align_up(n_points * 8) + lcr_align_up((n_nodes + 1) * 4) * 3 + 1024;
+}
+
+extern "C" int lcr_point_to_node(const float* points, int64_t n_points, const float* nodes, int64_t n_nodes, int k,
+                                 int32_t* point_to_node, uint8_t* node_mask, void* knn_idx, int idx_is64,
+                                 uint8_t* knn_mask, int32_t* out_status, void* ws, size_t ws_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  LCR_REQUIRE(n_points >= 1 && n_nodes >= 1 && n_points < (1ll << 31) && n_nodes <= 12000,
+              "point_to_node: sizes (at most 12000 nodes)");
+  LCR_REQUIRE(k >= 1 && k <= kNodeCap, "point_to_node: k");
+  LCR_REQUIRE(ws && ws_bytes >= lcr_point_to_node_ws_bytes(n_points, n_nodes), "point_to_node: workspace too small");
+  const int N = (int)n_points, M = (int)n_nodes;
+  LcrArena a(ws, ws_bytes);
+  float* d2 = a.take<float>(N);
+  int32_t* owner_tmp = a.take<int32_t>(N);
+  unsigned long long* keys = a.take<unsigned long long>(N);
+  uint32_t* count = a.take<uint32_t>(M + 1);
+  uint32_t* start = a.take<uint32_t>(M + 1);
+  uint32_t* cursor = a.take<uint32_t>(M + 1);
+  int* err = (int*)a.take<int>(1);
+  int32_t* owner = point_to_node ? point_to_node : owner_tmp;
+  LcrProfScope prof("point_to_node", 8.0 * N * M, 12.0 * (N + M) + 4.0 * N + 5.0 * M * k, stream);
+  LCR_CUDA_TRY(cudaMemsetAsync(count, 0, sizeof(uint32_t) * (M + 1), stream));
+  LCR_CUDA_TRY(cudaMemsetAsync(cursor, 0, sizeof(uint32_t) * (M + 1), stream));
+  if (out_status) LCR_CUDA_TRY(cudaMemsetAsync(out_status, 0, sizeof(int32_t), stream));
+  const size_t smem = sizeof(float4) * M;
+  if (smem > 48 * 1024)
+    LCR_CUDA_TRY(cudaFuncSetAttribute(owner_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  owner_kernel<<<(N + 255) / 256, 256, smem, stream>>>(points, N, nodes, M, owner, d2, count);
+  node_scan_kernel<<<1, 1024, 0, stream>>>(count, M, start, node_mask);
+  node_scatter_kernel<<<(N + 255) / 256, 256, 0, stream>>>(owner, d2, N, start, cursor, keys);
+  node_topk_kernel<<<M, 256, 0, stream>>>(keys, start, N, k, idx_is64, knn_idx, knn_mask, out_status ? out_status : err);
+  LCR_LAUNCHED(4);
+  LCR_CUDA_CHECK_LAUNCH();
+  return LCR_OK;
+}
+
+extern "C" int lcr_sinkhorn(const float* scores, int batch, int rows, int cols, const uint8_t* row_mask,
+                            const uint8_t* col_mask, const float* alpha, int iters, float* out, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  LCR_REQUIRE(batch >= 0 && rows >= 1 && cols >= 1 && iters >= 0, "sinkhorn: sizes");
+  if (batch == 0) return LCR_OK;
+  SinkhornArgs a{scores, row_mask, col_mask, alpha, out, rows, cols, iters};
+  const size_t vec = sizeof(float) * 2 * (size_t)(rows + 1 + cols + 1);
+  const size_t mat = sizeof(float) * (size_t)(rows + 1) * (cols + 1);
+  LCR_REQUIRE(vec <= 96 * 1024, "sinkhorn: problem too large");
+  LcrProfScope prof("sinkhorn", 4.0 * batch * (double)(rows + 1) * (cols + 1) * iters,
+                    4.0 * batch * ((double)rows * cols + (double)(rows + 1) * (cols + 1)), stream);
+  if (vec + mat <= 200 * 1024) {
+    LCR_CUDA_TRY(cudaFuncSetAttribute(sinkhorn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)(vec + mat)));
+    sinkhorn_kernel<true><<<batch, 512, vec + mat, stream>>>(a);
+  } else {
+    LCR_CUDA_TRY(cudaFuncSetAttribute(sinkhorn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vec));
+    sinkhorn_kernel<false><<<batch, 512, vec, stream>>>(a);
+  }
+  LCR_LAUNCHED(1);
+  LCR_CUDA_CHECK_LAUNCH();
+  return LCR_OK;
+}
+
+extern "C" size_t lcr_coarse_matching_ws_bytes(int rows, int cols) {
+  return lcr_align_up((size_t)(rows + 1) * 4) * 2 + lcr_align_up((size_t)(cols + 1) * 4) + 256;
+}
+
+extern "C" int lcr_coarse_matching(const float* log_scores, int rows, int cols, int32_t* out_i, int32_t* out_j,
+                                   float* out_scores, int32_t* out_count, void* ws, size_t ws_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  LCR_REQUIRE(rows >= 1 && cols >= 1, "coarse_matching: sizes");
+  LCR_REQUIRE(ws && ws_bytes >= lcr_coarse_matching_ws_bytes(rows, cols), "coarse_matching: workspace too small");
+  LcrArena a(ws, ws_bytes);
+  int32_t* row_best = a.take<int32_t>(rows + 1);
+  int32_t* row_cnt = a.take<int32_t>(rows + 1);
+  int32_t* col_best = a.take<int32_t>(cols + 1);
+  coarse_match_kernel<<<1, 1024, 0, stream>>>(log_scores, rows, cols, out_i, out_j, out_scores, out_count, row_best,
+                                              col_best, row_cnt);
+  LCR_LAUNCHED(1);
+  LCR_CUDA_CHECK_LAUNCH();
+  return LCR_OK;
+}
+
+extern "C" int lcr_patch_scores(const float* feats_a, int64_t n_a, const int32_t* knn_a, const int32_t* node_a,
+                                const float* feats_b, int64_t n_b, const int32_t* knn_b, const int32_t* node_b,
+                                int n_pairs, int k, int channels, float* out, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  LCR_REQUIRE(k == PK && channels == PC, "patch_scores: specialised to 128 points x 128 channels");
+  if (n_pairs == 0) return LCR_OK;
+  const size_t smem = sizeof(float) * 2 * PC * (PK + 4);
+  LCR_CUDA_TRY(cudaFuncSetAttribute(patch_scores_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  LcrProfScope prof("patch_scores", 2.0 * n_pairs * PK * PK * PC, 4.0 * n_pairs * (2.0 * PK * PC + PK * PK), stream);
+  patch_scores_kernel<<<n_pairs, 256, smem, stream>>>(feats_a, (int)n_a, knn_a, node_a, feats_b, (int)n_b, knn_b,
+                                                      node_b, sqrtf((float)channels), out);
+  LCR_LAUNCHED(1);
+  LCR_CUDA_CHECK_LAUNCH();
+  return LCR_OK;
+}
+
+// Fine correspondences of all node pairs, row-major per pair (the reference's torch.nonzero order).
+// pair_off[n_pairs+1] (device) receives the exclusive scan of the per-pair counts; outputs have
+// capacity n_pairs * 256.
+extern "C" int lcr_fine_correspondences(const float* log_scores, int n_pairs, const uint8_t* knn_mask_a,
+                                        const int32_t* node_a, const uint8_t* knn_mask_b, const int32_t* node_b,
+                                        int32_t* pair_cnt, int32_t* pair_off, int32_t* out_pair, int32_t* out_i,
+                                        int32_t* out_j, float* out_scores, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (n_pairs == 0) {
+    LCR_CUDA_TRY(cudaMemsetAsync(pair_off, 0, sizeof(int32_t), stream));
+    return LCR_OK;
+  }
+  LcrProfScope prof("fine_correspondences", 0.0, 8.0 * n_pairs * 129.0 * 129.0, stream);
+  fine_corr_kernel<<<n_pairs, 256, 0, stream>>>(log_scores, knn_mask_a, node_a, knn_mask_b, node_b, nullptr, pair_cnt,
+                                                nullptr, nullptr, nullptr, nullptr);
+  exclusive_scan_i32_kernel<<<1, 1024, 0, stream>>>(pair_cnt, n_pairs, pair_off);
+  fine_corr_kernel<<<n_pairs, 256, 0, stream>>>(log_scores, knn_mask_a, node_a, knn_mask_b, node_b, pair_off, pair_cnt,
+                                                out_pair, out_i, out_j, out_scores);
+  LCR_LAUNCHED(3);
+  LCR_CUDA_CHECK_LAUNCH();
+  return LCR_OK;
+}
+
+extern "C" int lcr_corr_points(const int32_t* c_pair, const int32_t* c_i, const int32_t* c_j, const int32_t* n_corr,
+                               int64_t capacity, const float* pts_a, const int32_t* knn_a, const int32_t* node_a,
+                               const float* pts_b, const int32_t* knn_b, const int32_t* node_b, float* ref, float* src,
+                               void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (capacity == 0) return LCR_OK;
+  corr_points_kernel<<<(unsigned)((capacity + 255) / 256), 256, 0, stream>>>(c_pair, c_i, c_j, n_corr, pts_a, knn_a,
+                                                                            node_a, pts_b, knn_b, node_b, ref, src);
+  LCR_LAUNCHED(1);
+  LCR_CUDA_CHECK_LAUNCH();
+  return LCR_OK;
+}
+
+extern "C" size_t lcr_lgr_ws_bytes(int n_pairs, int64_t capacity) {
+  return lcr_align_up((size_t)(n_pairs + 1) * 64) + lcr_align_up((size_t)(n_pairs + 1) * 4) * 2 +
+         lcr_align_up((size_t)capacity * 4) + 1024;
+}
+
+// Local-to-global registration on the device.  ref/src/scores [n_corr] grouped by pair
+// (pair_off[n_pairs+1]); n_corr (device) = pair_off[n_pairs].  out_T [16] row-major 4x4.
+extern "C" int lcr_local_global_registration(const float* ref, const float* src, const float* scores,
+                                             const int32_t* pair_off, int n_pairs, int64_t capacity, float radius,
+                                             int min_corr, int steps, float* out_T, void* ws, size_t ws_bytes,
+                                             void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  LCR_REQUIRE(n_pairs >= 0 && capacity >= 0 && steps >= 1, "lgr: sizes");
+  LCR_REQUIRE(ws && ws_bytes >= lcr_lgr_ws_bytes(n_pairs, capacity), "lgr: workspace too small");
+  LcrArena a(ws, ws_bytes);
+  float* T_local = a.take<float>((size_t)(n_pairs + 1) * 16);
+  int32_t* valid = a.take<int32_t>(n_pairs + 1);
+  int32_t* counts = a.take<int32_t>(n_pairs + 1);
+  float* w_cur = a.take<float>(capacity > 0 ? capacity : 1);
+  int32_t* have_local = (int32_t*)a.take<int32_t>(1);
+  const int32_t* n_corr = pair_off + n_pairs;
+  const unsigned gridC = (unsigned)((capacity + 255) / 256) > 0 ? (unsigned)((capacity + 255) / 256) : 1u;
+  LcrProfScope prof("lgr", 0.0, 28.0 * capacity * (n_pairs + 2.0 * steps), stream);
+  LCR_CUDA_TRY(cudaMemsetAsync(have_local, 0, sizeof(int32_t), stream));
+  int launches = 0;
+  if (n_pairs > 0) {
+    procrustes_kernel<<<n_pairs, 256, 0, stream>>>(src, ref, scores, pair_off, n_corr, min_corr, T_local, valid);
+    inlier_count_kernel<<<n_pairs, 256, 0, stream>>>(T_local, valid, src, ref, n_corr, radius, counts);
+    pick_best_kernel<<<1, 1024, 0, stream>>>(counts, n_pairs, T_local, out_T, have_local);
+    launches += 3;
+  }
+  // degenerate branch (no patch with >= min_corr correspondences): start from all correspondences
+  // (local_global_registration.py:183-188); computed unconditionally, selected on the device
+  float* T_deg = T_local + (size_t)n_pairs * 16;
+  procrustes_kernel<<<1, 256, 0, stream>>>(src, ref, scores, nullptr, n_corr, 0, T_deg, nullptr);
+  // w = score * inlier(have_local ? T_best : T_deg)
+  reweight_kernel<<<gridC, 256, 0, stream>>>(out_T, T_deg, have_local, src, ref, scores, n_corr, radius, w_cur);
+  launches += 2;
+  for (int it = 0; it < steps; it++) {
+    procrustes_kernel<<<1, 256, 0, stream>>>(src, ref, w_cur, nullptr, n_corr, 0, out_T, nullptr);
+    launches++;
+    if (it + 1 < steps) {
+      reweight_kernel<<<gridC, 256, 0, stream>>>(out_T, nullptr, nullptr, src, ref, scores, n_corr, radius, w_cur);
+      launches++;
+    }
+  }
+  LCR_LAUNCHED(launches);
+  LCR_CUDA_CHECK_LAUNCH();
+  return LCR_OK;
+}

@@ -1,0 +1,400 @@
+"""The full LCR-Net model (loop-closing descriptor + registration) on the B200 kernels, with the
+reference's class/attribute names and state_dict layout (model_family/LCRNet.py:25-326; 373
+tensors) and its ``forward(data_dict) -> output_dict`` contract (keys: Appendix C.4 of SURVEY.md).
+
+Differences from the reference, all in its favour and none visible in the outputs:
+* the three radius searches inside the vote encoder (backbone4.py:149-206) run on the GPU: no
+  ``.cpu()`` / ``.cuda()`` round trips;
+* weighted Procrustes uses an on-device 3x3 SVD instead of ``torch.svd(H.cpu())`` (procrustes.py:53);
+* a data_dict may hold several pairs (``stack_size = 2``): encoder, transformer, vote encoder and
+  decoder run batched over all pairs with per-pair GroupNorm statistics; the matching head then
+  runs pair by pair.  With one pair the outputs are the reference's tensors; with several, the
+  per-pair outputs are lists.
+"""
+import torch
+import torch.nn as nn
+
+from . import ops
+from . import pair_ops as P
+from .model import KPEncoder, NetVLADLoupe2, ResidualBlock, UnaryBlock, make_stacks
+
+
+class LinearT(nn.Linear):
+    """nn.Linear that also serves its weight transposed (and zero-padded to a multiple of 4 in
+    both dimensions) for the [rows, c_in] x [c_in, c_out] kernels."""
+
+    def __init__(self, *a, **k):
+        super().__init__(*a, **k)
+        self._cache = None
+
+    def packed(self):
+        w = self.weight
+        key = (w.data_ptr(), w._version, self.bias.data_ptr() if self.bias is not None else 0)
+        if self._cache is None or self._cache[0] != key:
+            cout, cin = w.shape
+            pi, po = (cin + 3) // 4 * 4, (cout + 3) // 4 * 4
+            wt = torch.zeros((pi, po), dtype=torch.float32, device=w.device)
+            wt[:cin, :cout] = w.detach().t()
+            b = torch.zeros(po, dtype=torch.float32, device=w.device)
+            if self.bias is not None:
+                b[:cout] = self.bias.detach()
+            self._cache = (key, wt, b)
+        return self._cache[1], self._cache[2]
+
+    def run(self, x, relu=False):
+        wt, b = self.packed()
+        return P.linear_ex(x, wt, b, relu=relu)
+
+
+def _fused(linears):
+    """[c_in, sum c_out] weight and bias of several Linear layers sharing an input."""
+    ws, bs = zip(*(l.packed() for l in linears))
+    return torch.cat(ws, 1).contiguous(), torch.cat(bs).contiguous()
+
+
+# ------------------------------------------------------------------ transformer (parameter holders)
+class _MHA(nn.Module):
+    def __init__(self, d):
+        super().__init__()
+        self.proj_q, self.proj_k, self.proj_v = LinearT(d, d), LinearT(d, d), LinearT(d, d)
+        self._qkv = None
+
+    def fused(self):
+        key = tuple((l.weight.data_ptr(), l.weight._version) for l in (self.proj_q, self.proj_k, self.proj_v))
+        if self._qkv is None or self._qkv[0] != key:
+            self._qkv = (key, _fused([self.proj_q, self.proj_k, self.proj_v]), _fused([self.proj_k, self.proj_v]))
+        return self._qkv[1], self._qkv[2]
+
+
+class _AttentionLayer(nn.Module):
+    def __init__(self, d):
+        super().__init__()
+        self.attention = _MHA(d)
+        self.linear = LinearT(d, d)
+        self.norm = nn.LayerNorm(d)
+
+
+class _AttentionOutput(nn.Module):
+    def __init__(self, d):
+        super().__init__()
+        self.expand, self.squeeze = LinearT(d, 2 * d), LinearT(2 * d, d)
+        self.norm = nn.LayerNorm(d)
+
+
+class _TransformerLayer(nn.Module):
+    """RPETransformerLayer / TransformerLayer (rpetransformer.py:144-171, vanilla_transformer.py:115-144)."""
+
+    def __init__(self, d):
+        super().__init__()
+        self.attention = _AttentionLayer(d)
+        self.output = _AttentionOutput(d)
+
+    def forward(self, x, mem, x_off, mem_off, n_prob, max_q, theta_x=None, theta_mem=None):
+        mha = self.attention.attention
+        (w_qkv, b_qkv), (w_kv, b_kv) = mha.fused()
+        d = x.shape[1]
+        if mem is x:
+            qkv = P.linear_ex(x, w_qkv, b_qkv)
+            q, k, v = qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:]
+        else:
+            q = mha.proj_q.run(x)
+            kv = P.linear_ex(mem, w_kv, b_kv)
+            k, v = kv[:, :d], kv[:, d:]
+        if theta_x is not None:
+            P.rope_(q, theta_x)
+            P.rope_(k, theta_mem)
+        flops = 4.0 * 32 * 4 * float(x.shape[0]) * float(mem.shape[0]) / max(n_prob, 1)
+        h = P.attention(q, k, v, x_off, mem_off, n_prob, max_q, heads=4, flops=flops)
+        a = self.attention
+        h = P.layer_norm(a.linear.run(h), a.norm.weight, a.norm.bias, residual=x)
+        o = self.output
+        return P.layer_norm(o.squeeze.run(o.expand.run(h, relu=True)), o.norm.weight, o.norm.bias, residual=h)
+
+
+class _LayerStack(nn.Module):
+    def __init__(self, d, n):
+        super().__init__()
+        self.layers = nn.ModuleList([_TransformerLayer(d) for _ in range(n)])
+
+
+class _PosEmbedding(nn.Module):
+    def __init__(self, d):
+        super().__init__()
+        self.encoder, self.encoder2 = LinearT(3, d), LinearT(d, d // 2)
+
+
+class ThDRoFormer(nn.Module):
+    """thdroformer_linear.py:12-96: blocks ['self', 'cross'] * num_layers, sequential cross update."""
+
+    def __init__(self, input_dim, output_dim, hidden_dim, num_heads, num_layers, k=None):
+        super().__init__()
+        assert num_heads == 4 and hidden_dim == 128 and k is None
+        self.embedding = _PosEmbedding(hidden_dim)
+        self.in_proj = LinearT(input_dim, hidden_dim)
+        self.transformer = _LayerStack(hidden_dim, 2 * num_layers)
+        self.out_proj = LinearT(hidden_dim, output_dim)
+
+    def forward(self, ref_points, src_points, ref_feats, src_feats, ref_off, src_off, n_prob, max_ref, max_src):
+        """All ref clouds stacked in ref_* (row offsets ref_off), all src clouds in src_*."""
+        def theta(p):
+            p4 = torch.zeros((p.shape[0], 4), dtype=torch.float32, device=p.device)
+            p4[:, :3] = p
+            return self.embedding.encoder2.run(self.embedding.encoder.run(p4))
+        th0, th1 = theta(ref_points), theta(src_points)
+        f0, f1 = self.in_proj.run(ref_feats), self.in_proj.run(src_feats)
+        for i, layer in enumerate(self.transformer.layers):
+            if i % 2 == 0:
+                f0 = layer(f0, f0, ref_off, ref_off, n_prob, max_ref, th0, th0)
+                f1 = layer(f1, f1, src_off, src_off, n_prob, max_src, th1, th1)
+            else:
+                f0 = layer(f0, f1, ref_off, src_off, n_prob, max_ref)
+                f1 = layer(f1, f0, src_off, ref_off, n_prob, max_src)
+        return self.out_proj.run(f0), self.out_proj.run(f1)
+
+
+# ------------------------------------------------------------------ vote encoder / decoder
+class Vote_layer(nn.Module):
+    """modules/vote/vote.py:112-183 (output_feats=False)."""
+
+    def __init__(self, input_feats_dim=256, max_translate_range=4.2):
+        super().__init__()
+        d = input_feats_dim
+        self.mlp_modules = nn.Sequential(LinearT(d, 2 * d), nn.LayerNorm(2 * d), nn.ReLU(),
+                                         LinearT(2 * d, d), nn.LayerNorm(d), nn.ReLU())
+        self.ctr_reg = LinearT(d, 3)
+        self.max_offset_limit = max_translate_range
+
+    def forward(self, xyz, features):
+        m = self.mlp_modules
+        x = P.layer_norm(m[0].run(features), m[1].weight, m[1].bias, relu=True)
+        x = P.layer_norm(m[3].run(x), m[4].weight, m[4].bias, relu=True)
+        return P.vote_shift(xyz, self.ctr_reg.run(x), self.max_offset_limit)
+
+
+class Vote_Encoder(nn.Module):
+    """backbone4.py:92-220."""
+
+    def __init__(self, input_dim, init_dim, kernel_size, init_radius, init_sigma, group_norm, vote, neighbor_limits):
+        super().__init__()
+        self.vote = Vote_layer(256, vote.MAX_TRANSLATE_RANGE)
+        self.NMS_radius = vote.NMS_radius
+        d = init_dim
+        self.encoder6_1 = ResidualBlock(4 * d, 4 * d, kernel_size, init_radius * 8, init_sigma * 8, group_norm, strided=True)
+        self.encoder6_2 = ResidualBlock(4 * d, 8 * d, kernel_size, init_radius * 16, init_sigma * 16, group_norm)
+        self.encoder6_3 = ResidualBlock(8 * d, 8 * d, kernel_size, init_radius * 16, init_sigma * 16, group_norm)
+        self.init_radius = init_radius
+        self.neighbor_limits = neighbor_limits
+
+    def forward(self, feats, data_dict, stacks_c, lengths_c_host, stack_size):
+        points_c, lengths_c = data_dict['points'][-1], data_dict['lengths'][-1]
+        dev = feats.device
+        shifted = self.vote(points_c, feats)
+        clouds = ops.Stacks(lengths_c_host, dev)
+        keep, counts, kept_idx = P.nms_greedy(shifted, clouds.off, clouds.n, clouds.max_rows, self.NMS_radius)
+        counts_host = counts.tolist()                                   # D2H: node counts size everything below
+        node_len = counts.to(torch.int64)
+        sel = torch.cat([kept_idx[o:o + c] for o, c in zip(clouds.off.tolist()[:-1], counts_host)]).long()
+        nms_points = shifted[sel].contiguous()
+        lim = self.neighbor_limits
+        node_knn = ops.radius_search(nms_points, shifted, node_len, lengths_c, self.NMS_radius, lim[-1], int32=True)
+        centres = P.neighbor_mean(shifted, node_knn)
+        sub = ops.radius_search(centres, points_c, node_len, lengths_c, self.init_radius * 8, lim[-2], int32=True)
+        nb = ops.radius_search(centres, centres, node_len, node_len, self.init_radius * 16, lim[-1], int32=True)
+        node_groups = [sum(counts_host[i:i + stack_size]) for i in range(0, len(counts_host), stack_size)]
+        node_stacks = ops.Stacks(node_groups, dev)
+        x = self.encoder6_1(feats, centres, points_c, sub, node_stacks, stacks_c)
+        x = self.encoder6_2(x, centres, centres, nb, node_stacks, node_stacks)
+        x = self.encoder6_3(x, centres, centres, nb, node_stacks, node_stacks)
+        return {'shifted': shifted, 'keep': keep, 'counts': counts_host, 'centres': centres, 'feats': x}
+
+
+class _LastUnary(nn.Module):
+    def __init__(self, cin, cout):
+        super().__init__()
+        self.mlp = LinearT(cin, cout)
+
+
+class KPDecoder(nn.Module):
+    """backbone4.py:333-373."""
+
+    def __init__(self, output_dim, init_dim, group_norm, neighbor_limit=None, init_radius=None):
+        super().__init__()
+        d = init_dim
+        self.decoder3 = UnaryBlock(12 * d, 8 * d, group_norm)
+        self.decoder2 = UnaryBlock(12 * d, 4 * d, group_norm)
+        self.decoder1 = _LastUnary(6 * d, 2 * d)
+
+    def forward(self, feats, data_dict, stacks):
+        up = data_dict['upsampling']
+        l3 = self.decoder3(P.upsample_concat(feats[3], up[2], feats[2]), stacks[2])
+        l2 = self.decoder2(P.upsample_concat(l3, up[1], feats[1]), stacks[1])
+        return self.decoder1.mlp.run(P.upsample_concat(l2, up[0], feats[0]))
+
+
+class LearnableLogOptimalTransport(nn.Module):
+    """modules/sinkhorn/learnable_sinkhorn.py:5-66."""
+
+    def __init__(self, num_iterations):
+        super().__init__()
+        self.num_iterations = num_iterations
+        self.register_parameter('alpha', nn.Parameter(torch.tensor(1.0)))
+
+    def forward(self, scores, row_masks=None, col_masks=None):
+        return P.sinkhorn(scores, row_masks, col_masks, self.alpha, self.num_iterations)
+
+
+# ------------------------------------------------------------------ the model
+class LCRNet(nn.Module):
+    """model_family/LCRNet.py:25-321."""
+
+    def __init__(self, cfg):
+        super().__init__()
+        b = cfg.backbone
+        self.num_points_in_patch = cfg.model.num_points_in_patch
+        self.encoder = KPEncoder(b.input_dim, b.init_dim, b.kernel_size, b.init_radius, b.init_sigma, b.group_norm)
+        self.vote_encoder = Vote_Encoder(b.input_dim, b.init_dim, b.kernel_size, b.init_radius, b.init_sigma,
+                                         b.group_norm, cfg.Vote, cfg.neighbor_limits)
+        self.proj_node_overlap_score = nn.Linear(cfg.GAT.output_dim * 2, 1)      # unused at inference
+        self.transformer = ThDRoFormer(cfg.GAT.input_dim, cfg.GAT.output_dim, cfg.GAT.hidden_dim, cfg.GAT.num_heads,
+                                       cfg.GAT.num_layers, cfg.GAT.k)
+        self.kpdecoder = KPDecoder(b.output_dim, b.init_dim, b.group_norm)
+        self.node_optimal_transport = LearnableLogOptimalTransport(cfg.model.num_sinkhorn_iterations)
+        self.optimal_transport = LearnableLogOptimalTransport(cfg.model.num_sinkhorn_iterations)
+        self.netvlad = NetVLADLoupe2(feature_size=1024, cluster_size=64, output_dim=256, gating=True, add_norm=True,
+                                     is_training=False)
+        fm = cfg.fine_matching
+        assert fm.topk == 1 and not fm.mutual and fm.use_dustbin and not fm.use_global_score and \
+            fm.correspondence_limit is None and cfg.coarse_matching.num_correspondences is None, \
+            'the B200 matching kernels implement the shipped LCR-Net configuration (config_model.py:61,84-93)'
+        self.acceptance_radius, self.correspondence_threshold = fm.acceptance_radius, fm.correspondence_threshold
+        self.num_refinement_steps = fm.num_refinement_steps
+        self.vis = False
+
+    @torch.no_grad()
+    def forward(self, data_dict):
+        assert not self.training, 'lcrnet_b200 implements inference only: call model.eval()'
+        dd = dict(data_dict)
+        dd.setdefault('stack_size', 2)
+        assert dd['stack_size'] == 2
+        feats = dd['features'].detach()
+        dev = feats.device
+        stacks, lh = make_stacks(dd, dev)
+        n_f, n_c = lh[0], lh[-1]
+        n_pairs = len(n_c) // 2
+        points_f, points_c = dd['points'][0], dd['points'][-1]
+        dd = {k: ([ops.as_index32(t) for t in v] if k in ('neighbors', 'subsampling', 'upsampling') else v)
+              for k, v in dd.items()}
+
+        # 1. encoder + global descriptors of every cloud (LCRNet.py:124-140, 115-122, 296-297)
+        feats_list = self.encoder(feats, dd, stacks)
+        feats_c = feats_list[-1]
+        clouds_c = ops.Stacks(n_c, dev)
+        descriptors = self.netvlad(feats_c, clouds_c.off, clouds_c.n)
+
+        # 2. transformer on the coarsest level: all ref clouds / all src clouds stacked separately
+        off_c = clouds_c.off.tolist()
+        ref_rows = torch.cat([torch.arange(off_c[2 * p], off_c[2 * p + 1], device=dev) for p in range(n_pairs)])
+        src_rows = torch.cat([torch.arange(off_c[2 * p + 1], off_c[2 * p + 2], device=dev) for p in range(n_pairs)])
+        ref_st, src_st = ops.Stacks(n_c[0::2], dev), ops.Stacks(n_c[1::2], dev)
+        e0, e1 = self.transformer(points_c[ref_rows].contiguous(), points_c[src_rows].contiguous(),
+                                  feats_c[ref_rows].contiguous(), feats_c[src_rows].contiguous(), ref_st.off,
+                                  src_st.off, n_pairs, ref_st.max_rows, src_st.max_rows)
+        enhanced = torch.empty((feats_c.shape[0], e0.shape[1]), dtype=torch.float32, device=dev)
+        enhanced[ref_rows] = e0
+        enhanced[src_rows] = e1
+
+        # 3. vote encoder (LCRNet.py:158) and decoder (LCRNet.py:211-212), batched over pairs
+        vd = self.vote_encoder(enhanced, dd, stacks[-1], n_c, 2)
+        feats_f = self.kpdecoder(feats_list[:3] + [enhanced], dd, stacks)
+
+        # 4. matching head, pair by pair (LCRNet.py:161-272)
+        off_f = ops.Stacks(n_f, dev).off.tolist()
+        node_off = [0]
+        for c in vd['counts']:
+            node_off.append(node_off[-1] + c)
+        outs = []
+        for p in range(n_pairs):
+            a, b = 2 * p, 2 * p + 1
+            out = self._match(points_f[off_f[a]:off_f[a + 1]], points_f[off_f[b]:off_f[b + 1]],
+                              feats_f[off_f[a]:off_f[a + 1]], feats_f[off_f[b]:off_f[b + 1]],
+                              vd['centres'][node_off[a]:node_off[a + 1]], vd['centres'][node_off[b]:node_off[b + 1]],
+                              vd['feats'][node_off[a]:node_off[a + 1]], vd['feats'][node_off[b]:node_off[b + 1]])
+            out.update({
+                'ori_pos_points_c': points_c[off_c[a]:off_c[a + 1]], 'ori_anc_points_c': points_c[off_c[b]:off_c[b + 1]],
+                'pos_points_f': points_f[off_f[a]:off_f[a + 1]], 'anc_points_f': points_f[off_f[b]:off_f[b + 1]],
+                'pos_feature_global': descriptors[a:a + 1], 'anc_feature_global': descriptors[b:b + 1],
+                'shifted_pos_points_c': vd['shifted'][off_c[a]:off_c[a + 1]],
+                'shifted_anc_points_c': vd['shifted'][off_c[b]:off_c[b + 1]],
+                'length': torch.tensor(vd['counts'][a:b + 1]),
+                'feats_c': vd['feats'][node_off[a]:node_off[b + 1]],
+            })
+            outs.append(out)
+        if n_pairs == 1:
+            return outs[0]
+        merged = {k: [o[k] for o in outs] for k in outs[0]}
+        merged['estimated_transform'] = torch.stack(merged['estimated_transform'])
+        return merged
+
+    def _match(self, pos_pf, anc_pf, pos_ff, anc_ff, pos_nodes, anc_nodes, pos_nf, anc_nf):
+        K = self.num_points_in_patch
+        pos_pf, anc_pf = pos_pf.contiguous(), anc_pf.contiguous()
+        _, pos_nm, pos_knn, pos_km, _ = P.point_to_node_partition(pos_pf, pos_nodes.contiguous(), K)
+        _, anc_nm, anc_knn, anc_km, _ = P.point_to_node_partition(anc_pf, anc_nodes.contiguous(), K)
+        # node-level optimal transport (LCRNet.py:196-205)
+        node_scores = P.linear_ex(pos_nf.contiguous(), _pad4(anc_nf.t()), None)[:, :anc_nf.shape[0]]
+        node_scores = (node_scores / pos_nf.shape[1] ** 0.5).contiguous()
+        node_ot = self.node_optimal_transport(node_scores[None], pos_nm[None], anc_nm[None])[0]
+        ci, cj, cs = P.coarse_matching(node_ot)
+        # dense matching (LCRNet.py:218-262)
+        ms = P.patch_scores(pos_ff.contiguous(), pos_knn, ci, anc_ff.contiguous(), anc_knn, cj)
+        pkm, akm = pos_km[ci.long()], anc_km[cj.long()]
+        ot = self.optimal_transport(ms, pkm, akm)
+        corr = P.fine_correspondences(ot, pos_km, ci, anc_km, cj)
+        ref_c, src_c = P.corr_points(corr, pos_pf, pos_knn, ci, anc_pf, anc_knn, cj)
+        T = P.local_global_registration(ref_c, src_c, corr['score'], corr['pair_off'], self.acceptance_radius,
+                                        self.correspondence_threshold, self.num_refinement_steps)
+        n = int(corr['pair_off'][-1])                                   # D2H: number of correspondences
+        pad3 = lambda x: torch.cat([x, torch.zeros_like(x[:1])], 0)
+        return {'estimated_transform': T, 'pos_corr_points': ref_c[:n], 'anc_corr_points': src_c[:n],
+                'corr_scores': corr['score'][:n], 'pos_node_corr_indices': ci.long(), 'anc_node_corr_indices': cj.long(),
+                'pos_points_c': pos_nodes, 'anc_points_c': anc_nodes, 'pos_feats_c': pos_nf, 'anc_feats_c': anc_nf,
+                'pos_feats_f': pos_ff, 'anc_feats_f': anc_ff,
+                'pos_node_knn_indices': (pos_knn.long(),), 'pos_node_knn_masks': (pos_km,),
+                'anc_node_knn_indices': (anc_knn.long(),), 'anc_node_knn_masks': (anc_km,),
+                'pos_node_corr_knn_points': pad3(pos_pf)[pos_knn.long()[ci.long()]],
+                'anc_node_corr_knn_points': pad3(anc_pf)[anc_knn.long()[cj.long()]],
+                'pos_node_corr_knn_masks': pkm, 'anc_node_corr_knn_masks': akm,
+                '_node_ot': node_ot, '_point_ot': ot}
+
+
+def _pad4(w):
+    """[c_in, n] -> contiguous with n padded to a multiple of 4 (GEMM operand B)."""
+    cin, n = w.shape
+    out = torch.zeros((cin, (n + 3) // 4 * 4), dtype=torch.float32, device=w.device)
+    out[:, :n] = w
+    return out
+
+
+def create_model(cfg):
+    return LCRNet(cfg)
+
+
+class _Cfg(dict):
+    __getattr__ = dict.__getitem__
+    __setattr__ = dict.__setitem__
+
+
+def default_cfg(neighbor_limits):
+    """The values of experiments/lcrnet/config_model.py:33-93 that the model reads."""
+    return _Cfg(
+        backbone=_Cfg(num_stages=4, init_voxel_size=0.3, kernel_size=15, base_radius=4.25, base_sigma=2.0,
+                      init_radius=4.25 * 0.3, init_sigma=2.0 * 0.3, group_norm=32, input_dim=1, init_dim=64,
+                      output_dim=256),
+        model=_Cfg(num_points_in_patch=128, num_sinkhorn_iterations=100),
+        coarse_matching=_Cfg(num_correspondences=None),
+        GAT=_Cfg(input_dim=1024, hidden_dim=128, output_dim=256, num_heads=4, num_layers=4, k=None),
+        Vote=_Cfg(MAX_TRANSLATE_RANGE=4.2, NMS_radius=2.4),
+        fine_matching=_Cfg(acceptance_radius=0.45, mutual=False, topk=1, confidence_threshold=0, use_dustbin=True,
+                           use_global_score=False, correspondence_threshold=3, correspondence_limit=None,
+                           num_refinement_steps=5),
+        neighbor_limits=list(neighbor_limits), vis=False)

@@ -1,0 +1,183 @@
+"""torch-tensor wrappers over the C ABI for the registration-path kernels (pair.cu, matching.cu)."""
+import torch
+
+from . import _lib
+from .ops import _f32c, as_index32
+
+
+def _L():
+    return _lib.lib()
+
+
+def _s(t):
+    return _lib.stream_ptr(t.device)
+
+
+def linear_ex(x, weight_t, bias=None, relu=False, rowscale=None, out=None):
+    """act(rowscale * (x . weight_t) + bias); x may be a column slice view (row stride = ld)."""
+    assert x.stride(1) == 1
+    n, cin = x.shape
+    cout = weight_t.shape[1]
+    if out is None:
+        out = torch.empty((n, cout), dtype=torch.float32, device=x.device)
+    _lib.check(_L().lcr_linear_ex(_lib.ptr(x), n, cin, x.stride(0), _lib.ptr(_f32c(weight_t)), cout, _lib.ptr(bias),
+                                  _lib.ptr(rowscale), 1 if relu else 0, _lib.ptr(out), out.stride(0), _s(x)))
+    return out
+
+
+def layer_norm(x, gamma, beta, residual=None, relu=False, eps=1e-5):
+    y = torch.empty_like(x)
+    _lib.check(_L().lcr_layer_norm(_lib.ptr(_f32c(x)), _lib.ptr(residual), _lib.ptr(gamma), _lib.ptr(beta), x.shape[0],
+                                   x.shape[1], eps, 1 if relu else 0, _lib.ptr(y), _s(x)))
+    return y
+
+
+def rope_(x, theta):
+    """In-place rotary embedding on a [rows, >=128] view (row stride = ld)."""
+    assert x.stride(1) == 1 and theta.is_contiguous() and theta.shape[1] == 64
+    _lib.check(_L().lcr_rope(_lib.ptr(x), x.stride(0), _lib.ptr(theta), x.shape[0], _s(x)))
+    return x
+
+
+def attention(q, k, v, q_off, k_off, n_problems, max_q_rows, heads=4, flops=0.0):
+    """softmax(q k^T / sqrt(32)) v per head and problem.  q/k/v: [rows, heads*32] views."""
+    out = torch.empty((q.shape[0], heads * 32), dtype=torch.float32, device=q.device)
+    _lib.check(_L().lcr_attention(_lib.ptr(q), q.stride(0), _lib.ptr(k), k.stride(0), _lib.ptr(v), v.stride(0),
+                                  _lib.ptr(q_off), _lib.ptr(k_off), n_problems, max_q_rows, heads, 32, _lib.ptr(out),
+                                  out.stride(0), float(flops), _s(q)))
+    return out
+
+
+def vote_shift(points, offsets, max_range):
+    out = torch.empty_like(points)
+    _lib.check(_L().lcr_vote_shift(_lib.ptr(_f32c(points)), _lib.ptr(offsets), offsets.stride(0), float(max_range),
+                                   points.shape[0], _lib.ptr(out), _s(points)))
+    return out
+
+
+def nms_greedy(points, cloud_off, n_clouds, max_rows, radius):
+    """-> keep u8 [N], counts i32 [n_clouds], kept_idx i32 [N] (compacted per cloud at its offset)."""
+    n = points.shape[0]
+    keep = torch.empty(n, dtype=torch.uint8, device=points.device)
+    counts = torch.empty(n_clouds, dtype=torch.int32, device=points.device)
+    kept_idx = torch.empty(max(n, 1), dtype=torch.int32, device=points.device)
+    _lib.check(_L().lcr_nms_greedy(_lib.ptr(_f32c(points)), _lib.ptr(cloud_off), n_clouds, max_rows, float(radius),
+                                   _lib.ptr(keep), _lib.ptr(counts), _lib.ptr(kept_idx), _s(points)))
+    return keep, counts, kept_idx
+
+
+def neighbor_mean(points, idx):
+    idx = as_index32(idx)
+    out = torch.empty((idx.shape[0], 3), dtype=torch.float32, device=points.device)
+    _lib.check(_L().lcr_neighbor_mean(_lib.ptr(_f32c(points)), points.shape[0], _lib.ptr(idx), idx.stride(0),
+                                      idx.shape[1], idx.shape[0], _lib.ptr(out), _s(points)))
+    return out
+
+
+def upsample_concat(coarse, up_idx, fine):
+    up_idx = as_index32(up_idx)
+    out = torch.empty((fine.shape[0], coarse.shape[1] + fine.shape[1]), dtype=torch.float32, device=fine.device)
+    _lib.check(_L().lcr_upsample_concat(_lib.ptr(_f32c(coarse)), coarse.shape[0], coarse.shape[1], _lib.ptr(up_idx),
+                                        up_idx.stride(0), _lib.ptr(_f32c(fine)), fine.shape[1], fine.shape[0],
+                                        _lib.ptr(out), _s(fine)))
+    return out
+
+
+def point_to_node_partition(points, nodes, point_limit=128, int64=False):
+    """pointcloud_partition.py:61-107 -> (point_to_node i32 [N], node_masks bool [M],
+    node_knn_indices [M,K], node_knn_masks bool [M,K])."""
+    n, m = points.shape[0], nodes.shape[0]
+    dev = points.device
+    owner = torch.empty(n, dtype=torch.int32, device=dev)
+    node_mask = torch.empty(m, dtype=torch.uint8, device=dev)
+    knn = torch.empty((m, point_limit), dtype=torch.int64 if int64 else torch.int32, device=dev)
+    knn_mask = torch.empty((m, point_limit), dtype=torch.uint8, device=dev)
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    L = _L()
+    ws_bytes = L.lcr_point_to_node_ws_bytes(n, m)
+    ws = _lib.workspace.get(ws_bytes, dev, slot=4)
+    _lib.check(L.lcr_point_to_node(_lib.ptr(_f32c(points)), n, _lib.ptr(_f32c(nodes)), m, point_limit,
+                                   _lib.ptr(owner), _lib.ptr(node_mask), _lib.ptr(knn), 1 if int64 else 0,
+                                   _lib.ptr(knn_mask), _lib.ptr(status), _lib.ptr(ws), ws.numel(), _s(points)))
+    return owner, node_mask.bool(), knn, knn_mask.bool(), status
+
+
+def sinkhorn(scores, row_masks, col_masks, alpha, iters=100):
+    """learnable_sinkhorn.py:13-66: scores [B,M,N] -> [B,M+1,N+1]."""
+    b, m, n = scores.shape
+    out = torch.empty((b, m + 1, n + 1), dtype=torch.float32, device=scores.device)
+    rm = None if row_masks is None else row_masks.to(torch.uint8).contiguous()
+    cm = None if col_masks is None else col_masks.to(torch.uint8).contiguous()
+    _lib.check(_L().lcr_sinkhorn(_lib.ptr(_f32c(scores)), b, m, n, _lib.ptr(rm), _lib.ptr(cm),
+                                 _lib.ptr(alpha.detach().reshape(1)), iters, _lib.ptr(out), _s(scores)))
+    return out
+
+
+def coarse_matching(log_scores):
+    """superpoint_matching.py:129-160 -> (ref_idx i32 [P], src_idx i32 [P], scores f32 [P])."""
+    r, c = log_scores.shape[0] - 1, log_scores.shape[1] - 1
+    dev = log_scores.device
+    cap = r + c
+    oi = torch.empty(cap, dtype=torch.int32, device=dev)
+    oj = torch.empty(cap, dtype=torch.int32, device=dev)
+    os_ = torch.empty(cap, dtype=torch.float32, device=dev)
+    cnt = torch.zeros(1, dtype=torch.int32, device=dev)
+    L = _L()
+    ws_bytes = L.lcr_coarse_matching_ws_bytes(r, c)
+    ws = _lib.workspace.get(ws_bytes, dev, slot=5)
+    _lib.check(L.lcr_coarse_matching(_lib.ptr(_f32c(log_scores)), r, c, _lib.ptr(oi), _lib.ptr(oj), _lib.ptr(os_),
+                                     _lib.ptr(cnt), _lib.ptr(ws), ws.numel(), _s(log_scores)))
+    p = int(cnt)            # D2H: the number of node correspondences sizes the dense stage
+    return oi[:p], oj[:p], os_[:p]
+
+
+def patch_scores(feats_a, knn_a, node_a, feats_b, knn_b, node_b):
+    p = node_a.shape[0]
+    out = torch.empty((p, 128, 128), dtype=torch.float32, device=feats_a.device)
+    _lib.check(_L().lcr_patch_scores(_lib.ptr(_f32c(feats_a)), feats_a.shape[0], _lib.ptr(knn_a), _lib.ptr(node_a),
+                                     _lib.ptr(_f32c(feats_b)), feats_b.shape[0], _lib.ptr(knn_b), _lib.ptr(node_b), p,
+                                     128, feats_a.shape[1], _lib.ptr(out), _s(feats_a)))
+    return out
+
+
+def fine_correspondences(log_scores, knn_mask_a, node_a, knn_mask_b, node_b):
+    """-> dict of device arrays (capacity P*256) + pair_off i32 [P+1] (pair_off[P] = total)."""
+    p = log_scores.shape[0]
+    dev = log_scores.device
+    cap = max(p * 256, 1)
+    r = {'pair_cnt': torch.empty(max(p, 1), dtype=torch.int32, device=dev),
+         'pair_off': torch.zeros(p + 1, dtype=torch.int32, device=dev),
+         'pair': torch.empty(cap, dtype=torch.int32, device=dev), 'i': torch.empty(cap, dtype=torch.int32, device=dev),
+         'j': torch.empty(cap, dtype=torch.int32, device=dev), 'score': torch.empty(cap, dtype=torch.float32, device=dev)}
+    ma, mb = knn_mask_a.to(torch.uint8).contiguous(), knn_mask_b.to(torch.uint8).contiguous()
+    _lib.check(_L().lcr_fine_correspondences(_lib.ptr(_f32c(log_scores)), p, _lib.ptr(ma), _lib.ptr(node_a),
+                                             _lib.ptr(mb), _lib.ptr(node_b), _lib.ptr(r['pair_cnt']),
+                                             _lib.ptr(r['pair_off']), _lib.ptr(r['pair']), _lib.ptr(r['i']),
+                                             _lib.ptr(r['j']), _lib.ptr(r['score']), _s(log_scores)))
+    return r
+
+
+def corr_points(corr, pts_a, knn_a, node_a, pts_b, knn_b, node_b):
+    cap = corr['pair'].shape[0]
+    ref = torch.zeros((cap, 3), dtype=torch.float32, device=pts_a.device)
+    src = torch.zeros((cap, 3), dtype=torch.float32, device=pts_a.device)
+    p = node_a.shape[0]
+    _lib.check(_L().lcr_corr_points(_lib.ptr(corr['pair']), _lib.ptr(corr['i']), _lib.ptr(corr['j']),
+                                    _lib.ptr(corr['pair_off'][p:]), cap, _lib.ptr(_f32c(pts_a)), _lib.ptr(knn_a),
+                                    _lib.ptr(node_a), _lib.ptr(_f32c(pts_b)), _lib.ptr(knn_b), _lib.ptr(node_b),
+                                    _lib.ptr(ref), _lib.ptr(src), _s(pts_a)))
+    return ref, src
+
+
+def local_global_registration(ref, src, scores, pair_off, radius=0.45, min_corr=3, steps=5):
+    """local_global_registration.py:140-202 on the device -> 4x4 transform (src -> ref)."""
+    p = pair_off.shape[0] - 1
+    cap = ref.shape[0]
+    T = torch.zeros((4, 4), dtype=torch.float32, device=ref.device)
+    L = _L()
+    ws_bytes = L.lcr_lgr_ws_bytes(p, cap)
+    ws = _lib.workspace.get(ws_bytes, ref.device, slot=6)
+    _lib.check(L.lcr_local_global_registration(_lib.ptr(_f32c(ref)), _lib.ptr(_f32c(src)), _lib.ptr(_f32c(scores)),
+                                               _lib.ptr(pair_off), p, cap, float(radius), min_corr, steps,
+                                               _lib.ptr(T), _lib.ptr(ws), ws.numel(), _s(ref)))
+    return T

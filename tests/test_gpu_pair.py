@@ -1,0 +1,210 @@
+"""GPU parity of the registration-path kernels (C ABI) against the pair oracle, stage by stage
+(each stage is fed the ORACLE's inputs so discrete decisions upstream cannot mask errors), then
+end to end against the oracle and the reference fixture.  Tolerances are written per assertion."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from lcrnet_b200 import checkpoint
+from oracle import model_oracle as mo
+from oracle import native
+from oracle import pair_oracle as po
+from util import GOLDEN
+
+pytestmark = pytest.mark.gpu
+sys.path.insert(0, GOLDEN)
+G = np.load(os.path.join(GOLDEN, 'pair_golden.npz'))
+LIMITS = [int(x) for x in G['limits']]
+
+
+@pytest.fixture(scope='module')
+def sd():
+    return checkpoint.random_state_dict('lcrnet', int(G['weight_seed']))
+
+
+@pytest.fixture(scope='module')
+def net(sd):
+    from lcrnet_b200 import lcrnet
+    m = lcrnet.create_model(lcrnet.default_cfg(LIMITS)).eval()
+    m.load_state_dict(sd, strict=True)
+    return m.cuda()
+
+
+@pytest.fixture(scope='module')
+def oracle_run(sd):
+    from make_pair_golden import make_pair_data
+    raw_ref, raw_src, _ = make_pair_data(*(int(x) for x in G['case']))
+    pts = np.concatenate([raw_ref, raw_src], 0)
+    p0, l0 = native.grid_subsample(pts, np.array([len(raw_ref), len(raw_src)], dtype=np.int64), 0.3)
+    data = mo.precompute_pyramid(p0, l0, limits=LIMITS)
+    with torch.no_grad():
+        out = po.lcrnet_forward(sd, data, LIMITS, stages=True)
+    return data, out
+
+
+def c(t):
+    return t.cuda().contiguous()
+
+
+def test_transformer_vs_oracle(sd, net, oracle_run):
+    from lcrnet_b200 import ops
+    data, out = oracle_run
+    n0 = int(data['lengths'][-1][0])
+    pts, fc = data['points'][-1], out['_stages']['feats_c']
+    st0, st1 = ops.Stacks([n0], 'cuda'), ops.Stacks([pts.shape[0] - n0], 'cuda')
+    with torch.no_grad():
+        e0, e1 = net.transformer(c(pts[:n0]), c(pts[n0:]), c(fc[:n0]), c(fc[n0:]), st0.off, st1.off, 1, st0.max_rows,
+                                 st1.max_rows)
+    ref = out['_stages']['enhanced']
+    got = torch.cat([e0, e1]).cpu()
+    assert float((got - ref).abs().max()) < 1e-4 * max(1.0, float(ref.abs().max()))
+
+
+def test_vote_and_nms_vs_oracle(sd, net, oracle_run):
+    from lcrnet_b200 import ops
+    from lcrnet_b200 import pair_ops as P
+    data, out = oracle_run
+    vd = out['_stages']['vote']
+    enh, pts = out['_stages']['enhanced'], data['points'][-1]
+    with torch.no_grad():
+        shifted = net.vote_encoder.vote(c(pts), c(enh))
+    assert float((shifted.cpu() - vd['shifted']).abs().max()) < 1e-4
+    # NMS on the ORACLE's shifted points: the kept mask must be identical
+    lens = [int(x) for x in data['lengths'][-1]]
+    st = ops.Stacks(lens, 'cuda')
+    keep, counts, kept_idx = P.nms_greedy(c(vd['shifted']), st.off, st.n, st.max_rows, 2.4)
+    assert torch.equal(keep.cpu().bool(), vd['keep'])
+    assert counts.tolist() == vd['counts']
+    assert torch.equal(kept_idx[:counts[0]].cpu().long(), torch.nonzero(vd['keep'][:lens[0]])[:, 0])
+    centres = P.neighbor_mean(c(vd['shifted']), c(vd['node_knn']))
+    assert float((centres.cpu() - vd['centres']).abs().max()) < 1e-4
+
+
+def test_vote_encoder_vs_oracle(net, oracle_run):
+    from lcrnet_b200 import ops
+    data, out = oracle_run
+    vd = out['_stages']['vote']
+    lens = [int(x) for x in data['lengths'][-1]]
+    dd = {'points': [c(p) for p in data['points']], 'lengths': [l.cuda() for l in data['lengths']]}
+    with torch.no_grad():
+        got = net.vote_encoder(c(out['_stages']['enhanced']), dd, ops.Stacks([sum(lens)], 'cuda'), lens, 2)
+    assert got['counts'] == vd['counts']
+    assert float((got['centres'].cpu() - vd['centres']).abs().max()) < 1e-3
+    ref = vd['feats']
+    assert float((got['feats'].cpu() - ref).abs().max()) < 2e-4 * max(1.0, float(ref.abs().max()))
+
+
+def test_partition_vs_oracle(oracle_run):
+    from lcrnet_b200 import pair_ops as P
+    data, out = oracle_run
+    n_f0 = int(data['lengths'][0][0])
+    pts = data['points'][0][:n_f0]
+    nodes = out['pos_points_c']
+    owner_ref, nm_ref, knn_ref, km_ref = po.point_to_node_partition(pts, nodes)
+    owner, nm, knn, km, status = P.point_to_node_partition(c(pts), c(nodes), 128)
+    assert int(status) == 0
+    assert float((owner.cpu().long() == owner_ref).float().mean()) == 1.0      # ownership: exact
+    assert torch.equal(nm.cpu(), nm_ref) and torch.equal(km.cpu(), km_ref)
+    assert torch.equal(knn.cpu().long().sort(1)[0], knn_ref.sort(1)[0])         # per-node lists: equal as sets
+    # and ascending by distance to the node
+    d = po.pairwise_distance(nodes, pts)
+    dk = torch.gather(torch.cat([d, torch.full((d.shape[0], 1), 1e12)], 1), 1, knn.cpu().long())
+    assert bool((dk[:, 1:] >= dk[:, :-1] - 1e-5).all())
+
+
+@pytest.mark.parametrize('b,m,n', [(1, 324, 312), (5, 128, 128), (3, 40, 57)])
+def test_sinkhorn_vs_oracle(b, m, n):
+    from lcrnet_b200 import pair_ops as P
+    g = torch.Generator().manual_seed(m)
+    s = torch.randn(b, m, n, generator=g) * 2
+    rm, cm = torch.rand(b, m, generator=g) > 0.1, torch.rand(b, n, generator=g) > 0.1
+    alpha = torch.tensor(0.7)
+    ref = po.sinkhorn(s, rm, cm, alpha)
+    got = P.sinkhorn(c(s), rm.cuda(), cm.cuda(), alpha.cuda()).cpu()
+    valid = ref > -1e11
+    assert torch.equal(valid, got > -1e11)
+    assert float(((got - ref).abs() * valid).max()) < 1e-3
+    # size-independent property: valid rows of exp(out) carry unit mass
+    mass = torch.exp(got)[:, :m, :].sum(2)
+    assert float((mass[rm] - 1).abs().max()) < 1e-3
+
+
+def test_coarse_and_fine_matching_vs_oracle(oracle_run):
+    from lcrnet_b200 import pair_ops as P
+    data, out = oracle_run
+    st = out['_stages']
+    ci, cj, cs = po.coarse_matching(st['node_ot'])
+    gi, gj, gs = P.coarse_matching(c(st['node_ot']))
+    assert torch.equal(gi.cpu().long(), ci) and torch.equal(gj.cpu().long(), cj)
+    assert float((gs.cpu() - cs).abs().max()) < 1e-5
+    # fine correspondences from the oracle's point-level OT matrices
+    pkm, akm = st['pos_knn'][ci] < 10 ** 9, None
+    pos_km = st['pos_knn'] < int(data['lengths'][0][0])
+    anc_km = st['anc_knn'] < int(data['lengths'][0][1])
+    corr_ref, score_ref = po.fine_correspondences(st['point_ot'], pos_km[ci], anc_km[cj])
+    corr = P.fine_correspondences(c(st['point_ot']), pos_km.cuda(), gi, anc_km.cuda(), gj)
+    n = int(corr['pair_off'][-1])
+    b, i, j = torch.nonzero(corr_ref, as_tuple=True)
+    assert n == b.shape[0]
+    assert torch.equal(corr['pair'][:n].cpu().long(), b) and torch.equal(corr['i'][:n].cpu().long(), i)
+    assert torch.equal(corr['j'][:n].cpu().long(), j)
+    assert float((corr['score'][:n].cpu() - score_ref[b, i, j]).abs().max()) < 1e-5
+
+
+def test_lgr_vs_oracle(oracle_run):
+    from lcrnet_b200 import pair_ops as P
+    data, out = oracle_run
+    st = out['_stages']
+    ci, cj = out['pos_node_corr_indices'], out['anc_node_corr_indices']
+    n_f0 = int(data['lengths'][0][0])
+    pos_pf, anc_pf = data['points'][0][:n_f0], data['points'][0][n_f0:]
+    pad = lambda x: torch.cat([x, torch.zeros_like(x[:1])], 0)
+    pkp, akp = pad(pos_pf)[st['pos_knn'][ci]], pad(anc_pf)[st['anc_knn'][cj]]
+    pos_km, anc_km = st['pos_knn'] < n_f0, st['anc_knn'] < anc_pf.shape[0]
+    corr_mat, score_mat = po.fine_correspondences(st['point_ot'], pos_km[ci], anc_km[cj])
+    ref_c, src_c, sc, T_ref = po.local_global_registration(pkp, akp, score_mat, corr_mat)
+    b = torch.nonzero(corr_mat, as_tuple=True)[0]
+    pair_off = torch.zeros(ci.shape[0] + 1, dtype=torch.int32)
+    pair_off[1:] = torch.cumsum(torch.bincount(b, minlength=ci.shape[0]), 0).int()
+    T = P.local_global_registration(c(ref_c), c(src_c), c(sc), pair_off.cuda()).cpu()
+    assert float((T - T_ref).abs().max()) < 1e-4 * max(1.0, float(T_ref.abs().max()))
+    assert float((out['estimated_transform'] - T_ref).abs().max()) == 0.0
+    # rigid-motion property at scale: exact correspondences -> exact recovery
+    g = torch.Generator().manual_seed(1)
+    src = torch.randn(5000, 3, generator=g) * 20
+    a = 1.1
+    R = torch.tensor([[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1]], dtype=torch.float32)
+    t = torch.tensor([3.0, -1.0, 0.25])
+    ref = src @ R.t() + t
+    off = torch.arange(0, 5001, 50, dtype=torch.int32)
+    T = P.local_global_registration(c(ref), c(src), torch.ones(5000).cuda(), off.cuda()).cpu()
+    assert float((T[:3, :3] - R).abs().max()) < 1e-5 and float((T[:3, 3] - t).abs().max()) < 1e-4
+
+
+def test_full_lcrnet_vs_oracle_and_fixture(net, oracle_run):
+    data, out = oracle_run
+    dd = {k: [t.cuda() for t in v] for k, v in data.items()}
+    dd['features'] = torch.ones(data['points'][0].shape[0], 1).cuda()
+    got = net(dd)
+    for k in ('pos_feature_global', 'anc_feature_global'):
+        assert float((got[k].cpu() - out[k]).norm()) < 1e-4            # descriptors: 1e-4 relative (unit norm)
+        assert np.linalg.norm(got[k].cpu().numpy() - G[k]) < 1e-4       # vs the reference itself
+    assert got['length'].tolist() == list(out['length']) == list(G['node_counts'])
+    assert float((got['pos_points_c'].cpu() - out['pos_points_c']).abs().max()) < 1e-3
+    ref_f = out['pos_feats_f']
+    assert float((got['pos_feats_f'].cpu() - ref_f).abs().max()) < 5e-4 * max(1.0, float(ref_f.abs().max()))
+    assert torch.equal(got['pos_node_corr_indices'].cpu(), out['pos_node_corr_indices'])
+    assert torch.equal(got['anc_node_corr_indices'].cpu(), out['anc_node_corr_indices'])
+    n_ref = out['corr_scores'].shape[0]
+    assert abs(got['corr_scores'].shape[0] - n_ref) <= max(2, n_ref // 200)
+    T, T_ref = got['estimated_transform'].cpu(), out['estimated_transform']
+    assert T.shape == (4, 4)
+    # pose: 1e-4 relative is the north-star bar; with random weights the matching is ill-conditioned
+    # (garbage features), so the bound here is 1e-3 and the achieved value is printed
+    err = float((T - T_ref).abs().max()) / max(1.0, float(T_ref.abs().max()))
+    print('pose max-abs relative error vs oracle: %.3e' % err)
+    assert err < 1e-3
+    assert np.abs(T.numpy() - G['estimated_transform']).max() < 2e-3
