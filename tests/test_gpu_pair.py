@@ -202,9 +202,8 @@ def test_full_lcrnet_vs_oracle_and_fixture(net, oracle_run):
     assert abs(got['corr_scores'].shape[0] - n_ref) <= max(2, n_ref // 200)
     T, T_ref = got['estimated_transform'].cpu(), out['estimated_transform']
     assert T.shape == (4, 4)
-    # pose: 1e-4 relative is the north-star bar; with random weights the matching is ill-conditioned
-    # (garbage features), so the bound here is 1e-3 and the achieved value is printed
+    # pose: the north-star bar is 1e-4 relative (measured on B200: 9.1e-6 vs the oracle)
     err = float((T - T_ref).abs().max()) / max(1.0, float(T_ref.abs().max()))
     print('pose max-abs relative error vs oracle: %.3e' % err)
-    assert err < 1e-3
-    assert np.abs(T.numpy() - G['estimated_transform']).max() < 2e-3
+    assert err < 1e-4
+    assert np.abs(T.numpy() - G['estimated_transform']).max() < 1e-3     # vs the reference (oracle: < 1e-3)
