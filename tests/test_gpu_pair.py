@@ -207,3 +207,43 @@ def test_full_lcrnet_vs_oracle_and_fixture(net, oracle_run):
     print('pose max-abs relative error vs oracle: %.3e' % err)
     assert err < 1e-4
     assert np.abs(T.numpy() - G['estimated_transform']).max() < 1e-3     # vs the reference (oracle: < 1e-3)
+
+
+def test_demo_pair_and_batched_pairs(net):
+    """demo flow on a synthetic pair; two pairs in one forward == one pair per forward (the
+    reference semantics); the estimated transform is a proper rigid motion."""
+    from lcrnet_b200 import data as gdata
+    from lcrnet_b200 import synth
+    pairs = []
+    for s in (5, 6):
+        ref, src, _ = synth.make_pair(s, 100 + s)
+        pairs += [np.ascontiguousarray(ref[::6]), np.ascontiguousarray(src[::6])]
+    mk = lambda scans: gdata.scans_collate_fn_stack_mode(scans, 4, 0.3, 1.275, LIMITS, pre_voxel=0.3, stack_size=2,
+                                                         int32=True, upsampling=True)
+    both = net(mk(pairs))
+    assert both['estimated_transform'].shape == (2, 4, 4)
+    for p in range(2):
+        one = net(mk(pairs[2 * p:2 * p + 2]))
+        T1, T2 = one['estimated_transform'].cpu(), both['estimated_transform'][p].cpu()
+        assert float((T1 - T2).abs().max()) < 1e-4 * max(1.0, float(T1.abs().max()))
+        assert float((one['pos_feature_global'] - both['pos_feature_global'][p]).norm()) < 1e-5
+        R = T1[:3, :3].double()
+        assert float((R @ R.t() - torch.eye(3, dtype=torch.float64)).abs().max()) < 1e-5
+        assert abs(float(torch.det(R)) - 1.0) < 1e-5
+        assert one['corr_scores'].shape[0] == both['corr_scores'][p].shape[0]
+
+
+def test_loop_candidates_vs_oracle():
+    from lcrnet_b200 import retrieval
+    rng = np.random.default_rng(4)
+    db = rng.standard_normal((400, 256)).astype(np.float32)
+    db /= np.linalg.norm(db, axis=1, keepdims=True)
+    rows = retrieval.loop_candidates(torch.from_numpy(db).cuda(), k=50, gap=100)
+    q_ids = np.arange(101, 399)
+    d2, idx = mo.l2_topk(db[q_ids], db, 50, valid_counts=retrieval.causal_valid_counts(q_ids))
+    n_ref = int((idx >= 0).sum())
+    assert rows.shape == (n_ref, 3)
+    assert (rows[:, 0] - rows[:, 1] >= 100).all()
+    # top-1 of every query agrees (descriptor distances are well separated)
+    first = {int(i): int(j) for i, j, _ in rows[::-1]}
+    assert all(first[int(q)] == int(idx[n, 0]) for n, q in enumerate(q_ids))
