@@ -89,13 +89,14 @@ int lcr_radius_neighbors(const float* q_points, int64_t nq_total, const float* s
  * (first H columns used, pad = n_support), kernel_points[15,3], weights[15, c_in, c_out],
  * bias[c_out] or NULL -> out[m_query, c_out].  s_flags[n_support] (u8, optional): 1 where the
  * feature row sum is > 0 (the reference's neighbour_num counts only those rows, :113-116);
- * NULL counts every valid neighbour.  c_in in {1, 32, 64, 128, 256}.
+ * NULL counts every valid neighbour.  c_in in {1, 32, 64, 128, 256}.  weights_nk (optional): the same
+ * weights transposed to [c_out, 15 * c_in]; when given, the contraction runs on the tcgen05 3xTF32 GEMM.
  * ---------------------------------------------------------------------------------------- */
 size_t lcr_kpconv_ws_bytes(int64_t m_query, int c_in);
 int lcr_kpconv(const float* s_feats, const uint8_t* s_flags, int64_t n_support, const float* q_points,
                int64_t m_query, const float* s_points, const int32_t* idx, int ld_idx, int H,
-               const float* kernel_points, float sigma, const float* weights, const float* bias, int c_in,
-               int c_out, float* out, void* ws, size_t ws_bytes, void* stream);
+               const float* kernel_points, float sigma, const float* weights, const float* weights_nk,
+               const float* bias, int c_in, int c_out, float* out, void* ws, size_t ws_bytes, void* stream);
 /* flags[r] = (sum_c x[r, c] > 0) */
 int lcr_row_flags(const float* x, int64_t rows, int channels, uint8_t* flags, void* stream);
 
@@ -151,6 +152,12 @@ int lcr_l2_topk(const float* queries, int64_t n_queries, const float* db, int64_
 /* out = act(rowscale[m] * (x . weight_t) + bias): lcr_linear with leading dimensions, an optional
  * per-row scale and act in {0: none, 1: ReLU} (FFN of vanilla_transformer.py:22-28, vote MLP). */
 int lcr_linear_ex(const float* x, int64_t n_rows, int c_in, int ld_x, const float* weight_t, int c_out,
+                  const float* bias, const float* rowscale, int act, float* out, int ld_out, void* stream);
+
+/* Tensor-core variant of lcr_linear_ex (tcgen05.mma kind::tf32 with 3xTF32 operand splitting, fp32-class
+ * accuracy): `weight` is in nn.Linear layout [c_out, c_in] (no transpose).  Requires c_in % 32 == 0,
+ * c_out % 4 == 0. */
+int lcr_linear_tc(const float* x, int64_t n_rows, int c_in, int ld_x, const float* weight, int c_out, int ld_w,
                   const float* bias, const float* rowscale, int act, float* out, int ld_out, void* stream);
 
 /* ------------------------------------------------------------------------------------------

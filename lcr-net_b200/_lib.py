@@ -28,8 +28,8 @@ SIGNATURES = {
     'lcr_radius_neighbors': (c_i32, [c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_i32, c_f32, c_i32, c_vp, c_i32, c_vp,
                                      c_vp, c_vp, c_vp, c_sz, c_vp]),
     'lcr_kpconv_ws_bytes': (c_sz, [c_i64, c_i32]),
-    'lcr_kpconv': (c_i32, [c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_i32, c_i32, c_vp, c_f32, c_vp, c_vp, c_i32,
-                           c_i32, c_vp, c_vp, c_sz, c_vp]),
+    'lcr_kpconv': (c_i32, [c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_i32, c_i32, c_vp, c_f32, c_vp, c_vp, c_vp,
+                           c_i32, c_i32, c_vp, c_vp, c_sz, c_vp]),
     'lcr_row_flags': (c_i32, [c_vp, c_i64, c_i32, c_vp, c_vp]),
     'lcr_linear': (c_i32, [c_vp, c_i64, c_i32, c_vp, c_i32, c_vp, c_vp, c_vp]),
     'lcr_group_norm_ws_bytes': (c_sz, [c_i64, c_i32, c_i32]),
@@ -41,6 +41,7 @@ SIGNATURES = {
     'lcr_netvlad': (c_i32, [c_vp, c_i64, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_sz,
                             c_vp]),
     'lcr_linear_ex': (c_i32, [c_vp, c_i64, c_i32, c_i32, c_vp, c_i32, c_vp, c_vp, c_i32, c_vp, c_i32, c_vp]),
+    'lcr_linear_tc': (c_i32, [c_vp, c_i64, c_i32, c_i32, c_vp, c_i32, c_i32, c_vp, c_vp, c_i32, c_vp, c_i32, c_vp]),
     'lcr_layer_norm': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_f32, c_i32, c_vp, c_vp]),
     'lcr_rope': (c_i32, [c_vp, c_i32, c_vp, c_i64, c_vp]),
     'lcr_attention': (c_i32, [c_vp, c_i32, c_vp, c_i32, c_vp, c_i32, c_vp, c_vp, c_i32, c_i64, c_i32, c_i32, c_vp,

@@ -19,6 +19,8 @@
 
 int lcr_gemm_f32(const float* A, int lda, const float* B, int ldb, float* C, int ldc, int M, int N, int K,
                  const float* rowscale, const float* bias, cudaStream_t stream);
+int lcr_gemm_tf32x3(const float* A, int lda, const float* W, int ldw, float* C, int ldc, int M, int N, int K,
+                    const float* rowscale, const float* bias, int relu, cudaStream_t stream);
 
 namespace {
 
@@ -315,8 +317,9 @@ extern "C" size_t lcr_kpconv_ws_bytes(int64_t m_rows, int c_in) {
 
 extern "C" int lcr_kpconv(const float* s_feats, const uint8_t* s_flags, int64_t n_support, const float* q_points,
                           int64_t m_query, const float* s_points, const int32_t* idx, int ld_idx, int H,
-                          const float* kernel_points, float sigma, const float* weights, const float* bias, int c_in,
-                          int c_out, float* out, void* ws, size_t ws_bytes, void* stream_) {
+                          const float* kernel_points, float sigma, const float* weights, const float* weights_nk,
+                          const float* bias, int c_in, int c_out, float* out, void* ws, size_t ws_bytes,
+                          void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   LCR_REQUIRE(m_query >= 0 && n_support >= 0 && m_query < (1ll << 31) && n_support < (1ll << 31), "kpconv: sizes");
   LCR_REQUIRE(H >= 1 && ld_idx >= H, "kpconv: bad neighbour table width");
@@ -354,6 +357,9 @@ extern "C" int lcr_kpconv(const float* s_feats, const uint8_t* s_flags, int64_t 
   }
   LCR_LAUNCHED(1);
   LCR_CUDA_CHECK_LAUNCH();
+  if (weights_nk)  // tensor-core contraction: weights as [c_out, 15 * c_in]
+    return lcr_gemm_tf32x3(wf, KP * c_in, weights_nk, KP * c_in, out, c_out, M, c_out, KP * c_in, rowscale, bias, 0,
+                           stream);
   return lcr_gemm_f32(wf, KP * c_in, weights, c_out, out, c_out, M, c_out, KP * c_in, rowscale, bias, stream);
 }
 

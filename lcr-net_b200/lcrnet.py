@@ -42,14 +42,22 @@ class LinearT(nn.Linear):
         return self._cache[1], self._cache[2]
 
     def run(self, x, relu=False):
+        if self.in_features % 32 == 0 and self.out_features % 4 == 0 and ops.use_tensor_cores():
+            return P.linear_tc(x, self.weight, self.bias, relu=relu)
         wt, b = self.packed()
         return P.linear_ex(x, wt, b, relu=relu)
 
 
 def _fused(linears):
-    """[c_in, sum c_out] weight and bias of several Linear layers sharing an input."""
-    ws, bs = zip(*(l.packed() for l in linears))
-    return torch.cat(ws, 1).contiguous(), torch.cat(bs).contiguous()
+    """Several Linear layers sharing an input as one: weight [sum c_out, c_in] (nn.Linear layout) and bias."""
+    return (torch.cat([l.weight.detach() for l in linears], 0).contiguous(),
+            torch.cat([l.bias.detach() for l in linears]).contiguous())
+
+
+def _linear_nk(x, w_nk, b):
+    if ops.use_tensor_cores():
+        return P.linear_tc(x, w_nk, b)
+    return P.linear_ex(x, w_nk.t().contiguous(), b)
 
 
 # ------------------------------------------------------------------ transformer (parameter holders)
@@ -94,11 +102,11 @@ class _TransformerLayer(nn.Module):
         (w_qkv, b_qkv), (w_kv, b_kv) = mha.fused()
         d = x.shape[1]
         if mem is x:
-            qkv = P.linear_ex(x, w_qkv, b_qkv)
+            qkv = _linear_nk(x, w_qkv, b_qkv)
             q, k, v = qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:]
         else:
             q = mha.proj_q.run(x)
-            kv = P.linear_ex(mem, w_kv, b_kv)
+            kv = _linear_nk(mem, w_kv, b_kv)
             k, v = kv[:, :d], kv[:, d:]
         if theta_x is not None:
             P.rope_(q, theta_x)

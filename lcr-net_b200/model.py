@@ -34,10 +34,19 @@ class KPConv(nn.Module):
         else:
             self.register_parameter('bias', None)
         self.register_buffer('kernel_points', torch.zeros(kernel_size, 3))
+        self._w_nk = None
+
+    def weights_nk(self):
+        """[c_out, 15 * c_in] copy of the weights for the tensor-core contraction (cached)."""
+        w = self.weights
+        key = (w.data_ptr(), w._version)
+        if self._w_nk is None or self._w_nk[0] != key:
+            self._w_nk = (key, w.detach().reshape(-1, w.shape[2]).t().contiguous())
+        return self._w_nk[1]
 
     def forward(self, s_feats, q_points, s_points, neighbor_indices, s_flags=None):
         return ops.kpconv(s_feats, q_points, s_points, neighbor_indices, self.kernel_points, self.sigma,
-                          self.weights, self.bias, s_flags)
+                          self.weights, self.bias, s_flags, self.weights_nk() if self.in_channels > 1 else None)
 
 
 class GroupNorm(nn.Module):
@@ -74,7 +83,7 @@ class UnaryBlock(nn.Module):
         return self._wt[1]
 
     def linear(self, x):
-        return ops.linear(x, self.weight_t(), self.mlp.bias)
+        return ops.linear(x, self.weight_t(), self.mlp.bias, self.mlp.weight)
 
     def forward(self, x, stacks, want_flags=False):
         return self.norm(self.linear(x), stacks, leaky=self.has_relu, want_flags=want_flags)

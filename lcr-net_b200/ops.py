@@ -8,6 +8,13 @@ from . import _lib, ext
 GROUPS = 32
 
 
+def use_tensor_cores():
+    """GEMMs run on the tcgen05 3xTF32 kernel (gemm_tc.cu) unless LCR_GEMM=simt selects the fp32 SIMT
+    kernel (gemm.cu); both are fp32-accurate."""
+    import os
+    return os.environ.get('LCR_GEMM', 'tc') != 'simt'
+
+
 def grid_subsample(points, lengths, voxel_size, order='reference'):
     """ops/grid_subsample.py:7-22."""
     s_points, s_lengths = ext.grid_subsampling(points, lengths, voxel_size, order=order)
@@ -42,7 +49,7 @@ def row_flags(x):
     return flags
 
 
-def kpconv(s_feats, q_points, s_points, idx, kernel_points, sigma, weights, bias, s_flags=None):
+def kpconv(s_feats, q_points, s_points, idx, kernel_points, sigma, weights, bias, s_flags=None, weights_nk=None):
     """KPConv.forward (kpconv.py:79-122).  ``s_flags``: row-sum>0 flags of s_feats (computed if None)."""
     _lib.require_cuda(s_feats, q_points, s_points, idx)
     L = _lib.lib()
@@ -56,14 +63,23 @@ def kpconv(s_feats, q_points, s_points, idx, kernel_points, sigma, weights, bias
     ws = _lib.workspace.get(ws_bytes, s_feats.device, slot=1)
     _lib.check(L.lcr_kpconv(_lib.ptr(_f32c(s_feats)), _lib.ptr(s_flags), n, _lib.ptr(_f32c(q_points)), m,
                             _lib.ptr(_f32c(s_points)), _lib.ptr(idx), idx.stride(0), idx.shape[1],
-                            _lib.ptr(_f32c(kernel_points)), float(sigma), _lib.ptr(_f32c(weights)), _lib.ptr(bias),
-                            c_in, c_out, _lib.ptr(out), _lib.ptr(ws), ws.numel(), _lib.stream_ptr(s_feats.device)))
+                            _lib.ptr(_f32c(kernel_points)), float(sigma), _lib.ptr(_f32c(weights)),
+                            _lib.ptr(weights_nk if (weights_nk is not None and c_in > 1 and use_tensor_cores())
+                                     else None), _lib.ptr(bias), c_in, c_out, _lib.ptr(out), _lib.ptr(ws), ws.numel(), _lib.stream_ptr(s_feats.device)))
     return out
 
 
-def linear(x, weight_t, bias):
-    """nn.Linear with the weight pre-transposed to [c_in, c_out]."""
+def linear(x, weight_t, bias, weight_nk=None):
+    """nn.Linear: weight_t = weight transposed to [c_in, c_out] (SIMT kernel); weight_nk = the
+    nn.Linear layout [c_out, c_in] (tensor-core kernel, used when c_in % 32 == 0)."""
     _lib.require_cuda(x)
+    if weight_nk is not None and x.shape[1] % 32 == 0 and weight_nk.shape[0] % 4 == 0 and use_tensor_cores():
+        out = torch.empty((x.shape[0], weight_nk.shape[0]), dtype=torch.float32, device=x.device)
+        _lib.check(_lib.lib().lcr_linear_tc(_lib.ptr(_f32c(x)), x.shape[0], x.shape[1], x.stride(0),
+                                            _lib.ptr(_f32c(weight_nk)), weight_nk.shape[0], weight_nk.stride(0),
+                                            _lib.ptr(bias), None, 0, _lib.ptr(out), out.stride(0),
+                                            _lib.stream_ptr(x.device)))
+        return out
     out = torch.empty((x.shape[0], weight_t.shape[1]), dtype=torch.float32, device=x.device)
     _lib.check(_lib.lib().lcr_linear(_lib.ptr(_f32c(x)), x.shape[0], x.shape[1], _lib.ptr(_f32c(weight_t)),
                                      weight_t.shape[1], _lib.ptr(bias), _lib.ptr(out), _lib.stream_ptr(x.device)))

@@ -25,6 +25,19 @@ def linear_ex(x, weight_t, bias=None, relu=False, rowscale=None, out=None):
     return out
 
 
+def linear_tc(x, weight, bias=None, relu=False, rowscale=None, out=None):
+    """Tensor-core (tcgen05, 3xTF32) linear: weight in nn.Linear layout [c_out, c_in]."""
+    assert x.stride(1) == 1 and weight.stride(1) == 1
+    n, cin = x.shape
+    cout = weight.shape[0]
+    if out is None:
+        out = torch.empty((n, cout), dtype=torch.float32, device=x.device)
+    _lib.check(_L().lcr_linear_tc(_lib.ptr(x), n, cin, x.stride(0), _lib.ptr(weight), cout, weight.stride(0),
+                                  _lib.ptr(bias), _lib.ptr(rowscale), 1 if relu else 0, _lib.ptr(out), out.stride(0),
+                                  _s(x)))
+    return out
+
+
 def layer_norm(x, gamma, beta, residual=None, relu=False, eps=1e-5):
     y = torch.empty_like(x)
     _lib.check(_L().lcr_layer_norm(_lib.ptr(_f32c(x)), _lib.ptr(residual), _lib.ptr(gamma), _lib.ptr(beta), x.shape[0],

@@ -72,7 +72,13 @@ def test_kpconv_vs_oracle(c_in, c_out):
     ref = mo.kpconv(sdd, 'KPConv.', t(feats), t(q), t(s), t(idx), 1.2).numpy()
     got = ops.kpconv(t(feats).cuda(), t(q).cuda(), t(s).cuda(), t(idx).cuda(), t(kp).cuda(), 1.2, t(w).cuda(),
                      t(b).cuda()).cpu().numpy()
-    assert max_err(got, ref) < REL
+    assert max_err(got, ref) < REL                                   # fp32 SIMT contraction (gemm.cu)
+    if c_in > 1:                                                     # tcgen05 3xTF32 contraction (gemm_tc.cu)
+        w_nk = t(w).reshape(-1, c_out).t().contiguous().cuda()
+        got_tc = ops.kpconv(t(feats).cuda(), t(q).cuda(), t(s).cuda(), t(idx).cuda(), t(kp).cuda(), 1.2, t(w).cuda(),
+                            t(b).cuda(), weights_nk=w_nk).cpu().numpy()
+        assert max_err(got_tc, ref) < REL
+        assert max_err(got_tc, got) < 1e-5
 
 
 @pytest.mark.parametrize('c', [32, 64, 128, 256, 512, 1024])
