@@ -46,6 +46,10 @@ def parse():
     ap.add_argument('--cpu-pairs', type=int, default=1, help='pairs in the CPU baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--ncu', action='store_true', help='one warm-up step + one step only (for ncu captures)')
+    ap.add_argument('--workload', default='descriptor', choices=['descriptor', 'db', 'pairs'],
+                    help='descriptor: the headline line (configs[1]); db: descriptor-database build + all-gather + '
+                         'top-25 (configs[3]/[4]); pairs: full registration of scan pairs (configs[2])')
+    ap.add_argument('--db-scans', type=int, default=4000, help='db workload: scans per GPU')
     return ap.parse_args()
 
 
@@ -378,9 +382,139 @@ def dominant_kernel_roofline(step, pts, lens, flush):
             'share_of_step': ms / total_ms, 'kernel_groups': groups}
 
 
+def run_db(args):
+    """configs[3]/[4]: every rank builds the descriptors of its contiguous shard of `db_scans`
+    scans (a pool of 32 distinct synthetic scans cycled: descriptor cost does not depend on the
+    content), ONE all-gather assembles the database, then each rank answers its own shard's queries
+    with the brute-force L2 top-25 kernel.  One step = the whole build + search."""
+    import torch
+    import torch.distributed as dist
+    from lcrnet_b200 import _lib, checkpoint, model, retrieval
+    from lcrnet_b200 import data as gdata
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    net = model.create_model(model.default_cfg()).eval()
+    net.load_state_dict(checkpoint.random_state_dict('global_descriptor', 7351), strict=True)
+    net = net.to(dev)
+    pool = make_scans(16, rank)
+    limits = gdata.calibrate_neighbors_stack_mode(pool[:2], NUM_STAGES, VOXEL, RADIUS, pre_voxel=VOXEL, device=dev)
+    pts = torch.from_numpy(np.concatenate(pool, 0)).to(dev)
+    lens = torch.tensor([len(s) for s in pool], dtype=torch.int64, device=dev)
+    n_local, batch = args.db_scans, len(pool)
+    jitter = torch.linspace(0.0, 0.05, steps=(n_local + batch - 1) // batch, device=dev)
+
+    def step():
+        out = []
+        for b in range((n_local + batch - 1) // batch):
+            d = gdata.device_collate(pts + jitter[b], lens, NUM_STAGES, VOXEL, RADIUS, limits, pre_voxel=VOXEL,
+                                     stack_size=1, int32=True, upsampling=False)
+            out.append(net(d)['anc_global'])
+        local_db = torch.cat(out)[:n_local].contiguous()
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        db = retrieval.all_gather_descriptors(local_db)
+        ev2 = torch.cuda.Event(enable_timing=True)
+        ev2.record()
+        d2, idx = retrieval.search(local_db, db, k=25)
+        return db, idx, (ev, ev2)
+
+    step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    times, gather_ms, search_ms = [], [], []
+    for _ in range(args.steps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        db, idx, (g0, g1) = step()
+        b.record()
+        torch.cuda.synchronize()
+        times.append(a.elapsed_time(b))
+        gather_ms.append(g0.elapsed_time(g1))
+        search_ms.append(g1.elapsed_time(b))
+    # every query's nearest database row is itself (distance 0): index check across the gather
+    start, _ = retrieval.shard_range(n_local * world, rank, world)
+    ok = bool((idx[:, 0].cpu() == torch.arange(start, start + n_local)).float().mean() > 0.99)
+    total = sum(times)
+    if world > 1:
+        t = torch.tensor([total], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total = float(t)
+    if rank == 0:
+        n_all = n_local * world * args.steps
+        print(json.dumps({'metric': 'db_build_scans_per_sec', 'value': n_all / (total * 1e-3), 'unit': 'scans/s',
+                          'n_gpus': world, 'steps': args.steps, 'warmup': 1, 'ms_per_step': total / args.steps,
+                          'higher_is_better': True, 'scaling': 'weak', 'dtype': 'f32', 'data': 'synthetic',
+                          'config': {'workload': 'configs[%d]: %d-scan descriptor DB build sharded %d x B200, one '
+                                                 'all-gather, brute-force L2 top-25' % (3 if world == 1 else 4,
+                                                                                          n_local * world, world),
+                                     'scans_per_gpu': n_local, 'db_rows': n_local * world, 'k': 25},
+                          'all_gather_ms': float(np.mean(gather_ms)), 'topk_ms': float(np.mean(search_ms)),
+                          'all_gather_bytes': int(n_local * world * 256 * 4),
+                          'queries_per_sec': n_local * world / (float(np.mean(search_ms)) * 1e-3),
+                          'self_match_ok': ok}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_pairs(args):
+    """configs[2]: full registration (LCRNet: encoder, 3D-RoFormer, vote, matching, LGR) of a batch of
+    scan pairs per step; pairs/s."""
+    import torch
+    from lcrnet_b200 import checkpoint, lcrnet
+    from lcrnet_b200 import data as gdata
+    dev = torch.device('cuda', int(os.environ.get('LOCAL_RANK', '0')))
+    torch.cuda.set_device(dev)
+    scans = make_scans(args.pairs)
+    limits = gdata.calibrate_neighbors_stack_mode(scans[:2], NUM_STAGES, VOXEL, RADIUS, pre_voxel=VOXEL, device=dev)
+    net = lcrnet.create_model(lcrnet.default_cfg(limits)).eval()
+    net.load_state_dict(checkpoint.random_state_dict('lcrnet', 7351), strict=True)
+    net = net.to(dev)
+    pts = torch.from_numpy(np.concatenate(scans, 0)).to(dev)
+    lens = torch.tensor([len(s) for s in scans], dtype=torch.int64, device=dev)
+
+    def step():
+        d = gdata.device_collate(pts, lens, NUM_STAGES, VOXEL, RADIUS, limits, pre_voxel=VOXEL, stack_size=2,
+                                 int32=True, upsampling=True)
+        return net(d)
+
+    for _ in range(max(1, min(args.warmup, 2))):
+        out = step()
+    torch.cuda.synchronize()
+    times = []
+    for _ in range(args.steps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        out = step()
+        b.record()
+        torch.cuda.synchronize()
+        times.append(a.elapsed_time(b))
+    roof = dominant_kernel_roofline(lambda p, l: step(), pts, lens, torch.empty(1 << 20, dtype=torch.uint8, device=dev))
+    T = out['estimated_transform']
+    n_corr = [int(c.shape[0]) for c in out['corr_scores']] if isinstance(out['corr_scores'], list) else \
+        [int(out['corr_scores'].shape[0])]
+    print(json.dumps({'metric': 'registration_pairs_per_sec', 'value': args.pairs * args.steps / (sum(times) * 1e-3),
+                      'unit': 'pairs/s', 'n_gpus': 1, 'steps': args.steps, 'ms_per_step': sum(times) / args.steps,
+                      'higher_is_better': True, 'dtype': 'f32', 'data': 'synthetic',
+                      'config': {'workload': 'configs[2]: scan-pair registration (LCRNet full forward), batch %d pairs'
+                                             % args.pairs, 'neighbor_limits': limits,
+                                 'weights': 'seeded random: correspondences are not meaningful'},
+                      'mean_correspondences': float(np.mean(n_corr)), 'finite': bool(torch.isfinite(T).all()),
+                      'kernel_groups': roof['kernel_groups'] if roof else None}))
+
+
 if __name__ == '__main__':
     a = parse()
     if a.impl == 'reference':
         run_reference(a)
+    elif a.workload == 'db':
+        run_db(a)
+    elif a.workload == 'pairs':
+        run_pairs(a)
     else:
         run_b200(a)

@@ -162,6 +162,28 @@ gemm_tf32x3_kernel(const float* __restrict__ A, int lda, const float* __restrict
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       mbar_arrive(&acc_empty[b]);
     };
+    // global -> register prefetch one k-block ahead: the L2 latency of block kb+1 overlaps the
+    // split + shared-memory stores of block kb
+    constexpr int kALoads = BM * 8 / kProducerThreads, kBLoads = BN * 8 / kProducerThreads;
+    float4 ra[kALoads], rb[kBLoads];
+    auto load_block = [&](int kb) {
+      const int k0 = kb * BK;
+#pragma unroll
+      for (int i = 0; i < kALoads; i++) {
+        const int idx = tid + i * kProducerThreads;
+        const int gm = m0 + (idx >> 3);
+        ra[i] = gm < M ? *reinterpret_cast<const float4*>(A + (size_t)gm * lda + k0 + (idx & 7) * 4)
+                       : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int i = 0; i < kBLoads; i++) {
+        const int idx = tid + i * kProducerThreads;
+        const int gn = n0 + (idx >> 3);
+        rb[i] = gn < N ? *reinterpret_cast<const float4*>(W + (size_t)gn * ldw + k0 + (idx & 7) * 4)
+                       : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    load_block(0);
     for (int c = 0; c < n_chunks; c++) {
       // ---------------------------------------------------------- produce the chunk's k-blocks
       const int kb_end = min((c + 1) * CH, nk);
@@ -172,24 +194,21 @@ gemm_tf32x3_kernel(const float* __restrict__ A, int lda, const float* __restrict
         float* a_lo = a_hi + BM * BK;
         float* b_hi = a_lo + BM * BK;
         float* b_lo = b_hi + BN * BK;
-        const int k0 = kb * BK;
+        float4 ca[kALoads], cb[kBLoads];
 #pragma unroll
-        for (int i = 0; i < BM * 8 / kProducerThreads; i++) {
+        for (int i = 0; i < kALoads; i++) ca[i] = ra[i];
+#pragma unroll
+        for (int i = 0; i < kBLoads; i++) cb[i] = rb[i];
+        if (kb + 1 < nk) load_block(kb + 1);
+#pragma unroll
+        for (int i = 0; i < kALoads; i++) {
           const int idx = tid + i * kProducerThreads;
-          const int row = idx >> 3, chunk = idx & 7;
-          const int gm = m0 + row;
-          const float4 v = gm < M ? *reinterpret_cast<const float4*>(A + (size_t)gm * lda + k0 + chunk * 4)
-                                  : make_float4(0.f, 0.f, 0.f, 0.f);
-          split_store(v, a_hi, a_lo, row, chunk);
+          split_store(ca[i], a_hi, a_lo, idx >> 3, idx & 7);
         }
 #pragma unroll
-        for (int i = 0; i < BN * 8 / kProducerThreads; i++) {
+        for (int i = 0; i < kBLoads; i++) {
           const int idx = tid + i * kProducerThreads;
-          const int row = idx >> 3, chunk = idx & 7;
-          const int gn = n0 + row;
-          const float4 v = gn < N ? *reinterpret_cast<const float4*>(W + (size_t)gn * ldw + k0 + chunk * 4)
-                                  : make_float4(0.f, 0.f, 0.f, 0.f);
-          split_store(v, b_hi, b_lo, row, chunk);
+          split_store(cb[i], b_hi, b_lo, idx >> 3, idx & 7);
         }
         // make the generic-proxy writes visible to the tensor-core (async) proxy, then signal
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
