@@ -34,7 +34,9 @@ kpconv_gather_kernel(const float* __restrict__ s_feats, const float* __restrict_
                      const float* __restrict__ kpts, float sigma, const uint8_t* __restrict__ flags, int M,
                      int N, float* __restrict__ wf, float* __restrict__ rowscale) {
   constexpr int C = 32 * CPL;
-  __shared__ float s_w[4][KP][32];
+  // influences of 32 neighbours, packed as float4 groups of kernel points: [k/4][neighbour] so that
+  // lanes write conflict-free 16-B vectors and the accumulation loop reads 4 broadcast LDS.128
+  __shared__ __align__(16) float4 s_w[4][4][32];
   __shared__ int s_j[4][32];
   __shared__ float s_kp[KP * 3];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -54,35 +56,61 @@ kpconv_gather_kernel(const float* __restrict__ s_feats, const float* __restrict_
     const int h = h0 + lane;
     const int j = h < H ? row[h] : N;
     const bool valid = j < N;
+    // valid neighbours are compacted to the front (rows are sorted with the pads last, but holes are
+    // tolerated) so the accumulation loop below is a counted loop the compiler can software-pipeline
+    const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+    const int slot = __popc(vmask & ((1u << lane) - 1u));
+    const int nv = __popc(vmask);
     if (valid) {
       const float rx = s_pts[3 * (size_t)j] - qx, ry = s_pts[3 * (size_t)j + 1] - qy,
                   rz = s_pts[3 * (size_t)j + 2] - qz;
+      float w[16];
 #pragma unroll
       for (int k = 0; k < KP; k++) {
         const float dx = rx - s_kp[3 * k], dy = ry - s_kp[3 * k + 1], dz = rz - s_kp[3 * k + 2];
         const float d2 = dx * dx + dy * dy + dz * dz;
-        s_w[warp][k][lane] = fmaxf(1.f - __fdiv_rn(sqrtf(d2), sigma), 0.f);
+        w[k] = fmaxf(1.f - __fdiv_rn(sqrtf(d2), sigma), 0.f);
       }
+      w[15] = 0.f;
+#pragma unroll
+      for (int g = 0; g < 4; g++) s_w[warp][g][slot] = make_float4(w[4 * g], w[4 * g + 1], w[4 * g + 2], w[4 * g + 3]);
+      s_j[warp][slot] = j;
       cnt += flags ? (int)flags[j] : 1;
     }
-    s_j[warp][lane] = j;
-    const unsigned vmask = __ballot_sync(0xffffffffu, valid);
     __syncwarp();
-    // rows are sorted by distance with the pads last, but tolerate holes: iterate set bits
-    unsigned rem = vmask;
-    while (rem) {
-      const int hh = __ffs(rem) - 1;
-      rem &= rem - 1;
+    constexpr int UN = CPL >= 4 ? 2 : 4;  // neighbours whose feature rows are in flight together
+    int hh = 0;
+    for (; hh + UN <= nv; hh += UN) {
+      float fv[UN][CPL];
+#pragma unroll
+      for (int u = 0; u < UN; u++) {
+        const float* f = s_feats + (size_t)s_j[warp][hh + u] * C + lane;
+#pragma unroll
+        for (int i = 0; i < CPL; i++) fv[u][i] = f[32 * i];
+      }
+#pragma unroll
+      for (int u = 0; u < UN; u++) {
+        float w[16];
+#pragma unroll
+        for (int g = 0; g < 4; g++) *reinterpret_cast<float4*>(w + 4 * g) = s_w[warp][g][hh + u];
+#pragma unroll
+        for (int k = 0; k < KP; k++)
+#pragma unroll
+          for (int i = 0; i < CPL; i++) acc[k][i] = fmaf(w[k], fv[u][i], acc[k][i]);
+      }
+    }
+    for (; hh < nv; hh++) {
       const float* f = s_feats + (size_t)s_j[warp][hh] * C + lane;
       float fv[CPL];
 #pragma unroll
       for (int i = 0; i < CPL; i++) fv[i] = f[32 * i];
+      float w[16];
 #pragma unroll
-      for (int k = 0; k < KP; k++) {
-        const float w = s_w[warp][k][hh];
+      for (int g = 0; g < 4; g++) *reinterpret_cast<float4*>(w + 4 * g) = s_w[warp][g][hh];
 #pragma unroll
-        for (int i = 0; i < CPL; i++) acc[k][i] = fmaf(w, fv[i], acc[k][i]);
-      }
+      for (int k = 0; k < KP; k++)
+#pragma unroll
+        for (int i = 0; i < CPL; i++) acc[k][i] = fmaf(w[k], fv[i], acc[k][i]);
     }
     __syncwarp();
   }

@@ -147,8 +147,20 @@ struct SinkhornArgs {
   int M, N, iters;
 };
 
+// exp(x) on the SFU with a compensated argument: ex2.approx(x * log2e) loses |x| * 2^-24 in the
+// product; the FMA residual restores it, leaving the ~2 ulp of ex2.approx itself (the same order
+// as expf) at a quarter of the instructions.  Sinkhorn evaluates 2 * 129^2 * 100 of these per patch pair.
+__device__ __forceinline__ float sk_exp(float x) {
+  const float kL2E = 1.4426950408889634f, kL2E_lo = 1.925963033500011e-8f;
+  const float y = x * kL2E;
+  const float e = fmaf(x, kL2E_lo, fmaf(x, kL2E, -y));
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(y));
+  return fmaf(r, e * 0.6931471805599453f, r);
+}
+
 template <bool kSmem>
-__global__ void __launch_bounds__(512) sinkhorn_kernel(SinkhornArgs a) {
+__global__ void __launch_bounds__(kSmem ? 512 : 1024) sinkhorn_kernel(SinkhornArgs a) {
   extern __shared__ float sm[];
   const int R = a.M + 1, C = a.N + 1;
   float* u = sm;
@@ -199,6 +211,32 @@ __global__ void __launch_bounds__(512) sinkhorn_kernel(SinkhornArgs a) {
   }
   __syncthreads();
   for (int it = 0; it < a.iters; it++) {
+    if (kSmem) {
+      // matrix in shared memory: one THREAD per row / per column (no shuffle reductions; with the
+      // odd row length 129 both the row walk and the column walk are bank-conflict free)
+      for (int i = tid; i < R; i += nt) {
+        const float* row = S + (size_t)i * C;
+        float mx = -INFINITY;
+#pragma unroll 4
+        for (int j = 0; j < C; j++) mx = fmaxf(mx, row[j] + v[j]);
+        float sum = 0.f;
+#pragma unroll 4
+        for (int j = 0; j < C; j++) sum += sk_exp(row[j] + v[j] - mx);
+        u[i] = log_mu[i] - (mx + logf(sum));
+      }
+      __syncthreads();
+      for (int j = tid; j < C; j += nt) {
+        float mx = -INFINITY;
+#pragma unroll 4
+        for (int i = 0; i < R; i++) mx = fmaxf(mx, S[(size_t)i * C + j] + u[i]);
+        float sum = 0.f;
+#pragma unroll 4
+        for (int i = 0; i < R; i++) sum += sk_exp(S[(size_t)i * C + j] + u[i] - mx);
+        v[j] = log_nu[j] - (mx + logf(sum));
+      }
+      __syncthreads();
+      continue;
+    }
     // u = log_mu - logsumexp_j(S + v)
     for (int i = warp; i < R; i += nw) {
       const float* row = S + (size_t)i * C;
@@ -206,7 +244,7 @@ __global__ void __launch_bounds__(512) sinkhorn_kernel(SinkhornArgs a) {
       for (int j = lane; j < C; j += 32) mx = fmaxf(mx, row[j] + v[j]);
       mx = lcr_warp_max(mx);
       float sum = 0.f;
-      for (int j = lane; j < C; j += 32) sum += expf(row[j] + v[j] - mx);
+      for (int j = lane; j < C; j += 32) sum += sk_exp(row[j] + v[j] - mx);
       sum = lcr_warp_sum(sum);
       if (lane == 0) u[i] = log_mu[i] - (mx + logf(sum));
     }
@@ -218,16 +256,34 @@ __global__ void __launch_bounds__(512) sinkhorn_kernel(SinkhornArgs a) {
         for (int i = lane; i < R; i += 32) mx = fmaxf(mx, S[(size_t)i * C + j] + u[i]);
         mx = lcr_warp_max(mx);
         float sum = 0.f;
-        for (int i = lane; i < R; i += 32) sum += expf(S[(size_t)i * C + j] + u[i] - mx);
+        for (int i = lane; i < R; i += 32) sum += sk_exp(S[(size_t)i * C + j] + u[i] - mx);
         sum = lcr_warp_sum(sum);
         if (lane == 0) v[j] = log_nu[j] - (mx + logf(sum));
       }
     } else {
-      for (int j = tid; j < C; j += nt) {  // adjacent threads read adjacent columns: coalesced
+      // matrix in L2: warp w owns a slab of rows, lanes stride the columns (coalesced row
+      // segments, independent columns -> ILP); per-slab (max, sum-exp) partials are combined
+      // per column through shared memory
+      float* part_m = log_nu + C;
+      float* part_s = part_m + (size_t)nw * C;
+      const int rs = (R + nw - 1) / nw, r0 = warp * rs, r1 = min(r0 + rs, R);
+      for (int j = lane; j < C; j += 32) {
         float mx = -INFINITY;
-        for (int i = 0; i < R; i++) mx = fmaxf(mx, S[(size_t)i * C + j] + u[i]);
+        for (int i = r0; i < r1; i++) mx = fmaxf(mx, S[(size_t)i * C + j] + u[i]);
         float sum = 0.f;
-        for (int i = 0; i < R; i++) sum += expf(S[(size_t)i * C + j] + u[i] - mx);
+        for (int i = r0; i < r1; i++) sum += sk_exp(S[(size_t)i * C + j] + u[i] - mx);
+        part_m[(size_t)warp * C + j] = mx;
+        part_s[(size_t)warp * C + j] = sum;
+      }
+      __syncthreads();
+      for (int j = tid; j < C; j += nt) {
+        float mx = -INFINITY;
+        for (int w = 0; w < nw; w++) mx = fmaxf(mx, part_m[(size_t)w * C + j]);
+        float sum = 0.f;
+        for (int w = 0; w < nw; w++) {
+          const float pm = part_m[(size_t)w * C + j];
+          if (pm > -INFINITY) sum += part_s[(size_t)w * C + j] * sk_exp(pm - mx);
+        }
         v[j] = log_nu[j] - (mx + logf(sum));
       }
     }
@@ -779,10 +835,15 @@ extern "C" int lcr_sinkhorn(const float* scores, int batch, int rows, int cols, 
   if (vec + mat <= 200 * 1024) {
     LCR_CUDA_TRY(cudaFuncSetAttribute(sinkhorn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)(vec + mat)));
-    sinkhorn_kernel<true><<<batch, 512, vec + mat, stream>>>(a);
+    int nt = ((rows > cols ? rows : cols) + 1 + 31) / 32 * 32;
+    nt = nt > 512 ? 512 : nt;
+    sinkhorn_kernel<true><<<batch, nt, vec + mat, stream>>>(a);
   } else {
-    LCR_CUDA_TRY(cudaFuncSetAttribute(sinkhorn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vec));
-    sinkhorn_kernel<false><<<batch, 512, vec, stream>>>(a);
+    const size_t part = sizeof(float) * 2 * 32 * (size_t)(cols + 1);  // per-warp column partials (32 warps)
+    LCR_REQUIRE(vec + part <= 200 * 1024, "sinkhorn: problem too large");
+    LCR_CUDA_TRY(cudaFuncSetAttribute(sinkhorn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)(vec + part)));
+    sinkhorn_kernel<false><<<batch, 1024, vec + part, stream>>>(a);
   }
   LCR_LAUNCHED(1);
   LCR_CUDA_CHECK_LAUNCH();

@@ -315,21 +315,57 @@ class LCRNet(nn.Module):
         vd = self.vote_encoder(enhanced, dd, stacks[-1], n_c, 2)
         feats_f = self.kpdecoder(feats_list[:3] + [enhanced], dd, stacks)
 
-        # 4. matching head, pair by pair (LCRNet.py:161-272)
+        # 4. matching head (LCRNet.py:161-272).  The two Sinkhorn stages are batched over all pairs:
+        #    node level padded to the largest node counts (masked rows/columns are exactly the
+        #    reference's masking), point level over the concatenated patch pairs.
         off_f = ops.Stacks(n_f, dev).off.tolist()
         node_off = [0]
         for c in vd['counts']:
             node_off.append(node_off[-1] + c)
-        outs = []
+        K = self.num_points_in_patch
+        st = []
         for p in range(n_pairs):
             a, b = 2 * p, 2 * p + 1
-            out = self._match(points_f[off_f[a]:off_f[a + 1]], points_f[off_f[b]:off_f[b + 1]],
-                              feats_f[off_f[a]:off_f[a + 1]], feats_f[off_f[b]:off_f[b + 1]],
-                              vd['centres'][node_off[a]:node_off[a + 1]], vd['centres'][node_off[b]:node_off[b + 1]],
-                              vd['feats'][node_off[a]:node_off[a + 1]], vd['feats'][node_off[b]:node_off[b + 1]])
+            s = {'pos_pf': points_f[off_f[a]:off_f[a + 1]].contiguous(), 'anc_pf': points_f[off_f[b]:off_f[b + 1]].contiguous(),
+                 'pos_ff': feats_f[off_f[a]:off_f[a + 1]].contiguous(), 'anc_ff': feats_f[off_f[b]:off_f[b + 1]].contiguous(),
+                 'pos_nodes': vd['centres'][node_off[a]:node_off[a + 1]].contiguous(),
+                 'anc_nodes': vd['centres'][node_off[b]:node_off[b + 1]].contiguous(),
+                 'pos_nf': vd['feats'][node_off[a]:node_off[a + 1]].contiguous(),
+                 'anc_nf': vd['feats'][node_off[b]:node_off[b + 1]].contiguous()}
+            _, s['pos_nm'], s['pos_knn'], s['pos_km'], _ = P.point_to_node_partition(s['pos_pf'], s['pos_nodes'], K)
+            _, s['anc_nm'], s['anc_knn'], s['anc_km'], _ = P.point_to_node_partition(s['anc_pf'], s['anc_nodes'], K)
+            st.append(s)
+        m_max = max(s['pos_nf'].shape[0] for s in st)
+        n_max = max(s['anc_nf'].shape[0] for s in st)
+        node_scores = torch.zeros((n_pairs, m_max, n_max), dtype=torch.float32, device=dev)
+        row_m = torch.zeros((n_pairs, m_max), dtype=torch.bool, device=dev)
+        col_m = torch.zeros((n_pairs, n_max), dtype=torch.bool, device=dev)
+        for p, s in enumerate(st):
+            m, n = s['pos_nf'].shape[0], s['anc_nf'].shape[0]
+            sc = P.linear_ex(s['pos_nf'], _pad4(s['anc_nf'].t()), None)[:, :n]       # LCRNet.py:196-199
+            node_scores[p, :m, :n] = sc / s['pos_nf'].shape[1] ** 0.5
+            row_m[p, :m] = s['pos_nm']
+            col_m[p, :n] = s['anc_nm']
+        node_ot = self.node_optimal_transport(node_scores, row_m, col_m)            # one launch, all pairs
+        pending = [P.coarse_matching(node_ot[p], defer=True) for p in range(n_pairs)]
+        counts = torch.cat([c[3] for c in pending]).tolist()                         # D2H: one read for all pairs
+        ms_all = []
+        for p, s in enumerate(st):
+            oi, oj, os_, _ = pending[p]
+            s['ci'], s['cj'], s['cs'] = oi[:counts[p]], oj[:counts[p]], os_[:counts[p]]
+            ms_all.append(P.patch_scores(s['pos_ff'], s['pos_knn'], s['ci'], s['anc_ff'], s['anc_knn'], s['cj']))
+            s['pkm'], s['akm'] = s['pos_km'][s['ci'].long()], s['anc_km'][s['cj'].long()]
+        ot_all = self.optimal_transport(torch.cat(ms_all), torch.cat([s['pkm'] for s in st]),
+                                        torch.cat([s['akm'] for s in st]))            # one launch, all patch pairs
+        outs, o0 = [], 0
+        for p, s in enumerate(st):
+            a, b = 2 * p, 2 * p + 1
+            ot = ot_all[o0:o0 + counts[p]]
+            o0 += counts[p]
+            out = self._register(s, ot, node_ot[p])
             out.update({
                 'ori_pos_points_c': points_c[off_c[a]:off_c[a + 1]], 'ori_anc_points_c': points_c[off_c[b]:off_c[b + 1]],
-                'pos_points_f': points_f[off_f[a]:off_f[a + 1]], 'anc_points_f': points_f[off_f[b]:off_f[b + 1]],
+                'pos_points_f': s['pos_pf'], 'anc_points_f': s['anc_pf'],
                 'pos_feature_global': descriptors[a:a + 1], 'anc_feature_global': descriptors[b:b + 1],
                 'shifted_pos_points_c': vd['shifted'][off_c[a]:off_c[a + 1]],
                 'shifted_anc_points_c': vd['shifted'][off_c[b]:off_c[b + 1]],
@@ -343,35 +379,25 @@ class LCRNet(nn.Module):
         merged['estimated_transform'] = torch.stack(merged['estimated_transform'])
         return merged
 
-    def _match(self, pos_pf, anc_pf, pos_ff, anc_ff, pos_nodes, anc_nodes, pos_nf, anc_nf):
-        K = self.num_points_in_patch
-        pos_pf, anc_pf = pos_pf.contiguous(), anc_pf.contiguous()
-        _, pos_nm, pos_knn, pos_km, _ = P.point_to_node_partition(pos_pf, pos_nodes.contiguous(), K)
-        _, anc_nm, anc_knn, anc_km, _ = P.point_to_node_partition(anc_pf, anc_nodes.contiguous(), K)
-        # node-level optimal transport (LCRNet.py:196-205)
-        node_scores = P.linear_ex(pos_nf.contiguous(), _pad4(anc_nf.t()), None)[:, :anc_nf.shape[0]]
-        node_scores = (node_scores / pos_nf.shape[1] ** 0.5).contiguous()
-        node_ot = self.node_optimal_transport(node_scores[None], pos_nm[None], anc_nm[None])[0]
-        ci, cj, cs = P.coarse_matching(node_ot)
-        # dense matching (LCRNet.py:218-262)
-        ms = P.patch_scores(pos_ff.contiguous(), pos_knn, ci, anc_ff.contiguous(), anc_knn, cj)
-        pkm, akm = pos_km[ci.long()], anc_km[cj.long()]
-        ot = self.optimal_transport(ms, pkm, akm)
-        corr = P.fine_correspondences(ot, pos_km, ci, anc_km, cj)
-        ref_c, src_c = P.corr_points(corr, pos_pf, pos_knn, ci, anc_pf, anc_knn, cj)
+    def _register(self, s, ot, node_ot):
+        """Fine correspondences + local-to-global registration of one pair (LCRNet.py:251-262)."""
+        ci, cj = s['ci'], s['cj']
+        corr = P.fine_correspondences(ot, s['pos_km'], ci, s['anc_km'], cj)
+        ref_c, src_c = P.corr_points(corr, s['pos_pf'], s['pos_knn'], ci, s['anc_pf'], s['anc_knn'], cj)
         T = P.local_global_registration(ref_c, src_c, corr['score'], corr['pair_off'], self.acceptance_radius,
                                         self.correspondence_threshold, self.num_refinement_steps)
         n = int(corr['pair_off'][-1])                                   # D2H: number of correspondences
         pad3 = lambda x: torch.cat([x, torch.zeros_like(x[:1])], 0)
+        m, k = s['pos_nf'].shape[0], s['anc_nf'].shape[0]
         return {'estimated_transform': T, 'pos_corr_points': ref_c[:n], 'anc_corr_points': src_c[:n],
                 'corr_scores': corr['score'][:n], 'pos_node_corr_indices': ci.long(), 'anc_node_corr_indices': cj.long(),
-                'pos_points_c': pos_nodes, 'anc_points_c': anc_nodes, 'pos_feats_c': pos_nf, 'anc_feats_c': anc_nf,
-                'pos_feats_f': pos_ff, 'anc_feats_f': anc_ff,
-                'pos_node_knn_indices': (pos_knn.long(),), 'pos_node_knn_masks': (pos_km,),
-                'anc_node_knn_indices': (anc_knn.long(),), 'anc_node_knn_masks': (anc_km,),
-                'pos_node_corr_knn_points': pad3(pos_pf)[pos_knn.long()[ci.long()]],
-                'anc_node_corr_knn_points': pad3(anc_pf)[anc_knn.long()[cj.long()]],
-                'pos_node_corr_knn_masks': pkm, 'anc_node_corr_knn_masks': akm,
+                'pos_points_c': s['pos_nodes'], 'anc_points_c': s['anc_nodes'], 'pos_feats_c': s['pos_nf'],
+                'anc_feats_c': s['anc_nf'], 'pos_feats_f': s['pos_ff'], 'anc_feats_f': s['anc_ff'],
+                'pos_node_knn_indices': (s['pos_knn'].long(),), 'pos_node_knn_masks': (s['pos_km'],),
+                'anc_node_knn_indices': (s['anc_knn'].long(),), 'anc_node_knn_masks': (s['anc_km'],),
+                'pos_node_corr_knn_points': pad3(s['pos_pf'])[s['pos_knn'].long()[ci.long()]],
+                'anc_node_corr_knn_points': pad3(s['anc_pf'])[s['anc_knn'].long()[cj.long()]],
+                'pos_node_corr_knn_masks': s['pkm'], 'anc_node_corr_knn_masks': s['akm'],
                 '_node_ot': node_ot, '_point_ot': ot}
 
 

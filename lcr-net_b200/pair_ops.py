@@ -126,8 +126,9 @@ def sinkhorn(scores, row_masks, col_masks, alpha, iters=100):
     return out
 
 
-def coarse_matching(log_scores):
-    """superpoint_matching.py:129-160 -> (ref_idx i32 [P], src_idx i32 [P], scores f32 [P])."""
+def coarse_matching(log_scores, defer=False):
+    """superpoint_matching.py:129-160 -> (ref_idx i32 [P], src_idx i32 [P], scores f32 [P]).
+    defer=True returns capacity-sized arrays and the device count (no host sync)."""
     r, c = log_scores.shape[0] - 1, log_scores.shape[1] - 1
     dev = log_scores.device
     cap = r + c
@@ -140,6 +141,8 @@ def coarse_matching(log_scores):
     ws = _lib.workspace.get(ws_bytes, dev, slot=5)
     _lib.check(L.lcr_coarse_matching(_lib.ptr(_f32c(log_scores)), r, c, _lib.ptr(oi), _lib.ptr(oj), _lib.ptr(os_),
                                      _lib.ptr(cnt), _lib.ptr(ws), ws.numel(), _s(log_scores)))
+    if defer:
+        return oi, oj, os_, cnt
     p = int(cnt)            # D2H: the number of node correspondences sizes the dense stage
     return oi[:p], oj[:p], os_[:p]
 
