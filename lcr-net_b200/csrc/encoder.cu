@@ -186,6 +186,7 @@ gn_partial_kernel(const float* __restrict__ x, int C, int G, const int64_t* __re
   if (C >= 256) {
     for (int c = threadIdx.x; c < C; c += 256) {
       float a = 0.f, b = 0.f;
+#pragma unroll 8
       for (int64_t r = r0; r < r1; r++) {
         const float v = x[r * C + c];
         a += v;
@@ -198,6 +199,7 @@ gn_partial_kernel(const float* __restrict__ x, int C, int G, const int64_t* __re
   } else {
     const int rl = 256 / C, c = threadIdx.x % C, rlane = threadIdx.x / C;  // 256/C row lanes
     float a = 0.f, b = 0.f;
+#pragma unroll 8
     for (int64_t r = r0 + rlane; r < r1; r += rl) {
       const float v = x[r * C + c];
       a += v;

@@ -19,7 +19,7 @@
 
 namespace {
 
-constexpr int BM = 128, BK = 32, STAGES = 3;
+constexpr int BM = 128, BK = 32;
 constexpr int kProducerThreads = 256;
 constexpr int kThreads = kProducerThreads + 32;
 
@@ -63,19 +63,19 @@ __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64
       : "memory");
 }
 
+// Round-to-nearest fp32 -> tf32 (10-bit mantissa) as two integer ops: add half a tf32 ulp to the
+// magnitude bits, clear the 13 low bits.  (cvt.rna.tf32.f32 expands to ~5 instructions with
+// inf/nan guards on sm_100a and made the producers ALU-bound; activations and weights are finite.)
+__device__ __forceinline__ float tf32_rn(float x) {
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+}
+
 __device__ __forceinline__ void split_store(float4 v, float* hi_tile, float* lo_tile, int row, int chunk) {
   float4 h, l;
-  uint32_t t;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.x)); h.x = __uint_as_float(t);
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.y)); h.y = __uint_as_float(t);
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.z)); h.z = __uint_as_float(t);
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.w)); h.w = __uint_as_float(t);
-  // the MMA truncates its operands to tf32; round the residual explicitly so the truncation does
-  // not bias the low-order term
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.x - h.x)); l.x = __uint_as_float(t);
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.y - h.y)); l.y = __uint_as_float(t);
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.z - h.z)); l.z = __uint_as_float(t);
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.w - h.w)); l.w = __uint_as_float(t);
+  h.x = tf32_rn(v.x); h.y = tf32_rn(v.y); h.z = tf32_rn(v.z); h.w = tf32_rn(v.w);
+  // the residual is exact in fp32; it is rounded (not left to the MMA's operand truncation) so the
+  // low-order products carry no bias
+  l.x = tf32_rn(v.x - h.x); l.y = tf32_rn(v.y - h.y); l.z = tf32_rn(v.z - h.z); l.w = tf32_rn(v.w - h.w);
   const int off = row * 32 + ((chunk ^ (row & 7)) << 2);  // floats: 128-B rows, 16-B chunks XOR-swizzled
   *reinterpret_cast<float4*>(hi_tile + off) = h;
   *reinterpret_cast<float4*>(lo_tile + off) = l;
@@ -99,7 +99,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
 // k-blocks (96 values of K): each chunk is accumulated in one of two TMEM buffers and then
 // PROMOTED: added, with IEEE rounding, into fp32 register accumulators by the producer warps
 // while the MMA warp already works on the next chunk in the other buffer.
-template <int BN>
+template <int BN, int STAGES>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tf32x3_kernel(const float* __restrict__ A, int lda, const float* __restrict__ W, int ldw, float* __restrict__ C,
                    int ldc, int M, int N, int K, const float* __restrict__ rowscale, const float* __restrict__ bias,
@@ -123,12 +123,12 @@ gemm_tf32x3_kernel(const float* __restrict__ A, int lda, const float* __restrict
 
   if (tid == 0) {
     for (int s = 0; s < STAGES; s++) {
-      mbar_init(&full_bar[s], kProducerThreads);
+      mbar_init(&full_bar[s], kProducerThreads / 32);   // one arrive per producer warp
       mbar_init(&empty_bar[s], 1);
     }
     for (int b = 0; b < 2; b++) {
       mbar_init(&acc_full[b], 1);
-      mbar_init(&acc_empty[b], kPromoters);
+      mbar_init(&acc_empty[b], kPromoters / 32);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -160,59 +160,76 @@ gemm_tf32x3_kernel(const float* __restrict__ A, int lda, const float* __restrict
         for (int j = 0; j < 32; j++) acc[c0 + j] += __uint_as_float(r[j]);
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      mbar_arrive(&acc_empty[b]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[b]);
     };
-    // global -> register prefetch one k-block ahead: the L2 latency of block kb+1 overlaps the
-    // split + shared-memory stores of block kb
+    // Staging: every thread owns a fixed set of 16-byte chunks of the A and W tiles.  The raw fp32
+    // chunks are fetched with cp.async (LDGSTS, zero-fill outside the matrix) straight into their
+    // swizzled slot of the HI tile of a stage, STAGES-1 k-blocks ahead and without holding
+    // registers; when its own copies have landed the thread converts IN PLACE: hi = rna_tf32(x)
+    // back into the same slot, lo = rna_tf32(x - hi) into the LO tile.  No cross-thread
+    // dependency exists before the full-barrier arrive.
     constexpr int kALoads = BM * 8 / kProducerThreads, kBLoads = BN * 8 / kProducerThreads;
-    float4 ra[kALoads], rb[kBLoads];
-    auto load_block = [&](int kb) {
-      const int k0 = kb * BK;
+    auto issue_block = [&](int kb) {
+      if (kb < nk) {
+        const int s = kb % STAGES;
+        const uint32_t a_hi = smem_u32(base + s * kStageBytes), b_hi = a_hi + 2 * kATile;
+        const int k0 = kb * BK;
 #pragma unroll
-      for (int i = 0; i < kALoads; i++) {
-        const int idx = tid + i * kProducerThreads;
-        const int gm = m0 + (idx >> 3);
-        ra[i] = gm < M ? *reinterpret_cast<const float4*>(A + (size_t)gm * lda + k0 + (idx & 7) * 4)
-                       : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
+        for (int i = 0; i < kALoads; i++) {
+          const int idx = tid + i * kProducerThreads;
+          const int row = idx >> 3, chunk = idx & 7;
+          const int gm = m0 + row;
+          const float* src = A + (size_t)(gm < M ? gm : 0) * lda + k0 + chunk * 4;
+          const uint32_t dst = a_hi + row * 128 + ((chunk ^ (row & 7)) << 4);
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(gm < M ? 16 : 0));
+        }
 #pragma unroll
-      for (int i = 0; i < kBLoads; i++) {
-        const int idx = tid + i * kProducerThreads;
-        const int gn = n0 + (idx >> 3);
-        rb[i] = gn < N ? *reinterpret_cast<const float4*>(W + (size_t)gn * ldw + k0 + (idx & 7) * 4)
-                       : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = 0; i < kBLoads; i++) {
+          const int idx = tid + i * kProducerThreads;
+          const int row = idx >> 3, chunk = idx & 7;
+          const int gn = n0 + row;
+          const float* src = W + (size_t)(gn < N ? gn : 0) * ldw + k0 + chunk * 4;
+          const uint32_t dst = b_hi + row * 128 + ((chunk ^ (row & 7)) << 4);
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(gn < N ? 16 : 0));
+        }
       }
+      asm volatile("cp.async.commit_group;" ::: "memory");   // always: keeps the group count uniform
     };
-    load_block(0);
+#pragma unroll
+    for (int kb = 0; kb < STAGES - 1; kb++) issue_block(kb);
     for (int c = 0; c < n_chunks; c++) {
       // ---------------------------------------------------------- produce the chunk's k-blocks
       const int kb_end = min((c + 1) * CH, nk);
       for (int kb = c * CH; kb < kb_end; kb++) {
         const int s = kb % STAGES;
-        if (kb >= STAGES) mbar_wait(&empty_bar[s], ((kb / STAGES) - 1) & 1);
+        asm volatile("cp.async.wait_group %0;" ::"n"(STAGES - 2) : "memory");   // this thread's block kb landed
         float* a_hi = reinterpret_cast<float*>(base + s * kStageBytes);
         float* a_lo = a_hi + BM * BK;
         float* b_hi = a_lo + BM * BK;
         float* b_lo = b_hi + BN * BK;
-        float4 ca[kALoads], cb[kBLoads];
-#pragma unroll
-        for (int i = 0; i < kALoads; i++) ca[i] = ra[i];
-#pragma unroll
-        for (int i = 0; i < kBLoads; i++) cb[i] = rb[i];
-        if (kb + 1 < nk) load_block(kb + 1);
 #pragma unroll
         for (int i = 0; i < kALoads; i++) {
           const int idx = tid + i * kProducerThreads;
-          split_store(ca[i], a_hi, a_lo, idx >> 3, idx & 7);
+          const int row = idx >> 3, chunk = idx & 7;
+          const float4 v = *reinterpret_cast<const float4*>(a_hi + row * 32 + ((chunk ^ (row & 7)) << 2));
+          split_store(v, a_hi, a_lo, row, chunk);
         }
 #pragma unroll
         for (int i = 0; i < kBLoads; i++) {
           const int idx = tid + i * kProducerThreads;
-          split_store(cb[i], b_hi, b_lo, idx >> 3, idx & 7);
+          const int row = idx >> 3, chunk = idx & 7;
+          const float4 v = *reinterpret_cast<const float4*>(b_hi + row * 32 + ((chunk ^ (row & 7)) << 2));
+          split_store(v, b_hi, b_lo, row, chunk);
         }
         // make the generic-proxy writes visible to the tensor-core (async) proxy, then signal
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_arrive(&full_bar[s]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full_bar[s]);   // 8 arrivals per stage instead of 256 shared-memory atomics
+        // refill the stage that block kb-1 occupied (free once its MMAs have completed)
+        const int nb = kb + STAGES - 1;
+        if (nb < nk && kb >= 1) mbar_wait(&empty_bar[nb % STAGES], ((nb / STAGES) - 1) & 1);
+        issue_block(nb);
       }
       // ---------------------------------------------------------- promote the previous chunk
       if (c >= 1 && promoter) promote(c - 1);
@@ -287,17 +304,174 @@ gemm_tf32x3_kernel(const float* __restrict__ A, int lda, const float* __restrict
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Small-K variant (K <= 128: the unary layers).  These GEMMs are bandwidth-bound (a 128 x BN output
+// tile is produced from at most four k-blocks), so the kernel is built for OCCUPANCY instead of
+// pipelining: one single-use stage per k-block (no ring), accumulators stay in TMEM (one chunk, no
+// promotion), ~64 registers, so 2-3 CTAs share an SM and hide each other's prologue / epilogue.
+// The epilogue goes TMEM -> registers -> per-warp shared-memory transpose -> 128-byte row stores.
 template <int BN>
+__global__ void __launch_bounds__(kThreads, BN >= 256 ? 2 : 3)
+gemm_tf32x3_small_kernel(const float* __restrict__ A, int lda, const float* __restrict__ W, int ldw,
+                         float* __restrict__ C, int ldc, int M, int N, int K, const float* __restrict__ rowscale,
+                         const float* __restrict__ bias, int relu) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  constexpr int kATile = BM * BK * 4, kBTile = BN * BK * 4;
+  __shared__ uint64_t full_bar, empty_bar, done_bar;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int nk = K / BK;
+  if (tid == 0) {
+    mbar_init(&full_bar, kProducerThreads / 32);
+    mbar_init(&empty_bar, 1);
+    mbar_init(&done_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 8) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
+                 "n"(BN));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_s;
+  float* a_hi = reinterpret_cast<float*>(base);
+  float* a_lo = a_hi + BM * BK;
+  float* b_hi = a_lo + BM * BK;
+  float* b_lo = b_hi + BN * BK;
+
+  if (warp < 8) {
+    constexpr int kALoads = BM * 8 / kProducerThreads, kBLoads = BN * 8 / kProducerThreads;
+    for (int kb = 0; kb < nk; kb++) {
+      const int k0 = kb * BK;
+      float4 ra[kALoads], rb[kBLoads];
+#pragma unroll
+      for (int i = 0; i < kALoads; i++) {
+        const int idx = tid + i * kProducerThreads;
+        const int gm = m0 + (idx >> 3);
+        ra[i] = gm < M ? *reinterpret_cast<const float4*>(A + (size_t)gm * lda + k0 + (idx & 7) * 4)
+                       : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int i = 0; i < kBLoads; i++) {
+        const int idx = tid + i * kProducerThreads;
+        const int gn = n0 + (idx >> 3);
+        rb[i] = gn < N ? *reinterpret_cast<const float4*>(W + (size_t)gn * ldw + k0 + (idx & 7) * 4)
+                       : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      if (kb >= 1) mbar_wait(&empty_bar, (kb - 1) & 1);   // the MMAs of block kb-1 have read the stage
+#pragma unroll
+      for (int i = 0; i < kALoads; i++) {
+        const int idx = tid + i * kProducerThreads;
+        split_store(ra[i], a_hi, a_lo, idx >> 3, idx & 7);
+      }
+#pragma unroll
+      for (int i = 0; i < kBLoads; i++) {
+        const int idx = tid + i * kProducerThreads;
+        split_store(rb[i], b_hi, b_lo, idx >> 3, idx & 7);
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full_bar);
+    }
+    // ------------------------------------------------------------ epilogue
+    mbar_wait(&done_bar, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // the stage is free now: per-warp 32 x 33 transpose buffers live in it
+    float* tb = reinterpret_cast<float*>(base) + warp * (32 * 33);
+    const int q = warp & 3;
+    constexpr int kColsPerWarp = BN >= 64 ? BN / 2 : BN;
+    const int c_begin = BN >= 64 ? (warp >> 2) * kColsPerWarp : 0;
+    if (BN >= 64 || warp < 4) {
+      const int row_l = q * 32 + lane;
+      const float rs = (rowscale && m0 + row_l < M) ? rowscale[m0 + row_l] : 1.f;
+#pragma unroll 1
+      for (int c0 = 0; c0 < kColsPerWarp; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c_begin + c0), r);
+#pragma unroll
+        for (int j = 0; j < 32; j++) tb[lane * 33 + j] = __uint_as_float(r[j]) * rs;
+        __syncwarp();
+        const int gn = n0 + c_begin + c0 + lane;
+        const float bv = (bias && gn < N) ? bias[gn] : 0.f;
+        if (gn < N) {
+#pragma unroll 8
+          for (int rr = 0; rr < 32; rr++) {
+            const int gm = m0 + q * 32 + rr;
+            if (gm < M) {
+              float o = tb[rr * 33 + lane] + bv;
+              if (relu) o = fmaxf(o, 0.f);
+              C[(size_t)gm * ldc + gn] = o;        // 32 lanes -> one 128-byte row segment
+            }
+          }
+        }
+        __syncwarp();
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  } else {
+    if (lane == 0) {
+      constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) |
+                                 ((uint32_t)(BM >> 4) << 24);
+      const uint32_t sa_hi = smem_u32(base), sa_lo = sa_hi + kATile, sb_hi = sa_lo + kATile, sb_lo = sb_hi + kBTile;
+      for (int kb = 0; kb < nk; kb++) {
+        mbar_wait(&full_bar, kb & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+        for (int k = 0; k < BK / 8; k++) {
+          const uint32_t koff = k * 32;
+          mma_tf32(tmem_base, make_desc(sa_hi + koff), make_desc(sb_hi + koff), idesc, (kb | k) != 0);
+          mma_tf32(tmem_base, make_desc(sa_hi + koff), make_desc(sb_lo + koff), idesc, 1);
+          mma_tf32(tmem_base, make_desc(sa_lo + koff), make_desc(sb_hi + koff), idesc, 1);
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                         smem_u32(kb + 1 < nk ? &empty_bar : &done_bar))
+                     : "memory");
+      }
+    }
+    __syncwarp();
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 8) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BN));
+  }
+}
+
+template <int BN>
+int launch_tc_small(const float* A, int lda, const float* W, int ldw, float* C, int ldc, int M, int N, int K,
+                    const float* rowscale, const float* bias, int relu, cudaStream_t stream) {
+  constexpr size_t stage = 2 * BM * BK * 4 + 2 * BN * BK * 4;
+  constexpr size_t smem = (stage > 8 * 32 * 33 * 4 ? stage : 8 * 32 * 33 * 4) + 1024;
+  static bool attr_done = false;
+  if (!attr_done) {
+    LCR_CUDA_TRY(cudaFuncSetAttribute(gemm_tf32x3_small_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)smem));
+    attr_done = true;
+  }
+  dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
+  gemm_tf32x3_small_kernel<BN><<<grid, kThreads, smem, stream>>>(A, lda, W, ldw, C, ldc, M, N, K, rowscale, bias,
+                                                                 relu);
+  return LCR_OK;
+}
+
+template <int BN, int STAGES>
 int launch_tc(const float* A, int lda, const float* W, int ldw, float* C, int ldc, int M, int N, int K,
               const float* rowscale, const float* bias, int relu, cudaStream_t stream) {
   constexpr size_t smem = (size_t)STAGES * (2 * BM * BK * 4 + 2 * BN * BK * 4) + 1024;
   static bool attr_done = false;
   if (!attr_done) {
-    LCR_CUDA_TRY(cudaFuncSetAttribute(gemm_tf32x3_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LCR_CUDA_TRY(cudaFuncSetAttribute(gemm_tf32x3_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)smem));
     attr_done = true;
   }
   dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
-  gemm_tf32x3_kernel<BN><<<grid, kThreads, smem, stream>>>(A, lda, W, ldw, C, ldc, M, N, K, rowscale, bias, relu);
+  gemm_tf32x3_kernel<BN, STAGES><<<grid, kThreads, smem, stream>>>(A, lda, W, ldw, C, ldc, M, N, K, rowscale, bias,
+                                                                   relu);
   return LCR_OK;
 }
 
@@ -314,9 +488,22 @@ int lcr_gemm_tf32x3(const float* A, int lda, const float* W, int ldw, float* C, 
   if (M == 0) return LCR_OK;
   LcrProfScope prof("gemm_tf32x3", 2.0 * M * N * K, 4.0 * ((double)M * K + (double)K * N + (double)M * N), stream);
   int rc;
-  if (N <= 32) rc = launch_tc<32>(A, lda, W, ldw, C, ldc, M, N, K, rowscale, bias, relu, stream);
-  else if (N <= 64) rc = launch_tc<64>(A, lda, W, ldw, C, ldc, M, N, K, rowscale, bias, relu, stream);
-  else rc = launch_tc<128>(A, lda, W, ldw, C, ldc, M, N, K, rowscale, bias, relu, stream);
+  if (K <= 4 * BK) {  // bandwidth-bound unary layers: occupancy-oriented kernel
+    if (N <= 32) rc = launch_tc_small<32>(A, lda, W, ldw, C, ldc, M, N, K, rowscale, bias, relu, stream);
+    else if (N <= 64) rc = launch_tc_small<64>(A, lda, W, ldw, C, ldc, M, N, K, rowscale, bias, relu, stream);
+    else if (N <= 128) rc = launch_tc_small<128>(A, lda, W, ldw, C, ldc, M, N, K, rowscale, bias, relu, stream);
+    else rc = launch_tc_small<256>(A, lda, W, ldw, C, ldc, M, N, K, rowscale, bias, relu, stream);
+    if (rc != LCR_OK) return rc;
+    LCR_LAUNCHED(1);
+    LCR_CUDA_CHECK_LAUNCH();
+    return LCR_OK;
+  }
+  // wide tiles amortise the A-operand staging (each 128 x 32 A block is split once per N tile)
+  if (N <= 32) rc = launch_tc<32, 4>(A, lda, W, ldw, C, ldc, M, N, K, rowscale, bias, relu, stream);
+  else if (N <= 64) rc = launch_tc<64, 4>(A, lda, W, ldw, C, ldc, M, N, K, rowscale, bias, relu, stream);
+  else if (N <= 128 || (long)((M + 127) / 128) * ((N + 255) / 256) < LCR_SM_COUNT)
+    rc = launch_tc<128, 3>(A, lda, W, ldw, C, ldc, M, N, K, rowscale, bias, relu, stream);
+  else rc = launch_tc<256, 2>(A, lda, W, ldw, C, ldc, M, N, K, rowscale, bias, relu, stream);
   if (rc != LCR_OK) return rc;
   LCR_LAUNCHED(1);
   LCR_CUDA_CHECK_LAUNCH();
