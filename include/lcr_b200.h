@@ -189,6 +189,13 @@ int lcr_attention(const float* q, int ld_q, const float* k, int ld_k, const floa
  *   compacted at the cloud's row offset.
  * lcr_neighbor_mean: out[m] = mean of points[idx[m, h]] over valid entries (idx < n_points).
  * ---------------------------------------------------------------------------------------- */
+/* Tensor-core attention: same contract as lcr_attention, computed with tcgen05.mma kind::tf32 (3xTF32
+ * operand splitting, fp32-class accuracy), TMEM accumulators and TMA (cp.async.bulk) operand fetch.
+ * Requires 16-byte aligned rows. */
+int lcr_attention_tc(const float* q, int ld_q, const float* k, int ld_k, const float* v, int ld_v,
+                     const int64_t* q_off, const int64_t* k_off, int n_problems, int64_t max_q_rows, int heads,
+                     int head_dim, float* out, int ld_out, double flops_hint, void* stream);
+
 int lcr_vote_shift(const float* points, const float* offsets, int ld_offsets, float max_range, int64_t n, float* out,
                    void* stream);
 int lcr_nms_greedy(const float* points, const int64_t* cloud_off, int n_clouds, int64_t max_cloud_rows, float radius,

@@ -1,0 +1,321 @@
+// attention_tc.cu -- a7: multi-head softmax attention of the 3D-RoFormer on the 5th-gen tensor
+// cores (tcgen05) with operands fetched by the TMA engine (cp.async.bulk + mbarrier tx counts).
+// Reference: dynamic_attention (thdroformer/rpetransformer.py:19-24) and MultiHeadAttention
+// (vanilla_transformer.py:58-72): out = softmax(q k^T / sqrt(32)) v per head; rotary embedding is
+// applied to q/k beforehand by lcr_rope.
+//
+// One CTA = (problem, head, 128-query tile); keys stream through in tiles of 64:
+//   TMA     : every worker thread issues one 128-byte bulk copy (one q / k / v row slice of the
+//             head) into a raw staging buffer; completion is tracked by an mbarrier tx count.
+//   workers : 4 warps = 128 threads, thread t owns query row t.  They split the raw fp32 tiles into
+//             tf32 hi/lo pairs in the canonical K-major SWIZZLE_128B layout (V is transposed on
+//             the fly so that keys become its K dimension), run the online softmax on the score
+//             row they read back from TMEM, publish P (hi/lo) as the A operand of the second
+//             MMA and fold each tile's P.V result into register accumulators.
+//   MMA     : one elected lane issues tcgen05.mma.kind::tf32: S = Q.K^T (128 x 64 x 32) and
+//             O_j = P.V (128 x 32 x 64), each as 3 products (hi.hi + hi.lo + lo.hi) -> fp32-class
+//             accuracy, which the discrete stages downstream of the transformer (NMS, arg-max
+//             correspondences) need; completion via tcgen05.commit -> mbarrier.
+// TMEM: S in columns [0, 64), O_j in [64, 96).
+#include "common.cuh"
+
+namespace {
+
+constexpr int QT = 128, KT = 64, HD = 32;
+constexpr int kWorkers = 128, kThreadsA = kWorkers + 32;
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
+}
+__device__ __forceinline__ void bar_arrive(uint64_t* bar) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void bar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(
+                   smem_addr(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_addr(bar);
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  }
+}
+// TMA bulk copy global -> shared, completion counted in bytes on an mbarrier
+__device__ __forceinline__ void tma_row(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_addr(dst)),
+               "l"(src), "r"(bytes), "r"(smem_addr(bar))
+               : "memory");
+}
+__device__ __forceinline__ uint64_t sw128_desc(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
+         (2ull << 61);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_addr(bar))
+               : "memory");
+}
+__device__ __forceinline__ float rn_tf32(float x) {
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+}
+__device__ __forceinline__ void ld_tmem32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// float offset of element (row, col) inside a K-major SWIZZLE_128B tile with 32-float rows
+__device__ __forceinline__ int sw_off(int row, int col) { return row * 32 + ((((col >> 2) ^ (row & 7)) << 2) | (col & 3)); }
+
+// Shared-memory map (bytes, all tile bases 1024-aligned)
+constexpr int kQhi = 0, kQlo = 16384;                  // 128 x 32
+constexpr int kKhi = 32768, kKlo = 40960;              // 64 x 32
+constexpr int kVhi = 49152, kVlo = 57344;              // V^T: 2 sub-tiles of 32 (dims) x 32 (keys)
+constexpr int kPhi = 65536, kPlo = 98304;              // P:   2 sub-tiles of 128 (queries) x 32 (keys)
+constexpr int kQraw = 131072, kKraw = 147456, kVraw = 155648;   // raw TMA staging
+constexpr int kSmemBytes = 163840 + 1024;
+
+__global__ void __launch_bounds__(kThreadsA, 1)
+attention_tc_kernel(const float* __restrict__ q, int ld_q, const float* __restrict__ k, int ld_k,
+                    const float* __restrict__ v, int ld_v, const int64_t* __restrict__ q_off,
+                    const int64_t* __restrict__ k_off, int heads, float scale_div, float* __restrict__ out,
+                    int ld_o) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t bar_tq, bar_tkv, bar_kv_ready, bar_s_full, bar_p_ready, bar_o_full;
+  __shared__ uint32_t tmem_base_s;
+  const int prob = blockIdx.y / heads, head = blockIdx.y % heads;
+  const int64_t q0 = q_off[prob] + (int64_t)blockIdx.x * QT, q1 = q_off[prob + 1];
+  if (q0 >= q1) return;
+  const int64_t k0 = k_off[prob], k1 = k_off[prob + 1];
+  const int n_tiles = (int)((k1 - k0 + KT - 1) / KT);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    bar_init(&bar_tq, 1);
+    bar_init(&bar_tkv, 1);
+    bar_init(&bar_kv_ready, kWorkers / 32);
+    bar_init(&bar_s_full, 1);
+    bar_init(&bar_p_ready, kWorkers / 32);
+    bar_init(&bar_o_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(&tmem_base_s)),
+                 "n"(128));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_s;
+  const uint32_t tmem_s = tmem_base, tmem_o = tmem_base + 64;
+
+  float* Qhi = reinterpret_cast<float*>(base + kQhi);
+  float* Qlo = reinterpret_cast<float*>(base + kQlo);
+  float* Khi = reinterpret_cast<float*>(base + kKhi);
+  float* Klo = reinterpret_cast<float*>(base + kKlo);
+  float* Vhi = reinterpret_cast<float*>(base + kVhi);
+  float* Vlo = reinterpret_cast<float*>(base + kVlo);
+  float* Phi = reinterpret_cast<float*>(base + kPhi);
+  float* Plo = reinterpret_cast<float*>(base + kPlo);
+  float* Qraw = reinterpret_cast<float*>(base + kQraw);
+  float* Kraw = reinterpret_cast<float*>(base + kKraw);
+  float* Vraw = reinterpret_cast<float*>(base + kVraw);
+
+  if (warp < 4) {
+    // ------------------------------------------------------------ Q tile: TMA rows -> split
+    const int nq = (int)min((int64_t)QT, q1 - q0);
+    if (tid == 0) bar_expect_tx(&bar_tq, (uint32_t)nq * HD * 4);
+    if (tid < nq) tma_row(Qraw + tid * HD, q + (q0 + tid) * ld_q + head * HD, HD * 4, &bar_tq);
+    bar_wait(&bar_tq, 0);
+#pragma unroll
+    for (int c = 0; c < HD; c += 4) {
+      float4 x = tid < nq ? *reinterpret_cast<const float4*>(Qraw + tid * HD + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 h = make_float4(rn_tf32(x.x), rn_tf32(x.y), rn_tf32(x.z), rn_tf32(x.w));
+      float4 l = make_float4(rn_tf32(x.x - h.x), rn_tf32(x.y - h.y), rn_tf32(x.z - h.z), rn_tf32(x.w - h.w));
+      *reinterpret_cast<float4*>(Qhi + sw_off(tid, c)) = h;
+      *reinterpret_cast<float4*>(Qlo + sw_off(tid, c)) = l;
+    }
+    float o_acc[HD];
+#pragma unroll
+    for (int c = 0; c < HD; c++) o_acc[c] = 0.f;
+    float m_run = -INFINITY, l_run = 0.f;
+
+    for (int j = 0; j < n_tiles; j++) {
+      const int64_t kb = k0 + (int64_t)j * KT;
+      const int nkv = (int)min((int64_t)KT, k1 - kb);
+      const uint32_t ph = j & 1;
+      // ---------------------------------------------------------- K / V tile: TMA rows
+      if (tid == 0) bar_expect_tx(&bar_tkv, (uint32_t)nkv * HD * 4 * 2);
+      if (tid < KT) {
+        if (tid < nkv) tma_row(Kraw + tid * HD, k + (kb + tid) * ld_k + head * HD, HD * 4, &bar_tkv);
+      } else if (tid - KT < nkv) {
+        tma_row(Vraw + (tid - KT) * HD, v + (kb + tid - KT) * ld_v + head * HD, HD * 4, &bar_tkv);
+      }
+      bar_wait(&bar_tkv, ph);
+      if (tid < KT) {  // K row -> hi / lo (K-major: row = key)
+#pragma unroll
+        for (int c = 0; c < HD; c += 4) {
+          float4 x = tid < nkv ? *reinterpret_cast<const float4*>(Kraw + tid * HD + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+          float4 h = make_float4(rn_tf32(x.x), rn_tf32(x.y), rn_tf32(x.z), rn_tf32(x.w));
+          float4 l = make_float4(rn_tf32(x.x - h.x), rn_tf32(x.y - h.y), rn_tf32(x.z - h.z), rn_tf32(x.w - h.w));
+          *reinterpret_cast<float4*>(Khi + sw_off(tid, c)) = h;
+          *reinterpret_cast<float4*>(Klo + sw_off(tid, c)) = l;
+        }
+      } else {         // V row -> transposed: V^T[dim][key], keys are the K dimension of the second MMA
+        const int key = tid - KT, sub = key >> 5, kc = key & 31;
+#pragma unroll
+        for (int d = 0; d < HD; d++) {
+          const float x = key < nkv ? Vraw[key * HD + d] : 0.f;
+          const float h = rn_tf32(x);
+          Vhi[sub * 1024 + sw_off(d, kc)] = h;
+          Vlo[sub * 1024 + sw_off(d, kc)] = rn_tf32(x - h);
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) bar_arrive(&bar_kv_ready);
+      // ---------------------------------------------------------- softmax on the score row
+      bar_wait(&bar_s_full, ph);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      uint32_t sr[KT];
+      ld_tmem32(tmem_s + ((uint32_t)(warp * 32) << 16), sr);
+      ld_tmem32(tmem_s + ((uint32_t)(warp * 32) << 16) + 32, sr + 32);
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < KT; c++) {
+        const float s = c < nkv ? __uint_as_float(sr[c]) / scale_div : -INFINITY;
+        sr[c] = __float_as_uint(s);
+        mx = fmaxf(mx, s);
+      }
+      const float m_new = fmaxf(m_run, mx);
+      const float corr = expf(m_run - m_new);
+      float psum = 0.f;
+#pragma unroll
+      for (int c = 0; c < KT; c += 4) {
+        float p[4], h[4], l[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+          p[e] = expf(__uint_as_float(sr[c + e]) - m_new);
+          psum += p[e];
+          h[e] = rn_tf32(p[e]);
+          l[e] = rn_tf32(p[e] - h[e]);
+        }
+        const int sub = c >> 5, cc = c & 31;
+        *reinterpret_cast<float4*>(Phi + sub * 4096 + sw_off(tid, cc)) = make_float4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<float4*>(Plo + sub * 4096 + sw_off(tid, cc)) = make_float4(l[0], l[1], l[2], l[3]);
+      }
+      l_run = l_run * corr + psum;
+      m_run = m_new;
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) bar_arrive(&bar_p_ready);
+      // ---------------------------------------------------------- fold this tile's P.V
+      bar_wait(&bar_o_full, ph);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      uint32_t orr[HD];
+      ld_tmem32(tmem_o + ((uint32_t)(warp * 32) << 16), orr);
+#pragma unroll
+      for (int c = 0; c < HD; c++) o_acc[c] = fmaf(o_acc[c], corr, __uint_as_float(orr[c]));
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    if (tid < nq) {
+      float* o = out + (q0 + tid) * ld_o + head * HD;
+#pragma unroll
+      for (int c = 0; c < HD; c += 4)
+        *reinterpret_cast<float4*>(o + c) =
+            make_float4(o_acc[c] / l_run, o_acc[c + 1] / l_run, o_acc[c + 2] / l_run, o_acc[c + 3] / l_run);
+    }
+  } else if (lane == 0) {
+    // -------------------------------------------------------------- MMA issuer
+    constexpr uint32_t idesc_s = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(KT >> 3) << 17) | ((uint32_t)(QT >> 4) << 24);
+    constexpr uint32_t idesc_o = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(HD >> 3) << 17) | ((uint32_t)(QT >> 4) << 24);
+    const uint32_t qhi = smem_addr(base + kQhi), qlo = smem_addr(base + kQlo), khi = smem_addr(base + kKhi),
+                   klo = smem_addr(base + kKlo), vhi = smem_addr(base + kVhi), vlo = smem_addr(base + kVlo),
+                   phi = smem_addr(base + kPhi), plo = smem_addr(base + kPlo);
+    for (int j = 0; j < n_tiles; j++) {
+      const uint32_t ph = j & 1;
+      bar_wait(&bar_kv_ready, ph);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+      for (int ks = 0; ks < HD / 8; ks++) {   // S = Q . K^T
+        const uint32_t koff = ks * 32;
+        umma_tf32(tmem_s, sw128_desc(qhi + koff), sw128_desc(khi + koff), idesc_s, ks != 0);
+        umma_tf32(tmem_s, sw128_desc(qhi + koff), sw128_desc(klo + koff), idesc_s, 1);
+        umma_tf32(tmem_s, sw128_desc(qlo + koff), sw128_desc(khi + koff), idesc_s, 1);
+      }
+      umma_commit(&bar_s_full);
+      bar_wait(&bar_p_ready, ph);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+      for (int ks = 0; ks < KT / 8; ks++) {   // O_j = P . V  (K = keys: 2 sub-tiles of 32)
+        const uint32_t sub = ks >> 2, koff = (ks & 3) * 32;
+        const uint32_t pa = sub * 16384 + koff, vb = sub * 4096 + koff;
+        umma_tf32(tmem_o, sw128_desc(phi + pa), sw128_desc(vhi + vb), idesc_o, ks != 0);
+        umma_tf32(tmem_o, sw128_desc(phi + pa), sw128_desc(vlo + vb), idesc_o, 1);
+        umma_tf32(tmem_o, sw128_desc(plo + pa), sw128_desc(vhi + vb), idesc_o, 1);
+      }
+      umma_commit(&bar_o_full);
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 4) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(128));
+  }
+}
+
+}  // namespace
+
+extern "C" int lcr_attention_tc(const float* q, int ld_q, const float* k, int ld_k, const float* v, int ld_v,
+                                const int64_t* q_off, const int64_t* k_off, int n_problems, int64_t max_q_rows,
+                                int heads, int head_dim, float* out, int ld_out, double flops_hint, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  LCR_REQUIRE(head_dim == HD, "attention_tc: head_dim must be 32");
+  LCR_REQUIRE(n_problems >= 1 && heads >= 1 && max_q_rows >= 0, "attention_tc: bad sizes");
+  LCR_REQUIRE((ld_q % 4) == 0 && (ld_k % 4) == 0 && (ld_v % 4) == 0 && (ld_out % 4) == 0 &&
+                  (((uintptr_t)q | (uintptr_t)k | (uintptr_t)v | (uintptr_t)out) & 15) == 0,
+              "attention_tc: rows must be 16-byte aligned (TMA bulk copies)");
+  if (max_q_rows == 0) return LCR_OK;
+  static bool attr_done = false;
+  if (!attr_done) {
+    LCR_CUDA_TRY(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    attr_done = true;
+  }
+  LcrProfScope prof("attention_tc", flops_hint, 0.0, stream);
+  dim3 grid((unsigned)((max_q_rows + QT - 1) / QT), (unsigned)(n_problems * heads));
+  attention_tc_kernel<<<grid, kThreadsA, kSmemBytes, stream>>>(q, ld_q, k, ld_k, v, ld_v, q_off, k_off, heads,
+                                                               sqrtf((float)head_dim), out, ld_out);
+  LCR_LAUNCHED(1);
+  LCR_CUDA_CHECK_LAUNCH();
+  return LCR_OK;
+}

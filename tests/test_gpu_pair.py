@@ -258,3 +258,29 @@ def test_loop_candidates_vs_oracle():
     # top-1 of every query agrees (descriptor distances are well separated)
     first = {int(i): int(j) for i, j, _ in rows[::-1]}
     assert all(first[int(q)] == int(idx[n, 0]) for n, q in enumerate(q_ids))
+
+
+@pytest.mark.parametrize('impl', ['simt', 'tc'])
+def test_attention_kernels_vs_torch(impl, monkeypatch):
+    """Both attention kernels (fp32 SIMT flash-style; tcgen05 3xTF32 + TMA) against torch fp64 on
+    ragged problems (lengths not multiples of the 64/128 tiles, strided q/k/v views)."""
+    from lcrnet_b200 import pair_ops as P
+    monkeypatch.setenv('LCR_ATTN', impl)
+    g = torch.Generator().manual_seed(3)
+    q_len, k_len = [130, 1, 257, 64], [77, 300, 128, 5]
+    qkv = torch.randn(sum(q_len), 384, generator=g).cuda()
+    kv = torch.randn(sum(k_len), 256, generator=g).cuda()
+    q, k, v = qkv[:, :128], kv[:, :128], kv[:, 128:]
+    qo = torch.tensor([0] + list(np.cumsum(q_len)), dtype=torch.int64).cuda()
+    ko = torch.tensor([0] + list(np.cumsum(k_len)), dtype=torch.int64).cuda()
+    got = P.attention(q, k, v, qo, ko, 4, max(q_len), heads=4).cpu().double()
+    ref = torch.zeros(sum(q_len), 128, dtype=torch.float64)
+    for p in range(4):
+        qs, ks = slice(int(qo[p]), int(qo[p + 1])), slice(int(ko[p]), int(ko[p + 1]))
+        for h in range(4):
+            hs = slice(32 * h, 32 * h + 32)
+            s = q[qs, hs].double().cpu() @ k[ks, hs].double().cpu().t() / 32 ** 0.5
+            ref[qs, hs] = torch.softmax(s, dim=-1) @ v[ks, hs].double().cpu()
+    err = float((got - ref).abs().max())
+    print('[%s] attention max abs error vs fp64: %.2e' % (impl, err))
+    assert err < 2e-5
