@@ -10,13 +10,14 @@
 //   workers : 4 warps = 128 threads, thread t owns query row t.  They split the raw fp32 tiles into
 //             tf32 hi/lo pairs in the canonical K-major SWIZZLE_128B layout (V is transposed on
 //             the fly so that keys become its K dimension), run the online softmax on the score
-//             row they read back from TMEM, publish P (hi/lo) as the A operand of the second
-//             MMA and fold each tile's P.V result into register accumulators.
+//             row they read back from TMEM, write P (hi/lo) back INTO TMEM (tcgen05.st) where the
+//             second MMA reads it as its A operand, and fold each tile's P.V result into register
+//             accumulators.  (P never touches shared memory: 96 KB per CTA, two CTAs per SM.)
 //   MMA     : one elected lane issues tcgen05.mma.kind::tf32: S = Q.K^T (128 x 64 x 32) and
 //             O_j = P.V (128 x 32 x 64), each as 3 products (hi.hi + hi.lo + lo.hi) -> fp32-class
 //             accuracy, which the discrete stages downstream of the transformer (NMS, arg-max
 //             correspondences) need; completion via tcgen05.commit -> mbarrier.
-// TMEM: S in columns [0, 64), O_j in [64, 96).
+// TMEM: S in columns [0, 64), O_j in [64, 96), P_hi in [96, 160), P_lo in [160, 224).
 #include "common.cuh"
 
 namespace {
@@ -90,6 +91,38 @@ __device__ __forceinline__ void ld_tmem32(uint32_t taddr, uint32_t* r) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void st_tmem32(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+      "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+      "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+// D[tmem] (+)= A[tmem] . B[smem]^T
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u)
+      : "memory");
+}
+// exp(x) on the SFU with a compensated argument (see matching.cu:sk_exp): ~2 ulp
+__device__ __forceinline__ float fast_exp(float x) {
+  x = fmaxf(x, -100.f);  // masked scores are -inf: exp(-100) flushes to 0 and no inf - inf appears below
+  const float kL2E = 1.4426950408889634f, kL2E_lo = 1.925963033500011e-8f;
+  const float y = x * kL2E;
+  const float e = fmaf(x, kL2E_lo, fmaf(x, kL2E, -y));
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(y));
+  return fmaf(r, e * 0.6931471805599453f, r);
+}
+
 // float offset of element (row, col) inside a K-major SWIZZLE_128B tile with 32-float rows
 __device__ __forceinline__ int sw_off(int row, int col) { return row * 32 + ((((col >> 2) ^ (row & 7)) << 2) | (col & 3)); }
 
@@ -97,18 +130,18 @@ __device__ __forceinline__ int sw_off(int row, int col) { return row * 32 + ((((
 constexpr int kQhi = 0, kQlo = 16384;                  // 128 x 32
 constexpr int kKhi = 32768, kKlo = 40960;              // 64 x 32
 constexpr int kVhi = 49152, kVlo = 57344;              // V^T: 2 sub-tiles of 32 (dims) x 32 (keys)
-constexpr int kPhi = 65536, kPlo = 98304;              // P:   2 sub-tiles of 128 (queries) x 32 (keys)
-constexpr int kQraw = 131072, kKraw = 147456, kVraw = 155648;   // raw TMA staging
-constexpr int kSmemBytes = 163840 + 1024;
+constexpr int kKraw = 65536, kVraw = 73728;            // raw TMA staging, double-buffered: + buf * 16384
+constexpr int kQraw = 81920;                           // raw Q (used once) aliases raw buffer 1
+constexpr int kSmemBytes = 98304 + 1024;
 
-__global__ void __launch_bounds__(kThreadsA, 1)
+__global__ void __launch_bounds__(kThreadsA, 2)
 attention_tc_kernel(const float* __restrict__ q, int ld_q, const float* __restrict__ k, int ld_k,
                     const float* __restrict__ v, int ld_v, const int64_t* __restrict__ q_off,
-                    const int64_t* __restrict__ k_off, int heads, float scale_div, float* __restrict__ out,
+                    const int64_t* __restrict__ k_off, int heads, float scale_mul, float* __restrict__ out,
                     int ld_o) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  __shared__ uint64_t bar_tq, bar_tkv, bar_kv_ready, bar_s_full, bar_p_ready, bar_o_full;
+  __shared__ uint64_t bar_tq, bar_tkv[2], bar_kv_ready, bar_s_full, bar_p_ready, bar_o_full;
   __shared__ uint32_t tmem_base_s;
   const int prob = blockIdx.y / heads, head = blockIdx.y % heads;
   const int64_t q0 = q_off[prob] + (int64_t)blockIdx.x * QT, q1 = q_off[prob + 1];
@@ -119,7 +152,8 @@ attention_tc_kernel(const float* __restrict__ q, int ld_q, const float* __restri
 
   if (tid == 0) {
     bar_init(&bar_tq, 1);
-    bar_init(&bar_tkv, 1);
+    bar_init(&bar_tkv[0], 1);
+    bar_init(&bar_tkv[1], 1);
     bar_init(&bar_kv_ready, kWorkers / 32);
     bar_init(&bar_s_full, 1);
     bar_init(&bar_p_ready, kWorkers / 32);
@@ -128,14 +162,14 @@ attention_tc_kernel(const float* __restrict__ q, int ld_q, const float* __restri
   }
   if (warp == 4) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(&tmem_base_s)),
-                 "n"(128));
+                 "n"(256));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = tmem_base_s;
-  const uint32_t tmem_s = tmem_base, tmem_o = tmem_base + 64;
+  const uint32_t tmem_s = tmem_base, tmem_o = tmem_base + 64, tmem_phi = tmem_base + 96, tmem_plo = tmem_base + 160;
 
   float* Qhi = reinterpret_cast<float*>(base + kQhi);
   float* Qlo = reinterpret_cast<float*>(base + kQlo);
@@ -143,17 +177,28 @@ attention_tc_kernel(const float* __restrict__ q, int ld_q, const float* __restri
   float* Klo = reinterpret_cast<float*>(base + kKlo);
   float* Vhi = reinterpret_cast<float*>(base + kVhi);
   float* Vlo = reinterpret_cast<float*>(base + kVlo);
-  float* Phi = reinterpret_cast<float*>(base + kPhi);
-  float* Plo = reinterpret_cast<float*>(base + kPlo);
   float* Qraw = reinterpret_cast<float*>(base + kQraw);
-  float* Kraw = reinterpret_cast<float*>(base + kKraw);
-  float* Vraw = reinterpret_cast<float*>(base + kVraw);
+  // the TMA engine fetches tile j+1 into the other raw buffer while tile j is being processed
+  auto issue_kv = [&](int j) {
+    const int64_t kb = k0 + (int64_t)j * KT;
+    const int nkv = (int)min((int64_t)KT, k1 - kb);
+    const int b = j & 1;
+    float* Kr = reinterpret_cast<float*>(base + kKraw + b * 16384);
+    float* Vr = reinterpret_cast<float*>(base + kVraw + b * 16384);
+    if (tid == 0) bar_expect_tx(&bar_tkv[b], (uint32_t)nkv * HD * 4 * 2);
+    if (tid < KT) {
+      if (tid < nkv) tma_row(Kr + tid * HD, k + (kb + tid) * ld_k + head * HD, HD * 4, &bar_tkv[b]);
+    } else if (tid - KT < nkv) {
+      tma_row(Vr + (tid - KT) * HD, v + (kb + tid - KT) * ld_v + head * HD, HD * 4, &bar_tkv[b]);
+    }
+  };
 
   if (warp < 4) {
     // ------------------------------------------------------------ Q tile: TMA rows -> split
     const int nq = (int)min((int64_t)QT, q1 - q0);
     if (tid == 0) bar_expect_tx(&bar_tq, (uint32_t)nq * HD * 4);
     if (tid < nq) tma_row(Qraw + tid * HD, q + (q0 + tid) * ld_q + head * HD, HD * 4, &bar_tq);
+    issue_kv(0);
     bar_wait(&bar_tq, 0);
 #pragma unroll
     for (int c = 0; c < HD; c += 4) {
@@ -172,14 +217,11 @@ attention_tc_kernel(const float* __restrict__ q, int ld_q, const float* __restri
       const int64_t kb = k0 + (int64_t)j * KT;
       const int nkv = (int)min((int64_t)KT, k1 - kb);
       const uint32_t ph = j & 1;
-      // ---------------------------------------------------------- K / V tile: TMA rows
-      if (tid == 0) bar_expect_tx(&bar_tkv, (uint32_t)nkv * HD * 4 * 2);
-      if (tid < KT) {
-        if (tid < nkv) tma_row(Kraw + tid * HD, k + (kb + tid) * ld_k + head * HD, HD * 4, &bar_tkv);
-      } else if (tid - KT < nkv) {
-        tma_row(Vraw + (tid - KT) * HD, v + (kb + tid - KT) * ld_v + head * HD, HD * 4, &bar_tkv);
-      }
-      bar_wait(&bar_tkv, ph);
+      // ---------------------------------------------------------- K / V tile (fetched by TMA one tile ahead)
+      const float* Kraw = reinterpret_cast<const float*>(base + kKraw + (j & 1) * 16384);
+      const float* Vraw = reinterpret_cast<const float*>(base + kVraw + (j & 1) * 16384);
+      if (j + 1 < n_tiles) issue_kv(j + 1);
+      bar_wait(&bar_tkv[j & 1], (j >> 1) & 1);
       if (tid < KT) {  // K row -> hi / lo (K-major: row = key)
 #pragma unroll
         for (int c = 0; c < HD; c += 4) {
@@ -211,30 +253,31 @@ attention_tc_kernel(const float* __restrict__ q, int ld_q, const float* __restri
       float mx = -INFINITY;
 #pragma unroll
       for (int c = 0; c < KT; c++) {
-        const float s = c < nkv ? __uint_as_float(sr[c]) / scale_div : -INFINITY;
+        const float s = c < nkv ? __uint_as_float(sr[c]) * scale_mul : -INFINITY;
         sr[c] = __float_as_uint(s);
         mx = fmaxf(mx, s);
       }
       const float m_new = fmaxf(m_run, mx);
-      const float corr = expf(m_run - m_new);
+      const float corr = fast_exp(m_run - m_new);
       float psum = 0.f;
+      const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
 #pragma unroll
-      for (int c = 0; c < KT; c += 4) {
-        float p[4], h[4], l[4];
+      for (int c0 = 0; c0 < KT; c0 += 32) {
+        uint32_t hi[32], lo[32];
 #pragma unroll
-        for (int e = 0; e < 4; e++) {
-          p[e] = expf(__uint_as_float(sr[c + e]) - m_new);
-          psum += p[e];
-          h[e] = rn_tf32(p[e]);
-          l[e] = rn_tf32(p[e] - h[e]);
+        for (int e = 0; e < 32; e++) {
+          const float p = fast_exp(__uint_as_float(sr[c0 + e]) - m_new);
+          psum += p;
+          const float h = rn_tf32(p);
+          hi[e] = __float_as_uint(h);
+          lo[e] = __float_as_uint(rn_tf32(p - h));
         }
-        const int sub = c >> 5, cc = c & 31;
-        *reinterpret_cast<float4*>(Phi + sub * 4096 + sw_off(tid, cc)) = make_float4(h[0], h[1], h[2], h[3]);
-        *reinterpret_cast<float4*>(Plo + sub * 4096 + sw_off(tid, cc)) = make_float4(l[0], l[1], l[2], l[3]);
+        st_tmem32(tmem_phi + lane_base + c0, hi);
+        st_tmem32(tmem_plo + lane_base + c0, lo);
       }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       l_run = l_run * corr + psum;
       m_run = m_new;
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) bar_arrive(&bar_p_ready);
@@ -259,8 +302,7 @@ attention_tc_kernel(const float* __restrict__ q, int ld_q, const float* __restri
     constexpr uint32_t idesc_s = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(KT >> 3) << 17) | ((uint32_t)(QT >> 4) << 24);
     constexpr uint32_t idesc_o = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(HD >> 3) << 17) | ((uint32_t)(QT >> 4) << 24);
     const uint32_t qhi = smem_addr(base + kQhi), qlo = smem_addr(base + kQlo), khi = smem_addr(base + kKhi),
-                   klo = smem_addr(base + kKlo), vhi = smem_addr(base + kVhi), vlo = smem_addr(base + kVlo),
-                   phi = smem_addr(base + kPhi), plo = smem_addr(base + kPlo);
+                   klo = smem_addr(base + kKlo), vhi = smem_addr(base + kVhi), vlo = smem_addr(base + kVlo);
     for (int j = 0; j < n_tiles; j++) {
       const uint32_t ph = j & 1;
       bar_wait(&bar_kv_ready, ph);
@@ -278,10 +320,10 @@ attention_tc_kernel(const float* __restrict__ q, int ld_q, const float* __restri
 #pragma unroll
       for (int ks = 0; ks < KT / 8; ks++) {   // O_j = P . V  (K = keys: 2 sub-tiles of 32)
         const uint32_t sub = ks >> 2, koff = (ks & 3) * 32;
-        const uint32_t pa = sub * 16384 + koff, vb = sub * 4096 + koff;
-        umma_tf32(tmem_o, sw128_desc(phi + pa), sw128_desc(vhi + vb), idesc_o, ks != 0);
-        umma_tf32(tmem_o, sw128_desc(phi + pa), sw128_desc(vlo + vb), idesc_o, 1);
-        umma_tf32(tmem_o, sw128_desc(plo + pa), sw128_desc(vhi + vb), idesc_o, 1);
+        const uint32_t vb = sub * 4096 + koff, pc = ks * 8;   // A (P) from TMEM: 8 tf32 columns per k-step
+        umma_tf32_ts(tmem_o, tmem_phi + pc, sw128_desc(vhi + vb), idesc_o, ks != 0);
+        umma_tf32_ts(tmem_o, tmem_phi + pc, sw128_desc(vlo + vb), idesc_o, 1);
+        umma_tf32_ts(tmem_o, tmem_plo + pc, sw128_desc(vhi + vb), idesc_o, 1);
       }
       umma_commit(&bar_o_full);
     }
@@ -290,7 +332,7 @@ attention_tc_kernel(const float* __restrict__ q, int ld_q, const float* __restri
   __syncthreads();
   if (warp == 4) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(128));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(256));
   }
 }
 
@@ -314,7 +356,7 @@ extern "C" int lcr_attention_tc(const float* q, int ld_q, const float* k, int ld
   LcrProfScope prof("attention_tc", flops_hint, 0.0, stream);
   dim3 grid((unsigned)((max_q_rows + QT - 1) / QT), (unsigned)(n_problems * heads));
   attention_tc_kernel<<<grid, kThreadsA, kSmemBytes, stream>>>(q, ld_q, k, ld_k, v, ld_v, q_off, k_off, heads,
-                                                               sqrtf((float)head_dim), out, ld_out);
+                                                               1.0f / sqrtf((float)head_dim), out, ld_out);
   LCR_LAUNCHED(1);
   LCR_CUDA_CHECK_LAUNCH();
   return LCR_OK;
