@@ -94,9 +94,13 @@ kpconv_gather_kernel(const float* __restrict__ s_feats, const float* __restrict_
 #pragma unroll
         for (int g = 0; g < 4; g++) *reinterpret_cast<float4*>(w + 4 * g) = s_w[warp][g][hh + u];
 #pragma unroll
-        for (int k = 0; k < KP; k++)
+        for (int k = 0; k < KP; k++) {
+          // a neighbour lies inside the influence radius of only a few of the 15 kernel points; the
+          // weight is warp-uniform, so for wide channel slices skipping the zero ones pays
+          if (CPL >= 4 && w[k] == 0.f) continue;
 #pragma unroll
           for (int i = 0; i < CPL; i++) acc[k][i] = fmaf(w[k], fv[u][i], acc[k][i]);
+        }
       }
     }
     for (; hh < nv; hh++) {
@@ -108,9 +112,11 @@ kpconv_gather_kernel(const float* __restrict__ s_feats, const float* __restrict_
 #pragma unroll
       for (int g = 0; g < 4; g++) *reinterpret_cast<float4*>(w + 4 * g) = s_w[warp][g][hh];
 #pragma unroll
-      for (int k = 0; k < KP; k++)
+      for (int k = 0; k < KP; k++) {
+        if (CPL >= 4 && w[k] == 0.f) continue;
 #pragma unroll
         for (int i = 0; i < CPL; i++) acc[k][i] = fmaf(w[k], fv[i], acc[k][i]);
+      }
     }
     __syncwarp();
   }

@@ -167,7 +167,9 @@ __global__ void __launch_bounds__(kSmem ? 512 : 1024) sinkhorn_kernel(SinkhornAr
   float* v = u + R;
   float* log_mu = v + C;
   float* log_nu = log_mu + R;
-  float* S = kSmem ? log_nu + C : a.out + (size_t)blockIdx.x * R * C;
+  float* u0 = log_nu + C;     // potentials saved at the switch to the linear domain
+  float* v0 = u0 + R;
+  float* S = kSmem ? v0 + C : a.out + (size_t)blockIdx.x * R * C;
   __shared__ float s_norm;
   __shared__ int s_cnt[2];
   const int b = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
@@ -210,7 +212,15 @@ __global__ void __launch_bounds__(kSmem ? 512 : 1024) sinkhorn_kernel(SinkhornAr
     S[e] = masked ? -inf : val;
   }
   __syncthreads();
-  for (int it = 0; it < a.iters; it++) {
+  // The first kLogIters iterations run in the log domain exactly as written in the reference;
+  // the potentials are then absorbed, K = exp(S + u + v) (the current transport plan, entries
+  // <= ~1, masked entries exactly 0) replaces S (shared memory, or L2 for the node-level
+  // problem) and the remaining iterations are the same Sinkhorn updates in the linear domain,
+  //     a_i = mu_i / sum_j K_ij b_j ,  b_j = nu_j / sum_i K_ij a_i     (u += log a, v += log b),
+  // one FMA per matrix element instead of one exp.  a, b stay O(1), so there is no range problem.
+  constexpr int kLogIters = 4;
+  const int log_iters = min(a.iters, kLogIters);
+  for (int it = 0; it < log_iters; it++) {
     if (kSmem) {
       // matrix in shared memory: one THREAD per row / per column (no shuffle reductions; with the
       // odd row length 129 both the row walk and the column walk are bank-conflict free)
@@ -264,7 +274,7 @@ __global__ void __launch_bounds__(kSmem ? 512 : 1024) sinkhorn_kernel(SinkhornAr
       // matrix in L2: warp w owns a slab of rows, lanes stride the columns (coalesced row
       // segments, independent columns -> ILP); per-slab (max, sum-exp) partials are combined
       // per column through shared memory
-      float* part_m = log_nu + C;
+      float* part_m = v0 + C;
       float* part_s = part_m + (size_t)nw * C;
       const int rs = (R + nw - 1) / nw, r0 = warp * rs, r1 = min(r0 + rs, R);
       for (int j = lane; j < C; j += 32) {
@@ -288,6 +298,96 @@ __global__ void __launch_bounds__(kSmem ? 512 : 1024) sinkhorn_kernel(SinkhornAr
       }
     }
     __syncthreads();
+  }
+  if (a.iters > log_iters) {
+    // absorb: K = exp(S + u + v); mu, nu to the linear domain (masked rows / columns carry no mass)
+    for (int e = tid; e < R * C; e += nt) {
+      const int i = e / C, j = e % C;
+      S[e] = sk_exp(S[e] + u[i] + v[j]);
+    }
+    __syncthreads();
+    float* mu = log_mu;   // reused in place
+    float* nu = log_nu;
+    for (int i = tid; i < R; i += nt) {
+      mu[i] = log_mu[i] > -1e11f ? expf(log_mu[i]) : 0.f;
+      u0[i] = u[i];
+      u[i] = 1.f;         // a
+    }
+    for (int j = tid; j < C; j += nt) {
+      nu[j] = log_nu[j] > -1e11f ? expf(log_nu[j]) : 0.f;
+      v0[j] = v[j];
+      v[j] = 1.f;         // b
+    }
+    __syncthreads();
+    float* part = v0 + C + (kSmem ? 0 : 0);   // (global variant) per-warp column partials, after the vectors
+    for (int it = log_iters; it < a.iters; it++) {
+      if (kSmem) {
+        for (int i = tid; i < R; i += nt) {       // one thread per row
+          const float* row = S + (size_t)i * C;
+          float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+          int j = 0;
+          for (; j + 4 <= C; j += 4) {
+            s0 = fmaf(row[j], v[j], s0);
+            s1 = fmaf(row[j + 1], v[j + 1], s1);
+            s2 = fmaf(row[j + 2], v[j + 2], s2);
+            s3 = fmaf(row[j + 3], v[j + 3], s3);
+          }
+          for (; j < C; j++) s0 = fmaf(row[j], v[j], s0);
+          const float sum = (s0 + s1) + (s2 + s3);
+          u[i] = sum > 0.f ? mu[i] / sum : 0.f;
+        }
+        __syncthreads();
+        for (int j = tid; j < C; j += nt) {       // one thread per column
+          float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+          int i = 0;
+          for (; i + 4 <= R; i += 4) {
+            s0 = fmaf(S[(size_t)i * C + j], u[i], s0);
+            s1 = fmaf(S[(size_t)(i + 1) * C + j], u[i + 1], s1);
+            s2 = fmaf(S[(size_t)(i + 2) * C + j], u[i + 2], s2);
+            s3 = fmaf(S[(size_t)(i + 3) * C + j], u[i + 3], s3);
+          }
+          for (; i < R; i++) s0 = fmaf(S[(size_t)i * C + j], u[i], s0);
+          const float sum = (s0 + s1) + (s2 + s3);
+          v[j] = sum > 0.f ? nu[j] / sum : 0.f;
+        }
+        __syncthreads();
+      } else {
+        for (int i = warp; i < R; i += nw) {      // warp per row, coalesced
+          const float* row = S + (size_t)i * C;
+          float sum = 0.f;
+          for (int j = lane; j < C; j += 32) sum = fmaf(row[j], v[j], sum);
+          sum = lcr_warp_sum(sum);
+          if (lane == 0) u[i] = sum > 0.f ? mu[i] / sum : 0.f;
+        }
+        __syncthreads();
+        const int rs = (R + nw - 1) / nw, r0 = warp * rs, r1 = min(r0 + rs, R);
+        for (int j = lane; j < C; j += 32) {      // warp per row slab, lanes over columns
+          float sum = 0.f;
+          for (int i = r0; i < r1; i++) sum = fmaf(S[(size_t)i * C + j], u[i], sum);
+          part[(size_t)warp * C + j] = sum;
+        }
+        __syncthreads();
+        for (int j = tid; j < C; j += nt) {
+          float sum = 0.f;
+          for (int w = 0; w < nw; w++) sum += part[(size_t)w * C + j];
+          v[j] = sum > 0.f ? nu[j] / sum : 0.f;
+        }
+        __syncthreads();
+      }
+    }
+    // back to log potentials (masked rows / columns: the value is irrelevant, their entries stay -1e12)
+    for (int i = tid; i < R; i += nt) u[i] = u0[i] + (u[i] > 0.f ? logf(u[i]) : 0.f);
+    for (int j = tid; j < C; j += nt) v[j] = v0[j] + (v[j] > 0.f ? logf(v[j]) : 0.f);
+    __syncthreads();
+    // S was overwritten by K: rebuild the padded log scores from the input for the output
+    float* dst = a.out + (size_t)b * R * C;
+    for (int e = tid; e < R * C; e += nt) {
+      const int i = e / C, j = e % C;
+      const float val = (i < a.M && j < a.N) ? src[(size_t)i * a.N + j] : alpha;
+      const bool masked = (i < a.M && rm && !rm[i]) || (j < a.N && cm && !cm[j]);
+      dst[e] = (masked ? -inf : val) + u[i] + v[j] - norm;
+    }
+    return;
   }
   float* dst = a.out + (size_t)b * R * C;
   for (int e = tid; e < R * C; e += nt) {
@@ -827,7 +927,7 @@ extern "C" int lcr_sinkhorn(const float* scores, int batch, int rows, int cols, 
   LCR_REQUIRE(batch >= 0 && rows >= 1 && cols >= 1 && iters >= 0, "sinkhorn: sizes");
   if (batch == 0) return LCR_OK;
   SinkhornArgs a{scores, row_mask, col_mask, alpha, out, rows, cols, iters};
-  const size_t vec = sizeof(float) * 2 * (size_t)(rows + 1 + cols + 1);
+  const size_t vec = sizeof(float) * 3 * (size_t)(rows + 1 + cols + 1);
   const size_t mat = sizeof(float) * (size_t)(rows + 1) * (cols + 1);
   LCR_REQUIRE(vec <= 96 * 1024, "sinkhorn: problem too large");
   LcrProfScope prof("sinkhorn", 4.0 * batch * (double)(rows + 1) * (cols + 1) * iters,
