@@ -46,6 +46,8 @@ def parse():
     ap.add_argument('--cpu-pairs', type=int, default=1, help='pairs in the CPU baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--ncu', action='store_true', help='one warm-up step + one step only (for ncu captures)')
+    ap.add_argument('--streams', type=int, default=2,
+                    help='descriptor workload: chunks of the batch in flight on separate CUDA streams (pipeline.py)')
     ap.add_argument('--workload', default='descriptor', choices=['descriptor', 'db', 'pairs'],
                     help='descriptor: the headline line (configs[1]); db: descriptor-database build + all-gather + '
                          'top-25 (configs[3]/[4]); pairs: full registration of scan pairs (configs[2])')
@@ -199,12 +201,13 @@ def calibrated_limits_cpu(scans):
     return [int(x) for x in np.sum(cum < 0.8 * cum[hist_n - 1, :], axis=0)]
 
 
-def workload_config(pairs, limits):
+def workload_config(pairs, limits, streams=1):
     return {'workload': 'configs[1]: descriptor path (0.3 m pre-voxel -> pyramid -> radius tables -> KPConv encoder '
                         '-> NetVLAD) on synthetic 64k-point scans, %d pairs (%d scans) per step per GPU, + pair '
                         'descriptor distance' % (pairs, 2 * pairs),
             'pairs_per_step_per_gpu': pairs, 'points_per_scan': 65536, 'neighbor_limits': limits,
-            'weights': 'seeded random (checkpoint.random_state_dict(7351))', 'cache': 'L2 flushed between timed steps'}
+            'weights': 'seeded random (checkpoint.random_state_dict(7351))', 'cache': 'L2 flushed between timed steps',
+            'streams': streams}
 
 
 # ----------------------------------------------------------------------------- GPU path
@@ -235,17 +238,19 @@ def run_b200(args):
     out_desc = torch.empty((2 * args.pairs, 256), dtype=torch.float32).pin_memory()
     out_dist = torch.empty(args.pairs, dtype=torch.float32).pin_memory()
 
-    def step(points, lengths):
-        d = gdata.device_collate(points, lengths, NUM_STAGES, VOXEL, RADIUS, limits, pre_voxel=VOXEL, stack_size=1,
-                                 int32=True, upsampling=False)
-        desc = net(d)['anc_global']
+    from lcrnet_b200 import pipeline
+    lens_list = host_len.tolist()
+    pipe1 = pipeline.DescriptorPipeline(net, limits, NUM_STAGES, VOXEL, RADIUS, pre_voxel=VOXEL, n_streams=1)
+    pipe = pipe1 if args.streams <= 1 or args.ncu else pipeline.DescriptorPipeline(
+        net, limits, NUM_STAGES, VOXEL, RADIUS, pre_voxel=VOXEL, n_streams=args.streams)
+
+    def step(points, lengths, p=None):
+        desc = (p or pipe)(points, lens_list)
         diff = desc[0::2] - desc[1::2]
         return desc, (diff * diff).sum(1)
 
     def step_e2e():
-        p = host_pts.to(dev, non_blocking=True)
-        l = host_len.to(dev, non_blocking=True)
-        desc, dd = step(p, l)
+        desc, dd = step(host_pts, None)           # every chunk copies its own slice of the pinned host buffer
         out_desc.copy_(desc, non_blocking=True)
         out_dist.copy_(dd, non_blocking=True)
         torch.cuda.current_stream().synchronize()
@@ -302,7 +307,8 @@ def run_b200(args):
     desc, dd = step(dev_pts, dev_len)
     assert torch.isfinite(desc).all() and abs(float(desc.norm(dim=1).mean()) - 1.0) < 1e-4
 
-    roof = dominant_kernel_roofline(step, dev_pts, dev_len, flush) if rank == 0 else None
+    # per-kernel event timing needs the launches serialised: the single-stream pipeline
+    roof = dominant_kernel_roofline(lambda a, b: step(a, b, pipe1), dev_pts, dev_len, flush) if rank == 0 else None
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -310,7 +316,7 @@ def run_b200(args):
     line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
             'warmup': max(args.warmup, 3), 'ms_per_step': total / args.steps, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': workload_config(args.pairs, limits),
+            'config': workload_config(args.pairs, limits, args.streams),
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(host_pts.numel() * 4 + host_len.numel() * 8),
                     'd2h_bytes_per_step': int(out_desc.numel() * 4 + out_dist.numel() * 4),
                     'ms_per_step': total_e2e / args.steps},

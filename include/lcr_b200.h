@@ -90,13 +90,23 @@ int lcr_radius_neighbors(const float* q_points, int64_t nq_total, const float* s
  * bias[c_out] or NULL -> out[m_query, c_out].  s_flags[n_support] (u8, optional): 1 where the
  * feature row sum is > 0 (the reference's neighbour_num counts only those rows, :113-116);
  * NULL counts every valid neighbour.  c_in in {1, 32, 64, 128, 256}.  weights_nk (optional): the same
- * weights transposed to [c_out, 15 * c_in]; when given, the contraction runs on the tcgen05 3xTF32 GEMM.
+ * weights transposed to [c_out, 15 * c_in]; when given, the contraction runs on the tcgen05 3xTF32 GEMM
+ * (weights_nk_lo != NULL: the pair is the pre-split hi / lo halves from lcr_tf32_split).
+ * kernel_points_host (optional): HOST copy of kernel_points; when given (and c_in > 1) the gather runs in
+ * its sparse form with the kernel points as constant-bank kernel arguments, otherwise the dense form
+ * reads them from device memory.
  * ---------------------------------------------------------------------------------------- */
 size_t lcr_kpconv_ws_bytes(int64_t m_query, int c_in);
+/* Tuning knob (A/B measurements, tests): gather variant used when kernel_points_host is given.
+ * 0 = exact dense loop (IEEE sqrt / divide influences, also used without host kernel points), 1 = fast dense
+ * loop (rsqrt influences, constant-bank kernel points), 2 = sparse influence lists, 3 = auto (default; the fast
+ * dense loop, which measured fastest for every channel width on B200). */
+void lcr_set_gather_mode(int mode);
 int lcr_kpconv(const float* s_feats, const uint8_t* s_flags, int64_t n_support, const float* q_points,
                int64_t m_query, const float* s_points, const int32_t* idx, int ld_idx, int H,
-               const float* kernel_points, float sigma, const float* weights, const float* weights_nk,
-               const float* bias, int c_in, int c_out, float* out, void* ws, size_t ws_bytes, void* stream);
+               const float* kernel_points, const float* kernel_points_host, float sigma, const float* weights,
+               const float* weights_nk, const float* weights_nk_lo, const float* bias, int c_in, int c_out,
+               float* out, void* ws, size_t ws_bytes, void* stream);
 /* flags[r] = (sum_c x[r, c] > 0) */
 int lcr_row_flags(const float* x, int64_t rows, int channels, uint8_t* flags, void* stream);
 
@@ -157,8 +167,14 @@ int lcr_linear_ex(const float* x, int64_t n_rows, int c_in, int ld_x, const floa
 /* Tensor-core variant of lcr_linear_ex (tcgen05.mma kind::tf32 with 3xTF32 operand splitting, fp32-class
  * accuracy): `weight` is in nn.Linear layout [c_out, c_in] (no transpose).  Requires c_in % 32 == 0,
  * c_out % 4 == 0. */
-int lcr_linear_tc(const float* x, int64_t n_rows, int c_in, int ld_x, const float* weight, int c_out, int ld_w,
-                  const float* bias, const float* rowscale, int act, float* out, int ld_out, void* stream);
+int lcr_linear_tc(const float* x, int64_t n_rows, int c_in, int ld_x, const float* weight, const float* weight_lo,
+                  int c_out, int ld_w, const float* bias, const float* rowscale, int act, float* out, int ld_out,
+                  void* stream);
+/* Operand split of the 3xTF32 scheme for a weight tensor, done once: hi = rna_tf32(w), lo = rna_tf32(w - hi).
+ * Passing (hi, lo) as (weight, weight_lo) to lcr_linear_tc / (weights_nk, weights_nk_lo) to lcr_kpconv lets
+ * the GEMM copy both halves of its weight tiles instead of splitting them in every CTA; weight_lo = NULL
+ * splits on the fly. */
+int lcr_tf32_split(const float* w, int64_t count, float* hi, float* lo, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * a7. 3D-RoFormer pieces (experiments/lcrnet/modules/thdroformer/*).

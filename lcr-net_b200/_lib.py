@@ -28,8 +28,9 @@ SIGNATURES = {
     'lcr_radius_neighbors': (c_i32, [c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_i32, c_f32, c_i32, c_vp, c_i32, c_vp,
                                      c_vp, c_vp, c_vp, c_sz, c_vp]),
     'lcr_kpconv_ws_bytes': (c_sz, [c_i64, c_i32]),
-    'lcr_kpconv': (c_i32, [c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_i32, c_i32, c_vp, c_f32, c_vp, c_vp, c_vp,
-                           c_i32, c_i32, c_vp, c_vp, c_sz, c_vp]),
+    'lcr_kpconv': (c_i32, [c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_f32, c_vp, c_vp,
+                           c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_sz, c_vp]),
+    'lcr_set_gather_mode': (None, [c_i32]),
     'lcr_row_flags': (c_i32, [c_vp, c_i64, c_i32, c_vp, c_vp]),
     'lcr_linear': (c_i32, [c_vp, c_i64, c_i32, c_vp, c_i32, c_vp, c_vp, c_vp]),
     'lcr_group_norm_ws_bytes': (c_sz, [c_i64, c_i32, c_i32]),
@@ -41,7 +42,9 @@ SIGNATURES = {
     'lcr_netvlad': (c_i32, [c_vp, c_i64, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_sz,
                             c_vp]),
     'lcr_linear_ex': (c_i32, [c_vp, c_i64, c_i32, c_i32, c_vp, c_i32, c_vp, c_vp, c_i32, c_vp, c_i32, c_vp]),
-    'lcr_linear_tc': (c_i32, [c_vp, c_i64, c_i32, c_i32, c_vp, c_i32, c_i32, c_vp, c_vp, c_i32, c_vp, c_i32, c_vp]),
+    'lcr_linear_tc': (c_i32, [c_vp, c_i64, c_i32, c_i32, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_i32, c_vp, c_i32,
+                              c_vp]),
+    'lcr_tf32_split': (c_i32, [c_vp, c_i64, c_vp, c_vp, c_vp]),
     'lcr_layer_norm': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_f32, c_i32, c_vp, c_vp]),
     'lcr_rope': (c_i32, [c_vp, c_i32, c_vp, c_i64, c_vp]),
     'lcr_attention': (c_i32, [c_vp, c_i32, c_vp, c_i32, c_vp, c_i32, c_vp, c_vp, c_i32, c_i64, c_i32, c_i32, c_vp,
@@ -109,13 +112,15 @@ def stream_ptr(device=None):
 
 
 class _Workspace:
-    """Grow-only scratch buffers, one per (device, slot)."""
+    """Grow-only scratch buffers, one per (device, stream, slot): work queued on different
+    streams (pipeline.py) never shares scratch memory."""
 
     def __init__(self):
         self._buf = {}
 
     def get(self, nbytes, device, slot=0):
-        key = (device.index if device.index is not None else torch.cuda.current_device(), slot)
+        key = (device.index if device.index is not None else torch.cuda.current_device(),
+               torch.cuda.current_stream(device).cuda_stream, slot)
         b = self._buf.get(key)
         if b is None or b.numel() < nbytes:
             b = torch.empty(max(int(nbytes * 1.25), 1 << 20), dtype=torch.uint8, device=device)

@@ -15,24 +15,35 @@
 //       owns C/32 channels and accumulates wf[k][c] = sum_h w[k,h] * feat[idx[h], c] in registers
 //       with coalesced 128 B feature-row loads.  Output wf[M, 15*C] and 1/neighbour_num.
 //   (B) the fp32 GEMM of gemm.cu: [M, 15C] x [15C, O] with the 1/num row scale and bias fused.
+#include <stdlib.h>
+#include <string.h>
+
 #include "common.cuh"
 
 int lcr_gemm_f32(const float* A, int lda, const float* B, int ldb, float* C, int ldc, int M, int N, int K,
                  const float* rowscale, const float* bias, cudaStream_t stream);
-int lcr_gemm_tf32x3(const float* A, int lda, const float* W, int ldw, float* C, int ldc, int M, int N, int K,
-                    const float* rowscale, const float* bias, int relu, cudaStream_t stream);
+int lcr_gemm_tf32x3(const float* A, int lda, const float* W, const float* W_lo, int ldw, float* C, int ldc, int M, int N,
+                    int K, const float* rowscale, const float* bias, int relu, cudaStream_t stream);
 
 namespace {
 
 constexpr int KP = 15;  // kernel points (config_model.py:35)
 
 // ------------------------------------------------------------------ KPConv gather
-template <int CPL>  // channels per lane: C = 32 * CPL
+// Kernel points by value: they land in the constant bank and feed the FADDs as immediate operands.
+struct KpArg { float v[KP * 3]; };
+
+// FAST: kernel points from the constant bank (kp) instead of shared memory (kpts), and the influence
+// 1 - d/sigma with d = d2 * rsqrt(d2) and a multiply by 1/sigma instead of the IEEE sqrt + divide
+// sequences (<= 3e-7 absolute from the reference's weights; parity bar 1e-4): the influence pass is
+// ~2.5x shorter, which matters most for the narrow layers where it outweighs the accumulation.
+template <int CPL, bool FAST>  // channels per lane: C = 32 * CPL
 __global__ void __launch_bounds__(128)
 kpconv_gather_kernel(const float* __restrict__ s_feats, const float* __restrict__ q_pts,
                      const float* __restrict__ s_pts, const int32_t* __restrict__ idx, int ld_idx, int H,
-                     const float* __restrict__ kpts, float sigma, const uint8_t* __restrict__ flags, int M,
-                     int N, float* __restrict__ wf, float* __restrict__ rowscale) {
+                     const float* __restrict__ kpts, const KpArg kp, float sigma,
+                     const uint8_t* __restrict__ flags, int M, int N, float* __restrict__ wf,
+                     float* __restrict__ rowscale) {
   constexpr int C = 32 * CPL;
   // influences of 32 neighbours, packed as float4 groups of kernel points: [k/4][neighbour] so that
   // lanes write conflict-free 16-B vectors and the accumulation loop reads 4 broadcast LDS.128
@@ -40,11 +51,14 @@ kpconv_gather_kernel(const float* __restrict__ s_feats, const float* __restrict_
   __shared__ int s_j[4][32];
   __shared__ float s_kp[KP * 3];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (threadIdx.x < KP * 3) s_kp[threadIdx.x] = kpts[threadIdx.x];
-  __syncthreads();
+  if (!FAST) {
+    if (threadIdx.x < KP * 3) s_kp[threadIdx.x] = kpts[threadIdx.x];
+    __syncthreads();
+  }
   const int m = blockIdx.x * 4 + warp;
   if (m >= M) return;
   const float qx = q_pts[3 * m], qy = q_pts[3 * m + 1], qz = q_pts[3 * m + 2];
+  const float inv_sigma = 1.f / sigma;
   float acc[KP][CPL];
 #pragma unroll
   for (int k = 0; k < KP; k++)
@@ -67,9 +81,15 @@ kpconv_gather_kernel(const float* __restrict__ s_feats, const float* __restrict_
       float w[16];
 #pragma unroll
       for (int k = 0; k < KP; k++) {
-        const float dx = rx - s_kp[3 * k], dy = ry - s_kp[3 * k + 1], dz = rz - s_kp[3 * k + 2];
-        const float d2 = dx * dx + dy * dy + dz * dz;
-        w[k] = fmaxf(1.f - __fdiv_rn(sqrtf(d2), sigma), 0.f);
+        if (FAST) {
+          const float dx = rx - kp.v[3 * k], dy = ry - kp.v[3 * k + 1], dz = rz - kp.v[3 * k + 2];
+          const float d2 = dx * dx + dy * dy + dz * dz;
+          w[k] = fmaxf(fmaf(-d2 * rsqrtf(fmaxf(d2, 1e-30f)), inv_sigma, 1.f), 0.f);
+        } else {
+          const float dx = rx - s_kp[3 * k], dy = ry - s_kp[3 * k + 1], dz = rz - s_kp[3 * k + 2];
+          const float d2 = dx * dx + dy * dy + dz * dz;
+          w[k] = fmaxf(1.f - __fdiv_rn(sqrtf(d2), sigma), 0.f);
+        }
       }
       w[15] = 0.f;
 #pragma unroll
@@ -129,19 +149,148 @@ kpconv_gather_kernel(const float* __restrict__ s_feats, const float* __restrict_
   if (lane == 0) rowscale[m] = 1.f / (float)max(cnt, 1);
 }
 
-// C_in = 1 (encoder1_1): lanes over neighbours, 15 warp-reduced sums, then O outputs per query.
+// ------------------------------------------------------------------ KPConv gather, sparse form
+// A neighbour lies inside the influence radius sigma of only ~1.6 of the 15 kernel points (measured
+// on the synthetic and demo pyramids; never more than 5), so ~90 % of the dense FFMAs above multiply
+// by zero.  This kernel builds, per query and kernel point, the compacted list of (neighbour, weight)
+// entries with non-zero influence (warp ballot + popc, neighbour order preserved), then accumulates
+//   wf[k][:] = sum_{e in list k} w_e * feat[j_e][:]
+// with one shared-memory broadcast, one vector feature load and CPL FFMAs per ENTRY instead of per
+// (neighbour, kernel point) pair.  Lists are padded with zero-weight entries to a multiple of UN so
+// UN feature rows are in flight without predication.  Kernel points are passed by value (constant
+// bank operands).  The weight is 1 - d/sigma with d = d2 * rsqrt(d2) (<= 3e-7 absolute from the
+// reference's sqrt and divide; parity bar 1e-4).
+
+template <int CPL>
 __global__ void __launch_bounds__(128)
-kpconv_c1_kernel(const float* __restrict__ s_feats, const float* __restrict__ q_pts, const float* __restrict__ s_pts,
-                 const int32_t* __restrict__ idx, int ld_idx, int H, const float* __restrict__ kpts, float sigma,
-                 const float* __restrict__ weights /*[15,1,O]*/, const float* __restrict__ bias, int O, int M, int N,
-                 float* __restrict__ out) {
-  __shared__ float s_kp[KP * 3];
+kpconv_gather_sparse_kernel(const float* __restrict__ s_feats, const float* __restrict__ q_pts,
+                            const float* __restrict__ s_pts, const int32_t* __restrict__ idx, int ld_idx, int H,
+                            const KpArg kp, float sigma, const uint8_t* __restrict__ flags, int M, int N,
+                            float* __restrict__ wf, float* __restrict__ rowscale) {
+  constexpr int C = 32 * CPL;
+  constexpr int VEC = CPL >= 4 ? 4 : CPL;       // channels per vector load: lane owns [lane*VEC, +VEC) of every 32*VEC slab
+  constexpr int NV = CPL / VEC;
+  constexpr int UN = CPL >= 8 ? 2 : 4;          // feature rows in flight per lane
+  constexpr int CAP = 64 + 4;                   // entries per kernel point per 64-neighbour super-chunk
+  __shared__ __align__(16) float2 s_ent[4][KP][CAP];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (threadIdx.x < KP * 3) s_kp[threadIdx.x] = kpts[threadIdx.x];
-  __syncthreads();
   const int m = blockIdx.x * 4 + warp;
   if (m >= M) return;
   const float qx = q_pts[3 * m], qy = q_pts[3 * m + 1], qz = q_pts[3 * m + 2];
+  const float sig2 = sigma * sigma * 1.000001f, inv_sigma = 1.f / sigma;
+  const unsigned lt = (1u << lane) - 1u;
+  float acc[KP][CPL];
+#pragma unroll
+  for (int k = 0; k < KP; k++)
+#pragma unroll
+    for (int i = 0; i < CPL; i++) acc[k][i] = 0.f;
+  int cnt = 0;
+  const int32_t* row = idx + (size_t)m * ld_idx;
+  float2(*ent)[CAP] = s_ent[warp];
+  for (int h0 = 0; h0 < H; h0 += 64) {
+    int nk[KP];
+#pragma unroll
+    for (int k = 0; k < KP; k++) nk[k] = 0;
+#pragma unroll
+    for (int sub = 0; sub < 2; sub++) {
+      const int h = h0 + sub * 32 + lane;
+      const int j = h < H ? row[h] : N;
+      const bool valid = j < N;
+      if (!__any_sync(0xffffffffu, valid)) continue;
+      float rx = 0.f, ry = 0.f, rz = 0.f;
+      if (valid) {
+        rx = s_pts[3 * (size_t)j] - qx;
+        ry = s_pts[3 * (size_t)j + 1] - qy;
+        rz = s_pts[3 * (size_t)j + 2] - qz;
+        cnt += flags ? (int)flags[j] : 1;
+      }
+#pragma unroll
+      for (int k = 0; k < KP; k++) {
+        const float dx = rx - kp.v[3 * k], dy = ry - kp.v[3 * k + 1], dz = rz - kp.v[3 * k + 2];
+        const float d2 = dx * dx + dy * dy + dz * dz;
+        const bool in = valid && d2 < sig2;
+        const unsigned mask = __ballot_sync(0xffffffffu, in);
+        if (in) {
+          const float d = d2 * rsqrtf(fmaxf(d2, 1e-30f));
+          ent[k][nk[k] + __popc(mask & lt)] = make_float2(__int_as_float(j), fmaxf(fmaf(-d, inv_sigma, 1.f), 0.f));
+        }
+        nk[k] += __popc(mask);
+      }
+    }
+    if (lane < UN) {
+#pragma unroll
+      for (int k = 0; k < KP; k++) ent[k][nk[k] + lane] = make_float2(__int_as_float(0), 0.f);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < KP; k++) {
+      for (int e = 0; e < nk[k]; e += UN) {
+        float2 en[UN];
+#pragma unroll
+        for (int u = 0; u < UN; u += 2) {
+          const float4 t = *reinterpret_cast<const float4*>(&ent[k][e + u]);
+          en[u] = make_float2(t.x, t.y);
+          en[u + 1] = make_float2(t.z, t.w);
+        }
+        float fv[UN][CPL];
+#pragma unroll
+        for (int u = 0; u < UN; u++) {
+          const float* f = s_feats + (size_t)__float_as_int(en[u].x) * C + lane * VEC;
+#pragma unroll
+          for (int v = 0; v < NV; v++) {
+            if (VEC == 4) {
+              const float4 t = *reinterpret_cast<const float4*>(f + v * 128);
+              fv[u][4 * v] = t.x; fv[u][4 * v + 1] = t.y; fv[u][4 * v + 2] = t.z; fv[u][4 * v + 3] = t.w;
+            } else if (VEC == 2) {
+              const float2 t = *reinterpret_cast<const float2*>(f);
+              fv[u][0] = t.x; fv[u][1] = t.y;
+            } else {
+              fv[u][0] = f[0];
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < UN; u++)
+#pragma unroll
+          for (int i = 0; i < CPL; i++) acc[k][i] = fmaf(en[u].y, fv[u][i], acc[k][i]);
+      }
+    }
+    __syncwarp();
+  }
+  cnt = lcr_warp_sum(cnt);
+  float* o = wf + (size_t)m * (KP * C) + lane * VEC;
+#pragma unroll
+  for (int k = 0; k < KP; k++)
+#pragma unroll
+    for (int v = 0; v < NV; v++) {
+      if (VEC == 4)
+        *reinterpret_cast<float4*>(o + k * C + v * 128) =
+            make_float4(acc[k][4 * v], acc[k][4 * v + 1], acc[k][4 * v + 2], acc[k][4 * v + 3]);
+      else if (VEC == 2)
+        *reinterpret_cast<float2*>(o + k * C) = make_float2(acc[k][0], acc[k][1]);
+      else
+        o[k * C] = acc[k][0];
+    }
+  if (lane == 0) rowscale[m] = 1.f / (float)max(cnt, 1);
+}
+
+// C_in = 1 (encoder1_1): lanes over neighbours, 15 warp-reduced sums, then O outputs per query.
+template <bool FAST>
+__global__ void __launch_bounds__(128)
+kpconv_c1_kernel(const float* __restrict__ s_feats, const float* __restrict__ q_pts, const float* __restrict__ s_pts,
+                 const int32_t* __restrict__ idx, int ld_idx, int H, const float* __restrict__ kpts, const KpArg kp,
+                 float sigma, const float* __restrict__ weights /*[15,1,O]*/, const float* __restrict__ bias, int O,
+                 int M, int N, float* __restrict__ out) {
+  __shared__ float s_kp[KP * 3];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (!FAST) {
+    if (threadIdx.x < KP * 3) s_kp[threadIdx.x] = kpts[threadIdx.x];
+    __syncthreads();
+  }
+  const int m = blockIdx.x * 4 + warp;
+  if (m >= M) return;
+  const float qx = q_pts[3 * m], qy = q_pts[3 * m + 1], qz = q_pts[3 * m + 2];
+  const float inv_sigma = 1.f / sigma;
   float ws[KP];
 #pragma unroll
   for (int k = 0; k < KP; k++) ws[k] = 0.f;
@@ -155,9 +304,15 @@ kpconv_c1_kernel(const float* __restrict__ s_feats, const float* __restrict__ q_
                   rz = s_pts[3 * (size_t)j + 2] - qz;
 #pragma unroll
       for (int k = 0; k < KP; k++) {
-        const float dx = rx - s_kp[3 * k], dy = ry - s_kp[3 * k + 1], dz = rz - s_kp[3 * k + 2];
-        const float d2 = dx * dx + dy * dy + dz * dz;
-        ws[k] = fmaf(fmaxf(1.f - __fdiv_rn(sqrtf(d2), sigma), 0.f), f, ws[k]);
+        if (FAST) {
+          const float dx = rx - kp.v[3 * k], dy = ry - kp.v[3 * k + 1], dz = rz - kp.v[3 * k + 2];
+          const float d2 = dx * dx + dy * dy + dz * dz;
+          ws[k] = fmaf(fmaxf(fmaf(-d2 * rsqrtf(fmaxf(d2, 1e-30f)), inv_sigma, 1.f), 0.f), f, ws[k]);
+        } else {
+          const float dx = rx - s_kp[3 * k], dy = ry - s_kp[3 * k + 1], dz = rz - s_kp[3 * k + 2];
+          const float d2 = dx * dx + dy * dy + dz * dz;
+          ws[k] = fmaf(fmaxf(1.f - __fdiv_rn(sqrtf(d2), sigma), 0.f), f, ws[k]);
+        }
       }
       cnt += f > 0.f;
     }
@@ -177,49 +332,39 @@ kpconv_c1_kernel(const float* __restrict__ s_feats, const float* __restrict__ q_
 
 // ------------------------------------------------------------------ GroupNorm statistics
 // partial[(s * n_chunks + chunk) * G + g] = (sum, sumsq) over rows of the chunk x channels of g.
-constexpr int kGnRows = 64;
+// A chunk is gn_chunk_rows(C) rows (>= 64 KB of x per block for every C).
+constexpr int kGnRows = 64;   // smallest chunk (workspace sizing)
+static inline int gn_chunk_rows(int C) { return C >= 256 ? 64 : 64 * (256 / C); }
 
 __global__ void __launch_bounds__(256)
 gn_partial_kernel(const float* __restrict__ x, int C, int G, const int64_t* __restrict__ stack_off, int n_chunks,
-                  double2* __restrict__ partial) {
-  // per-column partial sums of this chunk's rows go through shared memory, then one thread per
-  // group adds its columns in a fixed order (deterministic; no float atomics)
+                  int chunk_rows, double2* __restrict__ partial) {
+  // 16-byte loads: a thread owns one quad of columns and every (256 / (C/4))-th row of the chunk;
+  // its per-column partial sums go through shared memory, then one thread per group adds its
+  // columns in a fixed order (deterministic; no float atomics)
   __shared__ float s_sum[1024], s_sq[1024];
   const int s = blockIdx.y, chunk = blockIdx.x;
-  const int64_t r0 = stack_off[s] + (int64_t)chunk * kGnRows;
-  const int64_t r1 = min(r0 + kGnRows, stack_off[s + 1]);
-  int slots;  // number of shared-memory slots per column group layout
-  if (C >= 256) {
-    for (int c = threadIdx.x; c < C; c += 256) {
-      float a = 0.f, b = 0.f;
-#pragma unroll 8
-      for (int64_t r = r0; r < r1; r++) {
-        const float v = x[r * C + c];
-        a += v;
-        b = fmaf(v, v, b);
-      }
-      s_sum[c] = a;
-      s_sq[c] = b;
+  const int64_t r0 = stack_off[s] + (int64_t)chunk * chunk_rows;
+  const int64_t r1 = min(r0 + chunk_rows, stack_off[s + 1]);
+  const int quads = C >> 2;                       // <= 256
+  const int cq = threadIdx.x % quads, rl = threadIdx.x / quads, nrl = 256 / quads;
+  if (rl < nrl) {
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    const float* xp = x + 4 * cq;
+#pragma unroll 4
+    for (int64_t r = r0 + rl; r < r1; r += nrl) {
+      const float4 v = *reinterpret_cast<const float4*>(xp + r * C);
+      a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+      b.x = fmaf(v.x, v.x, b.x); b.y = fmaf(v.y, v.y, b.y); b.z = fmaf(v.z, v.z, b.z); b.w = fmaf(v.w, v.w, b.w);
     }
-    slots = 1;
-  } else {
-    const int rl = 256 / C, c = threadIdx.x % C, rlane = threadIdx.x / C;  // 256/C row lanes
-    float a = 0.f, b = 0.f;
-#pragma unroll 8
-    for (int64_t r = r0 + rlane; r < r1; r += rl) {
-      const float v = x[r * C + c];
-      a += v;
-      b = fmaf(v, v, b);
-    }
-    s_sum[rlane * C + c] = a;
-    s_sq[rlane * C + c] = b;
-    slots = rl;
+    *reinterpret_cast<float4*>(s_sum + rl * C + 4 * cq) = a;
+    *reinterpret_cast<float4*>(s_sq + rl * C + 4 * cq) = b;
   }
   __syncthreads();
   if (threadIdx.x < G) {
     const int cpg = C / G;
     double a = 0.0, b = 0.0;
-    for (int r = 0; r < slots; r++)
+    for (int r = 0; r < nrl; r++)
       for (int cc = 0; cc < cpg; cc++) {
         a += (double)s_sum[r * C + threadIdx.x * cpg + cc];
         b += (double)s_sq[r * C + threadIdx.x * cpg + cc];
@@ -230,13 +375,13 @@ gn_partial_kernel(const float* __restrict__ x, int C, int G, const int64_t* __re
 
 // one warp per (stack, group): fixed-order reduction over chunks -> mean, rstd
 __global__ void gn_finalize_kernel(const double2* __restrict__ partial, int G, int C,
-                                   const int64_t* __restrict__ stack_off, int n_chunks, int S, float eps,
-                                   float2* __restrict__ stats) {
+                                   const int64_t* __restrict__ stack_off, int n_chunks, int chunk_rows, int S,
+                                   float eps, float2* __restrict__ stats) {
   const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (w >= S * G) return;
   const int s = w / G, g = w % G;
   const int64_t rows = stack_off[s + 1] - stack_off[s];
-  const int used = (int)((rows + kGnRows - 1) / kGnRows);
+  const int used = (int)((rows + chunk_rows - 1) / chunk_rows);
   double a = 0.0, b = 0.0;
   for (int ch = lane; ch < used; ch += 32) {
     const double2 p = partial[((size_t)s * n_chunks + ch) * G + g];
@@ -311,6 +456,91 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(GnApplyArgs a) {
   }
 }
 
+// Streaming variant (every call except row flags on C > 128): a lane keeps ONE quad of columns for
+// kGnIter consecutive row groups, so gamma/beta and the per-stack scale/shift
+//   y = x * (rstd * gamma) + (beta - mean * rstd * gamma)
+// live in registers and are recomputed only when the rows cross into the next stack; the inner
+// loop is one 16-byte load, 4 FFMA (+4 for the normalised shortcut), the activation and one store.
+constexpr int kGnIter = 8;
+
+struct GnAffine {
+  float sc[4], sh[4];
+  __device__ __forceinline__ void set(const float2* __restrict__ stats, int s, int G, int cpg, int c, float4 g, float4 b) {
+    const float gg[4] = {g.x, g.y, g.z, g.w}, bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const float2 st = stats[s * G + (c + i) / cpg];
+      sc[i] = st.y * gg[i];
+      sh[i] = fmaf(-st.x, sc[i], bb[i]);
+    }
+  }
+};
+
+template <int MODE>  // 0: no other, 1: + raw other, 2: + normalised other
+__global__ void __launch_bounds__(256) gn_apply_stream_kernel(GnApplyArgs a) {
+  const int seg_lanes = min(32, a.C >> 2);       // lanes covering one segment of min(C, 128) channels
+  const int nseg = a.C > 128 ? a.C >> 7 : 1;
+  const int rpw = 32 / seg_lanes;                // rows per warp iteration
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int seg = (int)(warp % nseg);
+  const int64_t rb = warp / nseg;
+  const int sub = lane % seg_lanes, rsub = lane / seg_lanes;
+  const int c = seg * 128 + sub * 4;
+  const int cpg = a.C / a.G;
+  int64_t r = rb * (rpw * kGnIter) + rsub;
+  if (r >= a.rows) {
+    if (a.flags == nullptr) return;
+    r = a.rows;                                   // stay for the shuffles below
+  }
+  const float4 g1 = *reinterpret_cast<const float4*>(a.gamma + c), b1 = *reinterpret_cast<const float4*>(a.beta + c);
+  float4 g2 = g1, b2 = b1;
+  if (MODE == 2) {
+    g2 = *reinterpret_cast<const float4*>(a.gamma2 + c);
+    b2 = *reinterpret_cast<const float4*>(a.beta2 + c);
+  }
+  int s = r < a.rows ? lcr_find_segment(a.stack_off, a.S, r) : a.S - 1;
+  int64_t next = a.stack_off[s + 1];
+  GnAffine f1, f2;
+  f1.set(a.stats, s, a.G, cpg, c, g1, b1);
+  if (MODE == 2) f2.set(a.stats2, s, a.G, cpg, c, g2, b2);
+#pragma unroll 2
+  for (int it = 0; it < kGnIter; it++, r += rpw) {
+    const bool active = r < a.rows;
+    float rowsum = 0.f;
+    if (active) {
+      if (r >= next) {
+        while (r >= a.stack_off[s + 1]) s++;
+        next = a.stack_off[s + 1];
+        f1.set(a.stats, s, a.G, cpg, c, g1, b1);
+        if (MODE == 2) f2.set(a.stats2, s, a.G, cpg, c, g2, b2);
+      }
+      const float4 v = *reinterpret_cast<const float4*>(a.x + r * a.C + c);
+      float o[4] = {fmaf(v.x, f1.sc[0], f1.sh[0]), fmaf(v.y, f1.sc[1], f1.sh[1]), fmaf(v.z, f1.sc[2], f1.sh[2]),
+                    fmaf(v.w, f1.sc[3], f1.sh[3])};
+      if (MODE >= 1) {
+        const float4 w = *reinterpret_cast<const float4*>(a.x2 + r * a.C + c);
+        if (MODE == 2) {
+          o[0] += fmaf(w.x, f2.sc[0], f2.sh[0]); o[1] += fmaf(w.y, f2.sc[1], f2.sh[1]);
+          o[2] += fmaf(w.z, f2.sc[2], f2.sh[2]); o[3] += fmaf(w.w, f2.sc[3], f2.sh[3]);
+        } else {
+          o[0] += w.x; o[1] += w.y; o[2] += w.z; o[3] += w.w;
+        }
+      }
+      if (a.act) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) o[i] = o[i] > 0.f ? o[i] : o[i] * a.slope;
+      }
+      rowsum = (o[0] + o[1]) + (o[2] + o[3]);
+      *reinterpret_cast<float4*>(a.y + r * a.C + c) = make_float4(o[0], o[1], o[2], o[3]);
+    }
+    if (a.flags) {   // only launched with nseg == 1: the row lives inside the warp
+      for (int o = seg_lanes >> 1; o > 0; o >>= 1) rowsum += __shfl_xor_sync(0xffffffffu, rowsum, o);
+      if (active && sub == 0) a.flags[r] = rowsum > 0.f;
+    }
+  }
+}
+
 // ------------------------------------------------------------------ max-pool over neighbours
 __global__ void __launch_bounds__(256)
 maxpool_kernel(const float* __restrict__ x, const int32_t* __restrict__ idx, int ld_idx, int H, int M, int N, int C,
@@ -319,18 +549,38 @@ maxpool_kernel(const float* __restrict__ x, const int32_t* __restrict__ idx, int
   const int m = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (m >= M) return;
   const int32_t* row = idx + (size_t)m * ld_idx;
-  for (int c = lane * 4; c < C; c += 128) {
+  // the 32 lanes fetch 32 neighbour indices at once (one coalesced load) and hand them round by
+  // shuffle, so four independent 16-byte feature loads are in flight per lane
+  for (int c0 = 0; c0 < C; c0 += 128) {
+    const int c = c0 + lane * 4;
+    const bool on = c < C;
     float4 best = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-    for (int h = 0; h < H; h++) {
-      const int j = row[h];
-      // the pad row of the reference is a row of zeros appended to x (functional.py:64)
-      const float4 v = j < N ? *reinterpret_cast<const float4*>(x + (size_t)j * C + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-      best.x = fmaxf(best.x, v.x);
-      best.y = fmaxf(best.y, v.y);
-      best.z = fmaxf(best.z, v.z);
-      best.w = fmaxf(best.w, v.w);
+    for (int h0 = 0; h0 < H; h0 += 32) {
+      const int jl = h0 + lane < H ? row[h0 + lane] : -1;
+      const int n = min(32, H - h0);
+      int hh = 0;
+      for (; hh + 4 <= n; hh += 4) {
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int j = __shfl_sync(0xffffffffu, jl, hh + u);
+          // the pad row of the reference is a row of zeros appended to x (functional.py:64)
+          v[u] = (on && j < N) ? *reinterpret_cast<const float4*>(x + (size_t)j * C + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          best.x = fmaxf(best.x, v[u].x); best.y = fmaxf(best.y, v[u].y);
+          best.z = fmaxf(best.z, v[u].z); best.w = fmaxf(best.w, v[u].w);
+        }
+      }
+      for (; hh < n; hh++) {
+        const int j = __shfl_sync(0xffffffffu, jl, hh);
+        const float4 v = (on && j < N) ? *reinterpret_cast<const float4*>(x + (size_t)j * C + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        best.x = fmaxf(best.x, v.x); best.y = fmaxf(best.y, v.y);
+        best.z = fmaxf(best.z, v.z); best.w = fmaxf(best.w, v.w);
+      }
     }
-    *reinterpret_cast<float4*>(out + (size_t)m * C + c) = best;
+    if (on) *reinterpret_cast<float4*>(out + (size_t)m * C + c) = best;
   }
 }
 
@@ -346,6 +596,19 @@ __global__ void rowflag_kernel(const float* __restrict__ x, int64_t rows, int C,
 
 }  // namespace
 
+// gather variant when host kernel points are given: 0 exact dense loop (IEEE sqrt/divide influences),
+// 1 fast dense loop, 2 sparse influence lists, 3 auto (default).  LCR_GATHER={exact,dense,sparse,auto}
+// sets the default; lcr_set_gather_mode overrides it.
+static int g_gather_mode = -1;
+static int gather_mode() {
+  if (g_gather_mode < 0) {
+    const char* e = getenv("LCR_GATHER");
+    g_gather_mode = !e ? 3 : !strcmp(e, "exact") ? 0 : !strcmp(e, "dense") ? 1 : !strcmp(e, "sparse") ? 2 : 3;
+  }
+  return g_gather_mode;
+}
+extern "C" void lcr_set_gather_mode(int mode) { g_gather_mode = mode < 0 || mode > 3 ? 3 : mode; }
+
 // ================================================================== C ABI
 extern "C" size_t lcr_kpconv_ws_bytes(int64_t m_rows, int c_in) {
   return lcr_align_up((size_t)m_rows * KP * c_in * sizeof(float)) + lcr_align_up((size_t)m_rows * sizeof(float)) + 256;
@@ -353,7 +616,8 @@ extern "C" size_t lcr_kpconv_ws_bytes(int64_t m_rows, int c_in) {
 
 extern "C" int lcr_kpconv(const float* s_feats, const uint8_t* s_flags, int64_t n_support, const float* q_points,
                           int64_t m_query, const float* s_points, const int32_t* idx, int ld_idx, int H,
-                          const float* kernel_points, float sigma, const float* weights, const float* weights_nk,
+                          const float* kernel_points, const float* kernel_points_host, float sigma,
+                          const float* weights, const float* weights_nk, const float* weights_nk_lo,
                           const float* bias, int c_in, int c_out, float* out, void* ws, size_t ws_bytes,
                           void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
@@ -367,8 +631,16 @@ extern "C" int lcr_kpconv(const float* s_feats, const uint8_t* s_flags, int64_t 
   const unsigned grid = (unsigned)((M + 3) / 4);
   if (c_in == 1) {
     LcrProfScope prof("kpconv_c1", 2.0 * M * KP * (H + c_out), 4.0 * M * H + 16.0 * (M + N) + 4.0 * M * c_out, stream);
-    kpconv_c1_kernel<<<grid, 128, 0, stream>>>(s_feats, q_points, s_points, idx, ld_idx, H, kernel_points, sigma,
-                                               weights, bias, c_out, M, N, out);
+    KpArg kp;
+    const bool fast = kernel_points_host != nullptr && gather_mode() != 0;
+    if (fast) memcpy(kp.v, kernel_points_host, sizeof(kp.v));
+    else memset(kp.v, 0, sizeof(kp.v));
+    if (fast)
+      kpconv_c1_kernel<true><<<grid, 128, 0, stream>>>(s_feats, q_points, s_points, idx, ld_idx, H, kernel_points, kp,
+                                                       sigma, weights, bias, c_out, M, N, out);
+    else
+      kpconv_c1_kernel<false><<<grid, 128, 0, stream>>>(s_feats, q_points, s_points, idx, ld_idx, H, kernel_points, kp,
+                                                        sigma, weights, bias, c_out, M, N, out);
     LCR_LAUNCHED(1);
     LCR_CUDA_CHECK_LAUNCH();
     return LCR_OK;
@@ -380,9 +652,22 @@ extern "C" int lcr_kpconv(const float* s_feats, const uint8_t* s_flags, int64_t 
   {
   LcrProfScope prof("kpconv_gather", 2.0 * M * KP * (double)H * c_in,
                     4.0 * M * H + 4.0 * (double)N * c_in + 12.0 * (M + N) + 4.0 * (double)M * KP * c_in, stream);
-#define LCR_GATHER(CPL)                                                                                        \
-  kpconv_gather_kernel<CPL><<<grid, 128, 0, stream>>>(s_feats, q_points, s_points, idx, ld_idx, H, kernel_points, \
-                                                      sigma, s_flags, M, N, wf, rowscale)
+  // variant (see gather_mode): exact dense / fast dense / sparse lists
+  int mode = kernel_points_host == nullptr ? 0 : gather_mode();
+  if (mode == 3) mode = 1;   // auto: measured on B200, the fast dense loop wins or ties for every width (scripts/bench_gather.py)
+  KpArg kp;
+  if (mode != 0) memcpy(kp.v, kernel_points_host, sizeof(kp.v));
+  else memset(kp.v, 0, sizeof(kp.v));
+#define LCR_GATHER(CPL)                                                                                             \
+  if (mode == 0)                                                                                                    \
+    kpconv_gather_kernel<CPL, false><<<grid, 128, 0, stream>>>(s_feats, q_points, s_points, idx, ld_idx, H,         \
+                                                               kernel_points, kp, sigma, s_flags, M, N, wf, rowscale); \
+  else if (mode == 1)                                                                                               \
+    kpconv_gather_kernel<CPL, true><<<grid, 128, 0, stream>>>(s_feats, q_points, s_points, idx, ld_idx, H,          \
+                                                              kernel_points, kp, sigma, s_flags, M, N, wf, rowscale); \
+  else                                                                                                              \
+    kpconv_gather_sparse_kernel<CPL><<<grid, 128, 0, stream>>>(s_feats, q_points, s_points, idx, ld_idx, H, kp,     \
+                                                               sigma, s_flags, M, N, wf, rowscale)
   switch (c_in) {
     case 32: LCR_GATHER(1); break;
     case 64: LCR_GATHER(2); break;
@@ -394,8 +679,8 @@ extern "C" int lcr_kpconv(const float* s_feats, const uint8_t* s_flags, int64_t 
   LCR_LAUNCHED(1);
   LCR_CUDA_CHECK_LAUNCH();
   if (weights_nk)  // tensor-core contraction: weights as [c_out, 15 * c_in]
-    return lcr_gemm_tf32x3(wf, KP * c_in, weights_nk, KP * c_in, out, c_out, M, c_out, KP * c_in, rowscale, bias, 0,
-                           stream);
+    return lcr_gemm_tf32x3(wf, KP * c_in, weights_nk, weights_nk_lo, KP * c_in, out, c_out, M, c_out, KP * c_in,
+                           rowscale, bias, 0, stream);
   return lcr_gemm_f32(wf, KP * c_in, weights, c_out, out, c_out, M, c_out, KP * c_in, rowscale, bias, stream);
 }
 
@@ -414,14 +699,15 @@ extern "C" int lcr_group_norm_stats(const float* x, int64_t rows, int channels, 
   LCR_REQUIRE(n_stacks >= 1 && ws && ws_bytes >= lcr_group_norm_ws_bytes(max_stack_rows, n_stacks, groups),
               "group_norm: workspace too small");
   if (rows == 0) return LCR_OK;
-  const int n_chunks = (int)((max_stack_rows + kGnRows - 1) / kGnRows) + 1;
+  const int chunk_rows = gn_chunk_rows(channels);
+  const int n_chunks = (int)((max_stack_rows + chunk_rows - 1) / chunk_rows) + 1;
   double2* partial = (double2*)ws;
   LcrProfScope prof("group_norm_stats", 3.0 * rows * channels, 4.0 * rows * channels, stream);
   dim3 grid(n_chunks, n_stacks);
-  gn_partial_kernel<<<grid, 256, 0, stream>>>(x, channels, groups, stack_off, n_chunks, partial);
+  gn_partial_kernel<<<grid, 256, 0, stream>>>(x, channels, groups, stack_off, n_chunks, chunk_rows, partial);
   const int warps = n_stacks * groups;
   gn_finalize_kernel<<<(warps * 32 + 255) / 256, 256, 0, stream>>>(partial, groups, channels, stack_off, n_chunks,
-                                                                   n_stacks, eps, (float2*)stats_out);
+                                                                   chunk_rows, n_stacks, eps, (float2*)stats_out);
   LCR_LAUNCHED(2);
   LCR_CUDA_CHECK_LAUNCH();
   return LCR_OK;
@@ -443,7 +729,18 @@ extern "C" int lcr_group_norm_apply(const float* x, const float* stats, const fl
   const int rpw = 32 / lpr;
   const int64_t warps = (rows + rpw - 1) / rpw;
   LcrProfScope prof("group_norm_apply", 6.0 * rows * channels, 4.0 * rows * channels * (x2 ? 3.0 : 2.0), stream);
-  gn_apply_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, stream>>>(a);
+  if (channels % 4 == 0 && (channels <= 128 || (channels % 128 == 0 && row_flags == nullptr))) {
+    const int seg_lanes = channels / 4 < 32 ? channels / 4 : 32;
+    const int nseg = channels > 128 ? channels / 128 : 1;
+    const int64_t rows_per_warp = (32 / seg_lanes) * kGnIter;
+    const int64_t nwarps = ((rows + rows_per_warp - 1) / rows_per_warp) * nseg;
+    const unsigned grid = (unsigned)((nwarps * 32 + 255) / 256);
+    if (!x2) gn_apply_stream_kernel<0><<<grid, 256, 0, stream>>>(a);
+    else if (!stats2) gn_apply_stream_kernel<1><<<grid, 256, 0, stream>>>(a);
+    else gn_apply_stream_kernel<2><<<grid, 256, 0, stream>>>(a);
+  } else {
+    gn_apply_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, stream>>>(a);
+  }
   LCR_LAUNCHED(1);
   LCR_CUDA_CHECK_LAUNCH();
   return LCR_OK;

@@ -99,11 +99,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
 // k-blocks (96 values of K): each chunk is accumulated in one of two TMEM buffers and then
 // PROMOTED: added, with IEEE rounding, into fp32 register accumulators by the producer warps
 // while the MMA warp already works on the next chunk in the other buffer.
-template <int BN, int STAGES>
+// PS: the weights arrive PRE-SPLIT (W = tf32 hi part, W_lo = tf32 lo part, same layout; made once per
+// weight tensor by lcr_tf32_split): both halves of a B tile are then plain cp.async copies and the
+// producers only split the activations.
+template <int BN, int STAGES, bool PS>
 __global__ void __launch_bounds__(kThreads, 1)
-gemm_tf32x3_kernel(const float* __restrict__ A, int lda, const float* __restrict__ W, int ldw, float* __restrict__ C,
-                   int ldc, int M, int N, int K, const float* __restrict__ rowscale, const float* __restrict__ bias,
-                   int relu) {
+gemm_tf32x3_kernel(const float* __restrict__ A, int lda, const float* __restrict__ W, const float* __restrict__ W_lo,
+                   int ldw, float* __restrict__ C, int ldc, int M, int N, int K, const float* __restrict__ rowscale,
+                   const float* __restrict__ bias, int relu) {
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte aligned tiles (SWIZZLE_128B atom = 8 rows x 128 B)
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -189,9 +192,12 @@ gemm_tf32x3_kernel(const float* __restrict__ A, int lda, const float* __restrict
           const int idx = tid + i * kProducerThreads;
           const int row = idx >> 3, chunk = idx & 7;
           const int gn = n0 + row;
-          const float* src = W + (size_t)(gn < N ? gn : 0) * ldw + k0 + chunk * 4;
+          const size_t goff = (size_t)(gn < N ? gn : 0) * ldw + k0 + chunk * 4;
           const uint32_t dst = b_hi + row * 128 + ((chunk ^ (row & 7)) << 4);
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(gn < N ? 16 : 0));
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(W + goff), "r"(gn < N ? 16 : 0));
+          if (PS)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + kBTile), "l"(W_lo + goff),
+                         "r"(gn < N ? 16 : 0));
         }
       }
       asm volatile("cp.async.commit_group;" ::: "memory");   // always: keeps the group count uniform
@@ -215,12 +221,14 @@ gemm_tf32x3_kernel(const float* __restrict__ A, int lda, const float* __restrict
           const float4 v = *reinterpret_cast<const float4*>(a_hi + row * 32 + ((chunk ^ (row & 7)) << 2));
           split_store(v, a_hi, a_lo, row, chunk);
         }
+        if (!PS) {
 #pragma unroll
-        for (int i = 0; i < kBLoads; i++) {
-          const int idx = tid + i * kProducerThreads;
-          const int row = idx >> 3, chunk = idx & 7;
-          const float4 v = *reinterpret_cast<const float4*>(b_hi + row * 32 + ((chunk ^ (row & 7)) << 2));
-          split_store(v, b_hi, b_lo, row, chunk);
+          for (int i = 0; i < kBLoads; i++) {
+            const int idx = tid + i * kProducerThreads;
+            const int row = idx >> 3, chunk = idx & 7;
+            const float4 v = *reinterpret_cast<const float4*>(b_hi + row * 32 + ((chunk ^ (row & 7)) << 2));
+            split_store(v, b_hi, b_lo, row, chunk);
+          }
         }
         // make the generic-proxy writes visible to the tensor-core (async) proxy, then signal
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -310,11 +318,11 @@ gemm_tf32x3_kernel(const float* __restrict__ A, int lda, const float* __restrict
 // pipelining: one single-use stage per k-block (no ring), accumulators stay in TMEM (one chunk, no
 // promotion), ~64 registers, so 2-3 CTAs share an SM and hide each other's prologue / epilogue.
 // The epilogue goes TMEM -> registers -> per-warp shared-memory transpose -> 128-byte row stores.
-template <int BN>
+template <int BN, bool PS>
 __global__ void __launch_bounds__(kThreads, BN >= 256 ? 2 : 3)
-gemm_tf32x3_small_kernel(const float* __restrict__ A, int lda, const float* __restrict__ W, int ldw,
-                         float* __restrict__ C, int ldc, int M, int N, int K, const float* __restrict__ rowscale,
-                         const float* __restrict__ bias, int relu) {
+gemm_tf32x3_small_kernel(const float* __restrict__ A, int lda, const float* __restrict__ W,
+                         const float* __restrict__ W_lo, int ldw, float* __restrict__ C, int ldc, int M, int N, int K,
+                         const float* __restrict__ rowscale, const float* __restrict__ bias, int relu) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   constexpr int kATile = BM * BK * 4, kBTile = BN * BK * 4;
@@ -347,7 +355,7 @@ gemm_tf32x3_small_kernel(const float* __restrict__ A, int lda, const float* __re
     constexpr int kALoads = BM * 8 / kProducerThreads, kBLoads = BN * 8 / kProducerThreads;
     for (int kb = 0; kb < nk; kb++) {
       const int k0 = kb * BK;
-      float4 ra[kALoads], rb[kBLoads];
+      float4 ra[kALoads], rb[kBLoads], rbl[PS ? kBLoads : 1];
 #pragma unroll
       for (int i = 0; i < kALoads; i++) {
         const int idx = tid + i * kProducerThreads;
@@ -361,6 +369,9 @@ gemm_tf32x3_small_kernel(const float* __restrict__ A, int lda, const float* __re
         const int gn = n0 + (idx >> 3);
         rb[i] = gn < N ? *reinterpret_cast<const float4*>(W + (size_t)gn * ldw + k0 + (idx & 7) * 4)
                        : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (PS)
+          rbl[i] = gn < N ? *reinterpret_cast<const float4*>(W_lo + (size_t)gn * ldw + k0 + (idx & 7) * 4)
+                          : make_float4(0.f, 0.f, 0.f, 0.f);
       }
       if (kb >= 1) mbar_wait(&empty_bar, (kb - 1) & 1);   // the MMAs of block kb-1 have read the stage
 #pragma unroll
@@ -371,7 +382,14 @@ gemm_tf32x3_small_kernel(const float* __restrict__ A, int lda, const float* __re
 #pragma unroll
       for (int i = 0; i < kBLoads; i++) {
         const int idx = tid + i * kProducerThreads;
-        split_store(rb[i], b_hi, b_lo, idx >> 3, idx & 7);
+        if (PS) {
+          const int row = idx >> 3, chunk = idx & 7;
+          const int off = row * 32 + ((chunk ^ (row & 7)) << 2);
+          *reinterpret_cast<float4*>(b_hi + off) = rb[i];
+          *reinterpret_cast<float4*>(b_lo + off) = rbl[i];
+        } else {
+          split_store(rb[i], b_hi, b_lo, idx >> 3, idx & 7);
+        }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
@@ -442,79 +460,106 @@ gemm_tf32x3_small_kernel(const float* __restrict__ A, int lda, const float* __re
   }
 }
 
-template <int BN>
-int launch_tc_small(const float* A, int lda, const float* W, int ldw, float* C, int ldc, int M, int N, int K,
-                    const float* rowscale, const float* bias, int relu, cudaStream_t stream) {
+template <int BN, bool PS>
+int launch_tc_small(const float* A, int lda, const float* W, const float* W_lo, int ldw, float* C, int ldc, int M, int N,
+                    int K, const float* rowscale, const float* bias, int relu, cudaStream_t stream) {
   constexpr size_t stage = 2 * BM * BK * 4 + 2 * BN * BK * 4;
   constexpr size_t smem = (stage > 8 * 32 * 33 * 4 ? stage : 8 * 32 * 33 * 4) + 1024;
   static bool attr_done = false;
   if (!attr_done) {
-    LCR_CUDA_TRY(cudaFuncSetAttribute(gemm_tf32x3_small_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    LCR_CUDA_TRY(cudaFuncSetAttribute(gemm_tf32x3_small_kernel<BN, PS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)smem));
     attr_done = true;
   }
   dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
-  gemm_tf32x3_small_kernel<BN><<<grid, kThreads, smem, stream>>>(A, lda, W, ldw, C, ldc, M, N, K, rowscale, bias,
-                                                                 relu);
+  gemm_tf32x3_small_kernel<BN, PS><<<grid, kThreads, smem, stream>>>(A, lda, W, W_lo, ldw, C, ldc, M, N, K, rowscale,
+                                                                     bias, relu);
   return LCR_OK;
 }
 
-template <int BN, int STAGES>
-int launch_tc(const float* A, int lda, const float* W, int ldw, float* C, int ldc, int M, int N, int K,
+template <int BN, int STAGES, bool PS>
+int launch_tc(const float* A, int lda, const float* W, const float* W_lo, int ldw, float* C, int ldc, int M, int N, int K,
               const float* rowscale, const float* bias, int relu, cudaStream_t stream) {
   constexpr size_t smem = (size_t)STAGES * (2 * BM * BK * 4 + 2 * BN * BK * 4) + 1024;
   static bool attr_done = false;
   if (!attr_done) {
-    LCR_CUDA_TRY(cudaFuncSetAttribute(gemm_tf32x3_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    LCR_CUDA_TRY(cudaFuncSetAttribute(gemm_tf32x3_kernel<BN, STAGES, PS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)smem));
     attr_done = true;
   }
   dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
-  gemm_tf32x3_kernel<BN, STAGES><<<grid, kThreads, smem, stream>>>(A, lda, W, ldw, C, ldc, M, N, K, rowscale, bias,
-                                                                   relu);
+  gemm_tf32x3_kernel<BN, STAGES, PS><<<grid, kThreads, smem, stream>>>(A, lda, W, W_lo, ldw, C, ldc, M, N, K, rowscale,
+                                                                       bias, relu);
   return LCR_OK;
+}
+
+// hi = rna_tf32(w), lo = rna_tf32(w - hi): the operand split of the 3xTF32 scheme, done once for weights
+__global__ void tf32_split_kernel(const float* __restrict__ w, int64_t n, float* __restrict__ hi, float* __restrict__ lo) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const float x = w[i], h = tf32_rn(x);
+    hi[i] = h;
+    lo[i] = tf32_rn(x - h);
+  }
+}
+
+template <bool PS>
+int gemm_dispatch(const float* A, int lda, const float* W, const float* W_lo, int ldw, float* C, int ldc, int M, int N,
+                  int K, const float* rowscale, const float* bias, int relu, cudaStream_t stream) {
+  if (K <= 4 * BK) {  // bandwidth-bound unary layers: occupancy-oriented kernel
+    if (N <= 32) return launch_tc_small<32, PS>(A, lda, W, W_lo, ldw, C, ldc, M, N, K, rowscale, bias, relu, stream);
+    if (N <= 64) return launch_tc_small<64, PS>(A, lda, W, W_lo, ldw, C, ldc, M, N, K, rowscale, bias, relu, stream);
+    if (N <= 128) return launch_tc_small<128, PS>(A, lda, W, W_lo, ldw, C, ldc, M, N, K, rowscale, bias, relu, stream);
+    return launch_tc_small<256, PS>(A, lda, W, W_lo, ldw, C, ldc, M, N, K, rowscale, bias, relu, stream);
+  }
+  if (N <= 32) return launch_tc<32, 4, PS>(A, lda, W, W_lo, ldw, C, ldc, M, N, K, rowscale, bias, relu, stream);
+  if (N <= 64) return launch_tc<64, 4, PS>(A, lda, W, W_lo, ldw, C, ldc, M, N, K, rowscale, bias, relu, stream);
+  // wide tiles amortise the A-operand staging (each 128 x 32 A block is split once per N tile); when
+  // 256-wide tiles would leave the last wave of the 148 SMs mostly empty, 128-wide tiles fill it better
+  const long tiles_m = (M + 127) / 128;
+  const long t256 = tiles_m * ((N + 255) / 256), t128 = tiles_m * ((N + 127) / 128);
+  const long w256 = (t256 + LCR_SM_COUNT - 1) / LCR_SM_COUNT, w128 = (t128 + LCR_SM_COUNT - 1) / LCR_SM_COUNT;
+  if (N <= 128 || w128 < 2 * w256)   // a 128-wide tile costs about half a 256-wide one
+    return launch_tc<128, 3, PS>(A, lda, W, W_lo, ldw, C, ldc, M, N, K, rowscale, bias, relu, stream);
+  return launch_tc<256, 2, PS>(A, lda, W, W_lo, ldw, C, ldc, M, N, K, rowscale, bias, relu, stream);
 }
 
 }  // namespace
 
 // Internal entry: tensor-core GEMM.  Requirements: K % 32 == 0, N % 4 == 0, 16-byte aligned rows.
-int lcr_gemm_tf32x3(const float* A, int lda, const float* W, int ldw, float* C, int ldc, int M, int N, int K,
-                    const float* rowscale, const float* bias, int relu, cudaStream_t stream) {
+// W_lo != NULL: W / W_lo are the pre-split tf32 hi / lo parts of the weights (lcr_tf32_split).
+int lcr_gemm_tf32x3(const float* A, int lda, const float* W, const float* W_lo, int ldw, float* C, int ldc, int M, int N,
+                    int K, const float* rowscale, const float* bias, int relu, cudaStream_t stream) {
   LCR_REQUIRE(M >= 0 && N > 0 && K > 0, "gemm_tc: bad shape");
   LCR_REQUIRE((K % BK) == 0 && (N % 4) == 0 && (lda % 4) == 0 && (ldw % 4) == 0 && (ldc % 4) == 0,
               "gemm_tc: K must be a multiple of 32; N and leading dimensions multiples of 4");
-  LCR_REQUIRE((((uintptr_t)A | (uintptr_t)W | (uintptr_t)C | (uintptr_t)bias) & 15) == 0,
+  LCR_REQUIRE((((uintptr_t)A | (uintptr_t)W | (uintptr_t)W_lo | (uintptr_t)C | (uintptr_t)bias) & 15) == 0,
               "gemm_tc: pointers must be 16-byte aligned");
   if (M == 0) return LCR_OK;
   LcrProfScope prof("gemm_tf32x3", 2.0 * M * N * K, 4.0 * ((double)M * K + (double)K * N + (double)M * N), stream);
-  int rc;
-  if (K <= 4 * BK) {  // bandwidth-bound unary layers: occupancy-oriented kernel
-    if (N <= 32) rc = launch_tc_small<32>(A, lda, W, ldw, C, ldc, M, N, K, rowscale, bias, relu, stream);
-    else if (N <= 64) rc = launch_tc_small<64>(A, lda, W, ldw, C, ldc, M, N, K, rowscale, bias, relu, stream);
-    else if (N <= 128) rc = launch_tc_small<128>(A, lda, W, ldw, C, ldc, M, N, K, rowscale, bias, relu, stream);
-    else rc = launch_tc_small<256>(A, lda, W, ldw, C, ldc, M, N, K, rowscale, bias, relu, stream);
-    if (rc != LCR_OK) return rc;
-    LCR_LAUNCHED(1);
-    LCR_CUDA_CHECK_LAUNCH();
-    return LCR_OK;
-  }
-  // wide tiles amortise the A-operand staging (each 128 x 32 A block is split once per N tile)
-  if (N <= 32) rc = launch_tc<32, 4>(A, lda, W, ldw, C, ldc, M, N, K, rowscale, bias, relu, stream);
-  else if (N <= 64) rc = launch_tc<64, 4>(A, lda, W, ldw, C, ldc, M, N, K, rowscale, bias, relu, stream);
-  else if (N <= 128 || (long)((M + 127) / 128) * ((N + 255) / 256) < LCR_SM_COUNT)
-    rc = launch_tc<128, 3>(A, lda, W, ldw, C, ldc, M, N, K, rowscale, bias, relu, stream);
-  else rc = launch_tc<256, 2>(A, lda, W, ldw, C, ldc, M, N, K, rowscale, bias, relu, stream);
+  const int rc = W_lo ? gemm_dispatch<true>(A, lda, W, W_lo, ldw, C, ldc, M, N, K, rowscale, bias, relu, stream)
+                      : gemm_dispatch<false>(A, lda, W, nullptr, ldw, C, ldc, M, N, K, rowscale, bias, relu, stream);
   if (rc != LCR_OK) return rc;
   LCR_LAUNCHED(1);
   LCR_CUDA_CHECK_LAUNCH();
   return LCR_OK;
 }
 
-// C ABI: out = act(rowscale * (x . weight^T) + bias) with weight in nn.Linear layout [c_out, c_in]
-extern "C" int lcr_linear_tc(const float* x, int64_t n_rows, int c_in, int ld_x, const float* weight, int c_out,
-                             int ld_w, const float* bias, const float* rowscale, int act, float* out, int ld_out,
-                             void* stream) {
+// C ABI: out = act(rowscale * (x . weight^T) + bias) with weight in nn.Linear layout [c_out, c_in];
+// weight_lo != NULL: weight / weight_lo are the two halves written by lcr_tf32_split.
+extern "C" int lcr_linear_tc(const float* x, int64_t n_rows, int c_in, int ld_x, const float* weight,
+                             const float* weight_lo, int c_out, int ld_w, const float* bias, const float* rowscale,
+                             int act, float* out, int ld_out, void* stream) {
   LCR_REQUIRE(n_rows >= 0 && n_rows < (1ll << 31), "linear_tc: n_rows out of range");
-  return lcr_gemm_tf32x3(x, ld_x, weight, ld_w, out, ld_out, (int)n_rows, c_out, c_in, rowscale, bias, act,
+  return lcr_gemm_tf32x3(x, ld_x, weight, weight_lo, ld_w, out, ld_out, (int)n_rows, c_out, c_in, rowscale, bias, act,
                          (cudaStream_t)stream);
+}
+
+extern "C" int lcr_tf32_split(const float* w, int64_t count, float* hi, float* lo, void* stream) {
+  LCR_REQUIRE(count >= 0, "tf32_split: bad count");
+  if (count == 0) return LCR_OK;
+  tf32_split_kernel<<<(unsigned)((count + 255) / 256), 256, 0, (cudaStream_t)stream>>>(w, count, hi, lo);
+  LCR_LAUNCHED(1);
+  LCR_CUDA_CHECK_LAUNCH();
+  return LCR_OK;
 }

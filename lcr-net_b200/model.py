@@ -35,6 +35,15 @@ class KPConv(nn.Module):
             self.register_parameter('bias', None)
         self.register_buffer('kernel_points', torch.zeros(kernel_size, 3))
         self._w_nk = None
+        self._kp_host = None
+
+    def kernel_points_host(self):
+        """CPU copy of the kernel points (kernel arguments of the sparse gather; cached)."""
+        kp = self.kernel_points
+        key = (kp.data_ptr(), kp._version)
+        if self._kp_host is None or self._kp_host[0] != key:
+            self._kp_host = (key, kp.detach().to('cpu', torch.float32).contiguous())
+        return self._kp_host[1]
 
     def weights_nk(self):
         """[c_out, 15 * c_in] copy of the weights for the tensor-core contraction (cached)."""
@@ -46,7 +55,8 @@ class KPConv(nn.Module):
 
     def forward(self, s_feats, q_points, s_points, neighbor_indices, s_flags=None):
         return ops.kpconv(s_feats, q_points, s_points, neighbor_indices, self.kernel_points, self.sigma,
-                          self.weights, self.bias, s_flags, self.weights_nk() if self.in_channels > 1 else None)
+                          self.weights, self.bias, s_flags, self.weights_nk() if self.in_channels > 1 else None,
+                          self.kernel_points_host())
 
 
 class GroupNorm(nn.Module):

@@ -32,6 +32,36 @@ def _f32c(t):
     return t
 
 
+_SPLIT_CACHE = {}
+
+
+def tf32_split(weight):
+    """(hi, lo) tf32 halves of a weight tensor for the 3xTF32 GEMM (lcr_tf32_split), cached per
+    (storage, version): the cache entry keeps ``weight`` alive, so its address cannot be reused by
+    another tensor while the entry exists; an in-place update bumps the version and re-splits."""
+    key = (weight.data_ptr(), weight._version, tuple(weight.shape), tuple(weight.stride()))
+    ent = _SPLIT_CACHE.get(key)
+    if ent is None:
+        if len(_SPLIT_CACHE) > 4096:
+            _SPLIT_CACHE.clear()
+        w = weight.detach()
+        assert w.is_cuda and w.dtype == torch.float32 and w.stride(-1) == 1
+        wc = w.contiguous()
+        halves = torch.empty((2,) + tuple(wc.shape), dtype=torch.float32, device=w.device)
+        _lib.check(_lib.lib().lcr_tf32_split(_lib.ptr(wc), wc.numel(), _lib.ptr(halves[0]), _lib.ptr(halves[1]),
+                                             _lib.stream_ptr(w.device)))
+        ent = (weight, halves[0], halves[1])
+        _SPLIT_CACHE[key] = ent
+    return ent[1], ent[2]
+
+
+def _host_ptr(t):
+    if t is None:
+        return None
+    assert not t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.numel() == 45
+    return _lib.ptr(t)
+
+
 def as_index32(idx):
     """Neighbour tables are int32 inside the kernels; the reference's int64 tables are narrowed."""
     if idx.dtype != torch.int32:
@@ -49,8 +79,10 @@ def row_flags(x):
     return flags
 
 
-def kpconv(s_feats, q_points, s_points, idx, kernel_points, sigma, weights, bias, s_flags=None, weights_nk=None):
-    """KPConv.forward (kpconv.py:79-122).  ``s_flags``: row-sum>0 flags of s_feats (computed if None)."""
+def kpconv(s_feats, q_points, s_points, idx, kernel_points, sigma, weights, bias, s_flags=None, weights_nk=None,
+           kernel_points_host=None):
+    """KPConv.forward (kpconv.py:79-122).  ``s_flags``: row-sum>0 flags of s_feats (computed if None).
+    ``kernel_points_host``: contiguous float32 CPU copy of kernel_points (selects the sparse gather)."""
     _lib.require_cuda(s_feats, q_points, s_points, idx)
     L = _lib.lib()
     idx = as_index32(idx)
@@ -59,13 +91,15 @@ def kpconv(s_feats, q_points, s_points, idx, kernel_points, sigma, weights, bias
     if s_flags is None and c_in > 1:
         s_flags = row_flags(s_feats)
     out = torch.empty((m, c_out), dtype=torch.float32, device=s_feats.device)
+    w_hi = w_lo = None
+    if weights_nk is not None and c_in > 1 and use_tensor_cores():
+        w_hi, w_lo = tf32_split(weights_nk)
     ws_bytes = L.lcr_kpconv_ws_bytes(m, c_in)
     ws = _lib.workspace.get(ws_bytes, s_feats.device, slot=1)
     _lib.check(L.lcr_kpconv(_lib.ptr(_f32c(s_feats)), _lib.ptr(s_flags), n, _lib.ptr(_f32c(q_points)), m,
                             _lib.ptr(_f32c(s_points)), _lib.ptr(idx), idx.stride(0), idx.shape[1],
-                            _lib.ptr(_f32c(kernel_points)), float(sigma), _lib.ptr(_f32c(weights)),
-                            _lib.ptr(weights_nk if (weights_nk is not None and c_in > 1 and use_tensor_cores())
-                                     else None), _lib.ptr(bias), c_in, c_out, _lib.ptr(out), _lib.ptr(ws), ws.numel(), _lib.stream_ptr(s_feats.device)))
+                            _lib.ptr(_f32c(kernel_points)), _host_ptr(kernel_points_host), float(sigma), _lib.ptr(_f32c(weights)),
+                            _lib.ptr(w_hi), _lib.ptr(w_lo), _lib.ptr(bias), c_in, c_out, _lib.ptr(out), _lib.ptr(ws), ws.numel(), _lib.stream_ptr(s_feats.device)))
     return out
 
 
@@ -75,8 +109,9 @@ def linear(x, weight_t, bias, weight_nk=None):
     _lib.require_cuda(x)
     if weight_nk is not None and x.shape[1] % 32 == 0 and weight_nk.shape[0] % 4 == 0 and use_tensor_cores():
         out = torch.empty((x.shape[0], weight_nk.shape[0]), dtype=torch.float32, device=x.device)
+        w_hi, w_lo = tf32_split(weight_nk)
         _lib.check(_lib.lib().lcr_linear_tc(_lib.ptr(_f32c(x)), x.shape[0], x.shape[1], x.stride(0),
-                                            _lib.ptr(_f32c(weight_nk)), weight_nk.shape[0], weight_nk.stride(0),
+                                            _lib.ptr(w_hi), _lib.ptr(w_lo), weight_nk.shape[0], w_hi.stride(0),
                                             _lib.ptr(bias), None, 0, _lib.ptr(out), out.stride(0),
                                             _lib.stream_ptr(x.device)))
         return out

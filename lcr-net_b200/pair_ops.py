@@ -32,7 +32,9 @@ def linear_tc(x, weight, bias=None, relu=False, rowscale=None, out=None):
     cout = weight.shape[0]
     if out is None:
         out = torch.empty((n, cout), dtype=torch.float32, device=x.device)
-    _lib.check(_L().lcr_linear_tc(_lib.ptr(x), n, cin, x.stride(0), _lib.ptr(weight), cout, weight.stride(0),
+    from .ops import tf32_split
+    w_hi, w_lo = tf32_split(weight)
+    _lib.check(_L().lcr_linear_tc(_lib.ptr(x), n, cin, x.stride(0), _lib.ptr(w_hi), _lib.ptr(w_lo), cout, w_hi.stride(0),
                                   _lib.ptr(bias), _lib.ptr(rowscale), 1 if relu else 0, _lib.ptr(out), out.stride(0),
                                   _s(x)))
     return out

@@ -79,6 +79,50 @@ def test_kpconv_vs_oracle(c_in, c_out):
                             t(b).cuda(), weights_nk=w_nk).cpu().numpy()
         assert max_err(got_tc, ref) < REL
         assert max_err(got_tc, got) < 1e-5
+        # gather variants with the kernel points as kernel arguments: fast dense loop, sparse lists, auto
+        from lcrnet_b200 import _lib
+        try:
+            for mode in (1, 2, 3):
+                _lib.lib().lcr_set_gather_mode(mode)
+                got_v = ops.kpconv(t(feats).cuda(), t(q).cuda(), t(s).cuda(), t(idx).cuda(), t(kp).cuda(), 1.2,
+                                   t(w).cuda(), t(b).cuda(), weights_nk=w_nk,
+                                   kernel_points_host=t(kp).contiguous()).cpu().numpy()
+                assert max_err(got_v, ref) < REL, mode
+                assert max_err(got_v, got_tc) < 1e-5, mode
+        finally:
+            _lib.lib().lcr_set_gather_mode(3)
+    else:
+        got_fast = ops.kpconv(t(feats).cuda(), t(q).cuda(), t(s).cuda(), t(idx).cuda(), t(kp).cuda(), 1.2, t(w).cuda(),
+                              t(b).cuda(), kernel_points_host=t(kp).contiguous()).cpu().numpy()
+        assert max_err(got_fast, ref) < REL
+        assert max_err(got_fast, got) < 1e-5
+
+
+def test_kpconv_sparse_wide_table():
+    """Sparse gather with H > 64 (two super-chunks) and rows made only of pads."""
+    from lcrnet_b200 import ops
+    rng = np.random.default_rng(5)
+    s = rng.uniform(-3, 3, (700, 3)).astype(np.float32)
+    q = np.concatenate([s[::5], np.full((3, 3), 50.0, np.float32)])      # last queries have no neighbours
+    ql, sl = np.array([len(q)], dtype=np.int64), np.array([len(s)], dtype=np.int64)
+    idx = on.radius_neighbors(q, s, ql, sl, 2.5, limit=150)
+    assert idx.shape[1] > 64
+    feats = rng.standard_normal((len(s), 64)).astype(np.float32)
+    w = (rng.standard_normal((15, 64, 64)) * 0.1).astype(np.float32)
+    kp = checkpoint.default_kernel_points(2.5, rng)
+    t = torch.from_numpy
+    sdd = {'KPConv.kernel_points': t(kp), 'KPConv.weights': t(w)}
+    ref = mo.kpconv(sdd, 'KPConv.', t(feats), t(q), t(s), t(idx), 1.2).numpy()
+    w_nk = t(w).reshape(-1, 64).t().contiguous().cuda()
+    from lcrnet_b200 import _lib
+    try:
+        for mode in (1, 2):
+            _lib.lib().lcr_set_gather_mode(mode)
+            got = ops.kpconv(t(feats).cuda(), t(q).cuda(), t(s).cuda(), t(idx).cuda(), t(kp).cuda(), 1.2, t(w).cuda(),
+                             None, weights_nk=w_nk, kernel_points_host=t(kp).contiguous()).cpu().numpy()
+            assert max_err(got, ref) < REL, mode
+    finally:
+        _lib.lib().lcr_set_gather_mode(3)
 
 
 @pytest.mark.parametrize('c', [32, 64, 128, 256, 512, 1024])
@@ -207,3 +251,22 @@ def test_l2_topk_vs_oracle(nq, ndb, k):
     assert ((idx < valid[:, None]) | (idx == -1)).all()
     assert np.array_equal(idx == -1, ref_i == -1)
     assert np.allclose(d2.cpu().numpy()[ref_i >= 0], ref_d[ref_i >= 0], rtol=1e-5, atol=1e-6)
+
+
+def test_multistream_pipeline_matches_single_stream(net):
+    """pipeline.DescriptorPipeline: the batch cut into chunks on 3 streams / host threads gives the
+    descriptors of the single-stream pass (scans are independent units; bit-identical expected,
+    bar 1e-6)."""
+    from lcrnet_b200 import pipeline
+    scans = [np.ascontiguousarray(synth.make_scan(i // 2, 7351 + i)[::8]) for i in range(7)]
+    pts = torch.from_numpy(np.concatenate(scans, 0)).pin_memory()
+    lens = [len(s) for s in scans]
+    lim = [30, 30, 30, 30]
+    one = pipeline.DescriptorPipeline(net, lim, n_streams=1)(pts, lens).cpu().numpy()
+    pipe = pipeline.DescriptorPipeline(net, lim, n_streams=3)
+    for src in (pts, pts.cuda()):
+        many = pipe(src, lens)
+        torch.cuda.current_stream().synchronize()
+        assert np.abs(many.cpu().numpy() - one).max() <= 1e-6
+    pipe.close()
+    assert np.allclose(np.linalg.norm(one, axis=1), 1.0, atol=1e-5)
