@@ -376,16 +376,37 @@ def dominant_kernel_roofline(step, pts, lens, flush):
     src = 'measured (MEASURED_PEAKS.json)' if peaks else 'fallback (B200_PROFILING.md)'
     groups = {k: {'ms': round(v[0], 4), 'launches': v[3], 'share': round(v[0] / total_ms, 4),
                   'gflops': round(v[1] / 1e9, 3), 'mbytes': round(v[2] / 1e6, 3)} for k, v in agg.items()}
+    traffic, traffic_src = ncu_traffic(name, cnt)
     if fl > 0 and name.startswith('gemm'):
         ach = fl / (ms * 1e-3) / 1e12
+        note = ('achieved = fp32-equivalent algorithmic flops (2MNK) of all launches of the group in one step / their '
+                'summed event-timed duration; peak = dense bf16 tensor peak.  The tcgen05 kernel issues 3 TF32 MMAs per '
+                'fp32 product (3xTF32 split, DESIGN.md 5) and TF32 runs at half the bf16 rate, so the tensor pipe sees '
+                '6x this fraction' if name == 'gemm_tf32x3' else
+                'fp32 SIMT GEMM; fraction is against the dense bf16 tensor peak')
         return {'kernel': name, 'bound': 'tensor', 'achieved': ach, 'peak': tens_peak, 'unit': 'TFLOP/s',
-                'frac': ach / tens_peak, 'traffic': None, 'peak_source': src,
-                'note': 'fp32 SIMT GEMM (no fp32 MMA on tensor cores); fraction is against the dense bf16 tensor peak',
+                'frac': ach / tens_peak, 'traffic': traffic, 'traffic_source': traffic_src, 'peak_source': src,
+                'note': note, 'tf32_mma_tflops': 3 * ach if name == 'gemm_tf32x3' else None,
                 'launches_per_step': cnt, 'ms_per_step': ms, 'share_of_step': ms / total_ms, 'kernel_groups': groups}
     ach = by / (ms * 1e-3) / 1e9
     return {'kernel': name, 'bound': 'hbm', 'achieved': ach, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': ach / hbm_peak,
-            'traffic': None, 'peak_source': src, 'launches_per_step': cnt, 'ms_per_step': ms,
-            'share_of_step': ms / total_ms, 'kernel_groups': groups}
+            'traffic': traffic, 'traffic_source': traffic_src, 'peak_source': src, 'launches_per_step': cnt,
+            'ms_per_step': ms, 'share_of_step': ms / total_ms, 'kernel_groups': groups}
+
+
+def ncu_traffic(group, launches):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the group's launches in one step, from the committed ncu
+    capture of this same command (profiles/*_traffic.json, written by scripts/traffic_from_launches.py); bytes per
+    step over all launches of the group, like `achieved`.  None when the capture does not match this run."""
+    import glob
+    for path in sorted(glob.glob(os.path.join(REPO, 'profiles', '*_traffic.json')), reverse=True):
+        try:
+            g = json.load(open(path))['groups'].get(group)
+        except Exception:
+            continue
+        if g and g['launches'] == launches:
+            return g['dram_bytes'], os.path.relpath(path, REPO)
+    return None, None
 
 
 def run_db(args):

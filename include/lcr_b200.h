@@ -107,6 +107,17 @@ int lcr_kpconv(const float* s_feats, const uint8_t* s_flags, int64_t n_support, 
                const float* kernel_points, const float* kernel_points_host, float sigma, const float* weights,
                const float* weights_nk, const float* weights_nk_lo, const float* bias, int c_in, int c_out,
                float* out, void* ws, size_t ws_bytes, void* stream);
+/* lcr_kpconv with the GroupNorm statistics of its output fused into the GEMM epilogue (the KPConv of a
+ * ConvBlock / ResidualBlock is always followed by a GroupNorm: modules/kpconv/modules.py:104-146,186-196).
+ * gn_partial: f32 scratch of lcr_gn_blocks_ws_bytes(m_query, c_out) bytes; stack_off i64 [n_stacks+1] row
+ * offsets of the stacks among the query rows; every stack must have >= 32 rows.  Needs c_in > 1 and
+ * weights_nk.  Follow with lcr_group_norm_finalize_blocks to get the [n_stacks, groups, 2] statistics. */
+int lcr_kpconv_gn(const float* s_feats, const uint8_t* s_flags, int64_t n_support, const float* q_points,
+                  int64_t m_query, const float* s_points, const int32_t* idx, int ld_idx, int H,
+                  const float* kernel_points, const float* kernel_points_host, float sigma, const float* weights,
+                  const float* weights_nk, const float* weights_nk_lo, const float* bias, int c_in, int c_out,
+                  float* out, void* ws, size_t ws_bytes, float* gn_partial, const int64_t* stack_off, int n_stacks,
+                  void* stream);
 /* flags[r] = (sum_c x[r, c] > 0) */
 int lcr_row_flags(const float* x, int64_t rows, int channels, uint8_t* flags, void* stream);
 
@@ -128,6 +139,11 @@ size_t lcr_group_norm_ws_bytes(int64_t max_stack_rows, int n_stacks, int groups)
 int lcr_group_norm_stats(const float* x, int64_t rows, int channels, int groups, const int64_t* stack_off,
                          int n_stacks, int64_t max_stack_rows, float eps, float* stats_out, void* ws,
                          size_t ws_bytes, void* stream);
+/* GroupNorm statistics from the per-32-row-block column partials a fused producer wrote
+ * (lcr_linear_tc_gn, lcr_kpconv_gn): same result layout as lcr_group_norm_stats, fixed summation order. */
+size_t lcr_gn_blocks_ws_bytes(int64_t rows, int channels);
+int lcr_group_norm_finalize_blocks(const float* gn_partial, int64_t rows, int channels, int groups,
+                                   const int64_t* stack_off, int n_stacks, float eps, float* stats_out, void* stream);
 int lcr_group_norm_apply(const float* x, const float* stats, const float* gamma, const float* beta,
                          const float* x2, const float* stats2, const float* gamma2, const float* beta2,
                          int64_t rows, int channels, int groups, const int64_t* stack_off, int n_stacks,
@@ -170,6 +186,11 @@ int lcr_linear_ex(const float* x, int64_t n_rows, int c_in, int ld_x, const floa
 int lcr_linear_tc(const float* x, int64_t n_rows, int c_in, int ld_x, const float* weight, const float* weight_lo,
                   int c_out, int ld_w, const float* bias, const float* rowscale, int act, float* out, int ld_out,
                   void* stream);
+/* lcr_linear_tc (no row scale, no activation, dense output) + the GroupNorm statistics of the output fused
+ * into the epilogue (UnaryBlock: Linear -> GroupNorm, modules/kpconv/modules.py:53-83); see lcr_kpconv_gn. */
+int lcr_linear_tc_gn(const float* x, int64_t n_rows, int c_in, int ld_x, const float* weight, const float* weight_lo,
+                     int c_out, int ld_w, const float* bias, float* out, int ld_out, float* gn_partial,
+                     const int64_t* stack_off, int n_stacks, void* stream);
 /* Operand split of the 3xTF32 scheme for a weight tensor, done once: hi = rna_tf32(w), lo = rna_tf32(w - hi).
  * Passing (hi, lo) as (weight, weight_lo) to lcr_linear_tc / (weights_nk, weights_nk_lo) to lcr_kpconv lets
  * the GEMM copy both halves of its weight tiles instead of splitting them in every CTA; weight_lo = NULL

@@ -30,11 +30,15 @@ SIGNATURES = {
     'lcr_kpconv_ws_bytes': (c_sz, [c_i64, c_i32]),
     'lcr_kpconv': (c_i32, [c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_f32, c_vp, c_vp,
                            c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_sz, c_vp]),
+    'lcr_kpconv_gn': (c_i32, [c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_f32, c_vp, c_vp,
+                              c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_sz, c_vp, c_vp, c_i32, c_vp]),
     'lcr_set_gather_mode': (None, [c_i32]),
     'lcr_row_flags': (c_i32, [c_vp, c_i64, c_i32, c_vp, c_vp]),
     'lcr_linear': (c_i32, [c_vp, c_i64, c_i32, c_vp, c_i32, c_vp, c_vp, c_vp]),
     'lcr_group_norm_ws_bytes': (c_sz, [c_i64, c_i32, c_i32]),
     'lcr_group_norm_stats': (c_i32, [c_vp, c_i64, c_i32, c_i32, c_vp, c_i32, c_i64, c_f32, c_vp, c_vp, c_sz, c_vp]),
+    'lcr_gn_blocks_ws_bytes': (c_sz, [c_i64, c_i32]),
+    'lcr_group_norm_finalize_blocks': (c_i32, [c_vp, c_i64, c_i32, c_i32, c_vp, c_i32, c_f32, c_vp, c_vp]),
     'lcr_group_norm_apply': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_vp,
                                      c_i32, c_i32, c_f32, c_vp, c_vp, c_vp]),
     'lcr_maxpool': (c_i32, [c_vp, c_i64, c_vp, c_i32, c_i32, c_i64, c_i32, c_vp, c_vp]),
@@ -44,6 +48,8 @@ SIGNATURES = {
     'lcr_linear_ex': (c_i32, [c_vp, c_i64, c_i32, c_i32, c_vp, c_i32, c_vp, c_vp, c_i32, c_vp, c_i32, c_vp]),
     'lcr_linear_tc': (c_i32, [c_vp, c_i64, c_i32, c_i32, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_i32, c_vp, c_i32,
                               c_vp]),
+    'lcr_linear_tc_gn': (c_i32, [c_vp, c_i64, c_i32, c_i32, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_i32, c_vp, c_vp,
+                                 c_i32, c_vp]),
     'lcr_tf32_split': (c_i32, [c_vp, c_i64, c_vp, c_vp, c_vp]),
     'lcr_layer_norm': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_f32, c_i32, c_vp, c_vp]),
     'lcr_rope': (c_i32, [c_vp, c_i32, c_vp, c_i64, c_vp]),

@@ -24,6 +24,9 @@ int lcr_gemm_f32(const float* A, int lda, const float* B, int ldb, float* C, int
                  const float* rowscale, const float* bias, cudaStream_t stream);
 int lcr_gemm_tf32x3(const float* A, int lda, const float* W, const float* W_lo, int ldw, float* C, int ldc, int M, int N,
                     int K, const float* rowscale, const float* bias, int relu, cudaStream_t stream);
+int lcr_gemm_tf32x3_gn(const float* A, int lda, const float* W, const float* W_lo, int ldw, float* C, int ldc, int M,
+                       int N, int K, const float* rowscale, const float* bias, int relu, float* gn_partial,
+                       const int64_t* stack_off, int n_stacks, cudaStream_t stream);
 
 namespace {
 
@@ -401,6 +404,56 @@ __global__ void gn_finalize_kernel(const double2* __restrict__ partial, int G, i
   }
 }
 
+// Statistics fused into the GEMM epilogue (gemm_tc.cu, GnFuse): one 128-thread CTA per (stack, group)
+// adds the per-32-row-block column partials of its stack in a fixed order (thread t takes blocks
+// b0 + t, b0 + t + 128, ...; then a fixed shuffle / shared-memory tree).  Block b covers rows
+// [32b, 32b+32); slot 0 holds the rows of the block's first stack, slot 1 the rest (only the block that
+// contains a stack's first row can start in the previous stack: every stack has >= 32 rows).
+constexpr int kGnFinThreads = 128;
+__global__ void __launch_bounds__(kGnFinThreads)
+gn_finalize_blocks_kernel(const float2* __restrict__ partial, int G, int C, const int64_t* __restrict__ stack_off,
+                          int S, float eps, float2* __restrict__ stats) {
+  __shared__ double s_a[kGnFinThreads / 32], s_b[kGnFinThreads / 32];
+  const int w = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int s = w / G, g = w % G, cpg = C / G;
+  const int64_t r0 = stack_off[s], r1 = stack_off[s + 1];
+  double a = 0.0, b = 0.0;
+  if (r1 > r0) {
+    const int64_t b0 = r0 >> 5, b1 = (r1 - 1) >> 5;
+    for (int64_t blk = b0 + threadIdx.x; blk <= b1; blk += kGnFinThreads) {
+      const int slot = (blk << 5) < r0 ? 1 : 0;
+      const float2* p = partial + ((size_t)blk * 2 + slot) * C + g * cpg;
+      double aa = 0.0, bb = 0.0;
+#pragma unroll 4
+      for (int cc = 0; cc < cpg; cc++) {
+        const float2 v = p[cc];
+        aa += (double)v.x;
+        bb += (double)v.y;
+      }
+      a += aa;
+      b += bb;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+  }
+  if (lane == 0) {
+    s_a[warp] = a;
+    s_b[warp] = b;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    a = (s_a[0] + s_a[1]) + (s_a[2] + s_a[3]);
+    b = (s_b[0] + s_b[1]) + (s_b[2] + s_b[3]);
+    const double n = (double)(r1 - r0) * (double)cpg;
+    const double mean = n > 0 ? a / n : 0.0;
+    const double var = n > 0 ? fmax(b / n - mean * mean, 0.0) : 0.0;
+    stats[w] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
+  }
+}
+
 // ------------------------------------------------------------------ GroupNorm apply (+add, +LeakyReLU, +row flags)
 // y = act( gn(x; stats, gamma, beta) + other ),  other = none | raw tensor | gn(x2; stats2, gamma2, beta2)
 struct GnApplyArgs {
@@ -614,13 +667,12 @@ extern "C" size_t lcr_kpconv_ws_bytes(int64_t m_rows, int c_in) {
   return lcr_align_up((size_t)m_rows * KP * c_in * sizeof(float)) + lcr_align_up((size_t)m_rows * sizeof(float)) + 256;
 }
 
-extern "C" int lcr_kpconv(const float* s_feats, const uint8_t* s_flags, int64_t n_support, const float* q_points,
-                          int64_t m_query, const float* s_points, const int32_t* idx, int ld_idx, int H,
-                          const float* kernel_points, const float* kernel_points_host, float sigma,
-                          const float* weights, const float* weights_nk, const float* weights_nk_lo,
-                          const float* bias, int c_in, int c_out, float* out, void* ws, size_t ws_bytes,
-                          void* stream_) {
-  cudaStream_t stream = (cudaStream_t)stream_;
+static int kpconv_impl(const float* s_feats, const uint8_t* s_flags, int64_t n_support, const float* q_points,
+                       int64_t m_query, const float* s_points, const int32_t* idx, int ld_idx, int H,
+                       const float* kernel_points, const float* kernel_points_host, float sigma,
+                       const float* weights, const float* weights_nk, const float* weights_nk_lo,
+                       const float* bias, int c_in, int c_out, float* out, void* ws, size_t ws_bytes,
+                       float* gn_partial, const int64_t* stack_off, int n_stacks, cudaStream_t stream) {
   LCR_REQUIRE(m_query >= 0 && n_support >= 0 && m_query < (1ll << 31) && n_support < (1ll << 31), "kpconv: sizes");
   LCR_REQUIRE(H >= 1 && ld_idx >= H, "kpconv: bad neighbour table width");
   LCR_REQUIRE(c_in == 1 || c_in == 32 || c_in == 64 || c_in == 128 || c_in == 256,
@@ -679,9 +731,53 @@ extern "C" int lcr_kpconv(const float* s_feats, const uint8_t* s_flags, int64_t 
   LCR_LAUNCHED(1);
   LCR_CUDA_CHECK_LAUNCH();
   if (weights_nk)  // tensor-core contraction: weights as [c_out, 15 * c_in]
-    return lcr_gemm_tf32x3(wf, KP * c_in, weights_nk, weights_nk_lo, KP * c_in, out, c_out, M, c_out, KP * c_in,
-                           rowscale, bias, 0, stream);
+    return lcr_gemm_tf32x3_gn(wf, KP * c_in, weights_nk, weights_nk_lo, KP * c_in, out, c_out, M, c_out, KP * c_in,
+                              rowscale, bias, 0, gn_partial, stack_off, n_stacks, stream);
+  LCR_REQUIRE(!gn_partial, "kpconv: fused GroupNorm statistics need the tensor-core contraction (weights_nk)");
   return lcr_gemm_f32(wf, KP * c_in, weights, c_out, out, c_out, M, c_out, KP * c_in, rowscale, bias, stream);
+}
+
+extern "C" int lcr_kpconv(const float* s_feats, const uint8_t* s_flags, int64_t n_support, const float* q_points,
+                          int64_t m_query, const float* s_points, const int32_t* idx, int ld_idx, int H,
+                          const float* kernel_points, const float* kernel_points_host, float sigma,
+                          const float* weights, const float* weights_nk, const float* weights_nk_lo,
+                          const float* bias, int c_in, int c_out, float* out, void* ws, size_t ws_bytes,
+                          void* stream) {
+  return kpconv_impl(s_feats, s_flags, n_support, q_points, m_query, s_points, idx, ld_idx, H, kernel_points,
+                     kernel_points_host, sigma, weights, weights_nk, weights_nk_lo, bias, c_in, c_out, out, ws, ws_bytes,
+                     nullptr, nullptr, 0, (cudaStream_t)stream);
+}
+
+extern "C" int lcr_kpconv_gn(const float* s_feats, const uint8_t* s_flags, int64_t n_support, const float* q_points,
+                             int64_t m_query, const float* s_points, const int32_t* idx, int ld_idx, int H,
+                             const float* kernel_points, const float* kernel_points_host, float sigma,
+                             const float* weights, const float* weights_nk, const float* weights_nk_lo,
+                             const float* bias, int c_in, int c_out, float* out, void* ws, size_t ws_bytes,
+                             float* gn_partial, const int64_t* stack_off, int n_stacks, void* stream) {
+  LCR_REQUIRE(c_in > 1 && weights_nk && gn_partial && stack_off && n_stacks >= 1,
+              "kpconv_gn: needs c_in > 1, the [c_out, 15 c_in] weights and the partial buffer");
+  return kpconv_impl(s_feats, s_flags, n_support, q_points, m_query, s_points, idx, ld_idx, H, kernel_points,
+                     kernel_points_host, sigma, weights, weights_nk, weights_nk_lo, bias, c_in, c_out, out, ws, ws_bytes,
+                     gn_partial, stack_off, n_stacks, (cudaStream_t)stream);
+}
+
+extern "C" size_t lcr_gn_blocks_ws_bytes(int64_t rows, int channels) {
+  return lcr_align_up((size_t)((rows + 31) / 32) * 2 * (size_t)channels * sizeof(float2)) + 256;
+}
+
+extern "C" int lcr_group_norm_finalize_blocks(const float* gn_partial, int64_t rows, int channels, int groups,
+                                              const int64_t* stack_off, int n_stacks, float eps, float* stats,
+                                              void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  LCR_REQUIRE(gn_partial && stack_off && stats, "group_norm_finalize_blocks: null argument");
+  LCR_REQUIRE(groups >= 1 && channels % groups == 0 && n_stacks >= 1 && rows >= 0, "group_norm_finalize_blocks: shape");
+  LcrProfScope prof("group_norm_stats", 0.0, 16.0 * (double)((rows + 31) / 32) * channels, stream);
+  gn_finalize_blocks_kernel<<<n_stacks * groups, kGnFinThreads, 0, stream>>>(
+      reinterpret_cast<const float2*>(gn_partial), groups, channels, stack_off, n_stacks, eps,
+      reinterpret_cast<float2*>(stats));
+  LCR_LAUNCHED(1);
+  LCR_CUDA_CHECK_LAUNCH();
+  return LCR_OK;
 }
 
 extern "C" size_t lcr_group_norm_ws_bytes(int64_t max_stack_rows, int n_stacks, int groups) {

@@ -15,6 +15,8 @@
 //              per stage), tcgen05.commit releases the stage / signals the epilogue
 //   warps 0-7  epilogue: tcgen05.ld 32x32b.x32 from TMEM, row scale + bias (+ReLU), 128-B row stores
 // 3-stage shared-memory ring; accumulator: BN fp32 columns of TMEM.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -94,6 +96,73 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// GroupNorm statistics fused into the epilogue (the GEMM output is always followed by a GroupNorm in
+// the encoder: modules.py:53-83,104-146): while a warp streams its 32 x 32 chunk of finished values
+// out, lane = column, it also sums the column over the chunk's rows.  Rows are cut into 32-row
+// blocks (aligned to the tile); a block that straddles a stack boundary reports two partials:
+//   gn_partial[(block * 2 + 0) * N + col] = (sum, sumsq) over the rows of the block's FIRST stack,
+//   gn_partial[(block * 2 + 1) * N + col] = the same over the remaining rows (written only when the
+//                                           block straddles; every stack must have >= 32 rows),
+// combined per (stack, group) in a fixed order by gn_finalize_blocks_kernel (encoder.cu): no float
+// atomics, run-to-run deterministic.  The 32-row sums are fp32 (chains of <= 32 terms), the combination
+// fp64.  (fp64 in-loop sums were measured: +0.6 ms per step on the 4 epilogue warps, more than half of
+// what the fusion saves.)  Where the block boundaries fall inside a stack depends on the stack's position
+// in the batch, so the statistics of a stack evaluated inside a batch can differ from the same stack
+// evaluated alone in the last fp32 bits (~1e-7 relative), like any blocked summation.
+struct GnFuse {
+  float2* partial;              // nullptr: no statistics
+  const int64_t* stack_off;     // [S + 1] row offsets of the stacks
+  int S;
+};
+
+// Stores one 32-row x 32-column chunk held transposed in tb (tb[row * 33 + col], row scale applied):
+// adds the bias, applies ReLU, writes 128-byte row segments, and accumulates the column statistics.
+__device__ __forceinline__ void store_chunk(const float* tb, int lane, int row0, int M, int gn, int N,
+                                            const float* __restrict__ bias, int relu, float* __restrict__ C, int ldc,
+                                            const GnFuse& gnf, int split) {
+  const int nrows = min(32, M - row0);
+  if (gn >= N || nrows <= 0) return;
+  const float bv = bias ? bias[gn] : 0.f;
+  float* out = C + (size_t)row0 * ldc + gn;
+  const int cut = min(split, nrows);
+  if (!gnf.partial) {
+#pragma unroll 8
+    for (int rr = 0; rr < nrows; rr++) {
+      float o = tb[rr * 33 + lane] + bv;
+      if (relu) o = fmaxf(o, 0.f);
+      out[(size_t)rr * ldc] = o;        // 32 lanes -> one 128-byte row segment
+    }
+    return;
+  }
+  float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
+#pragma unroll 8
+  for (int rr = 0; rr < cut; rr++) {
+    float o = tb[rr * 33 + lane] + bv;
+    if (relu) o = fmaxf(o, 0.f);
+    out[(size_t)rr * ldc] = o;
+    s0 += o;
+    q0 = fmaf(o, o, q0);
+  }
+#pragma unroll 4
+  for (int rr = cut; rr < nrows; rr++) {
+    float o = tb[rr * 33 + lane] + bv;
+    if (relu) o = fmaxf(o, 0.f);
+    out[(size_t)rr * ldc] = o;
+    s1 += o;
+    q1 = fmaf(o, o, q1);
+  }
+  float2* p = gnf.partial + ((size_t)(row0 >> 5) * 2) * N + gn;
+  p[0] = make_float2(s0, q0);
+  if (cut < nrows) p[N] = make_float2(s1, q1);
+}
+
+// rows of the 32-row block starting at row0 that belong to the block's first stack
+__device__ __forceinline__ int gn_split(const GnFuse& gnf, int row0, int M) {
+  if (!gnf.partial || row0 >= M) return 32;
+  const int s = lcr_find_segment(gnf.stack_off, gnf.S, (int64_t)row0);
+  return (int)min((int64_t)32, gnf.stack_off[s + 1] - (int64_t)row0);
+}
+
 // The tensor core accumulates with truncation, which biases long K chains (measured: error grows
 // linearly with K, 2.7e-5 at K = 3840).  The K loop is therefore cut into chunks of STAGES
 // k-blocks (96 values of K): each chunk is accumulated in one of two TMEM buffers and then
@@ -102,11 +171,11 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
 // PS: the weights arrive PRE-SPLIT (W = tf32 hi part, W_lo = tf32 lo part, same layout; made once per
 // weight tensor by lcr_tf32_split): both halves of a B tile are then plain cp.async copies and the
 // producers only split the activations.
-template <int BN, int STAGES, bool PS>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int BN, int STAGES, bool PS, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB)
 gemm_tf32x3_kernel(const float* __restrict__ A, int lda, const float* __restrict__ W, const float* __restrict__ W_lo,
                    int ldw, float* __restrict__ C, int ldc, int M, int N, int K, const float* __restrict__ rowscale,
-                   const float* __restrict__ bias, int relu) {
+                   const float* __restrict__ bias, int relu, const GnFuse gnf) {
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte aligned tiles (SWIZZLE_128B atom = 8 rows x 128 B)
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -245,24 +314,21 @@ gemm_tf32x3_kernel(const float* __restrict__ A, int lda, const float* __restrict
     if (promoter) {
       promote(n_chunks - 1);
       // -------------------------------------------------------- epilogue from registers
-      const int gm = m0 + q * 32 + lane;
-      if (gm < M) {
-        const float rs = rowscale ? rowscale[gm] : 1.f;
+      // All MMAs have completed (acc_full of the last chunk), so the stage ring is free: every warp
+      // transposes its 32 x 32 chunks through a private 32 x 33 buffer in it and writes 128-byte row
+      // segments (+ the fused GroupNorm column statistics, see store_chunk).
+      float* tb = reinterpret_cast<float*>(base) + warp * (32 * 33);
+      const int row0 = m0 + q * 32;
+      const int gm = row0 + lane;
+      const float rs = (rowscale && gm < M) ? rowscale[gm] : 1.f;
+      const int split = gn_split(gnf, row0, M);
 #pragma unroll
-        for (int j = 0; j < kColsPerWarp; j += 4) {
-          const int gn = n0 + c_begin + j;
-          if (gn < N) {
-            float4 o = make_float4(acc[j] * rs, acc[j + 1] * rs, acc[j + 2] * rs, acc[j + 3] * rs);
-            if (bias) {
-              const float4 bv = *reinterpret_cast<const float4*>(bias + gn);
-              o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
-            }
-            if (relu) {
-              o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
-            }
-            *reinterpret_cast<float4*>(C + (size_t)gm * ldc + gn) = o;
-          }
-        }
+      for (int c0 = 0; c0 < kColsPerWarp; c0 += 32) {
+#pragma unroll
+        for (int j = 0; j < 32; j++) tb[lane * 33 + j] = acc[c0 + j] * rs;
+        __syncwarp();
+        store_chunk(tb, lane, row0, M, n0 + c_begin + c0 + lane, N, bias, relu, C, ldc, gnf, split);
+        __syncwarp();
       }
     }
   } else {
@@ -322,7 +388,8 @@ template <int BN, bool PS>
 __global__ void __launch_bounds__(kThreads, BN >= 256 ? 2 : 3)
 gemm_tf32x3_small_kernel(const float* __restrict__ A, int lda, const float* __restrict__ W,
                          const float* __restrict__ W_lo, int ldw, float* __restrict__ C, int ldc, int M, int N, int K,
-                         const float* __restrict__ rowscale, const float* __restrict__ bias, int relu) {
+                         const float* __restrict__ rowscale, const float* __restrict__ bias, int relu,
+                         const GnFuse gnf) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   constexpr int kATile = BM * BK * 4, kBTile = BN * BK * 4;
@@ -404,8 +471,9 @@ gemm_tf32x3_small_kernel(const float* __restrict__ A, int lda, const float* __re
     constexpr int kColsPerWarp = BN >= 64 ? BN / 2 : BN;
     const int c_begin = BN >= 64 ? (warp >> 2) * kColsPerWarp : 0;
     if (BN >= 64 || warp < 4) {
-      const int row_l = q * 32 + lane;
-      const float rs = (rowscale && m0 + row_l < M) ? rowscale[m0 + row_l] : 1.f;
+      const int row0 = m0 + q * 32;
+      const float rs = (rowscale && row0 + lane < M) ? rowscale[row0 + lane] : 1.f;
+      const int split = gn_split(gnf, row0, M);
 #pragma unroll 1
       for (int c0 = 0; c0 < kColsPerWarp; c0 += 32) {
         uint32_t r[32];
@@ -413,19 +481,7 @@ gemm_tf32x3_small_kernel(const float* __restrict__ A, int lda, const float* __re
 #pragma unroll
         for (int j = 0; j < 32; j++) tb[lane * 33 + j] = __uint_as_float(r[j]) * rs;
         __syncwarp();
-        const int gn = n0 + c_begin + c0 + lane;
-        const float bv = (bias && gn < N) ? bias[gn] : 0.f;
-        if (gn < N) {
-#pragma unroll 8
-          for (int rr = 0; rr < 32; rr++) {
-            const int gm = m0 + q * 32 + rr;
-            if (gm < M) {
-              float o = tb[rr * 33 + lane] + bv;
-              if (relu) o = fmaxf(o, 0.f);
-              C[(size_t)gm * ldc + gn] = o;        // 32 lanes -> one 128-byte row segment
-            }
-          }
-        }
+        store_chunk(tb, lane, row0, M, n0 + c_begin + c0 + lane, N, bias, relu, C, ldc, gnf, split);
         __syncwarp();
       }
     }
@@ -460,9 +516,250 @@ gemm_tf32x3_small_kernel(const float* __restrict__ A, int lda, const float* __re
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Persistent, warp-specialised variant (default for pre-split weights).  The one-tile-per-CTA kernels
+// above serialise load -> split -> MMA -> epilogue inside a CTA; for the bandwidth-bound layers (every
+// unary layer, the narrow KPConv contractions) that leaves HBM idle during every prologue and epilogue
+// (ncu: 37 % warps active, long-scoreboard + barrier stalls, 2.3 TB/s).  Here one CTA per SM walks over
+// output tiles and three roles run concurrently:
+//   warps 0-7   producers: cp.async (LDGSTS) of the raw fp32 A block and the pre-split W block into a
+//               STAGES-deep ring that runs ACROSS tile boundaries (the loads of the next tiles are in
+//               flight while this tile is multiplied and stored); the raw A block is used as the hi
+//               operand as it lands (kind::tf32 reads only the upper 19 bits of an fp32 word, i.e. the
+//               tensor core truncates), so the producers only compute lo = x - trunc(x) (exact in fp32)
+//               into the lo block: one LOP3 + one FADD per element.
+//   warp 8      one lane issues the 3 x (BK/8) tcgen05.mma per block; tcgen05.commit frees the stage
+//               and, per promotion chunk, hands the TMEM buffer to the epilogue warps.
+//   warps 9-12  epilogue: promote each finished chunk (TMEM -> fp32 registers, see above), and after a
+//               tile's last chunk release the TMEM buffer and stream the tile out (row scale, bias, ReLU,
+//               fused GroupNorm statistics) while the MMA warp is already in the next tile.
+// Two TMEM buffers of BN columns alternate per chunk.
+constexpr int kWsProducerWarps = 8, kWsEpilogueWarps = 4;
+constexpr int kWsThreads = (kWsProducerWarps + 1 + kWsEpilogueWarps) * 32;
+constexpr int kWsChunk = 3;   // k-blocks per promotion chunk (96 values of K)
+// 416 threads start with 128 registers each (53 K of the 64 K file): the epilogue warpgroup grows to 200
+// and the two producer warpgroups shrink to 72.  The register file is split between the four SM sub-partitions
+// (16 K each; warp w lives in partition w % 4): partition 0 holds an epilogue warp, two producer warps and the MMA
+// warp, so the growth (72 x 32) has to be paid for by the two producers on the same partition (2 x 56 x 32).
+constexpr int kWsEpilogueRegs = 200, kWsProducerRegs = 72;
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(kWsThreads, 1)
+gemm_tf32x3_ws_kernel(const float* __restrict__ A, int lda, const float* __restrict__ W, const float* __restrict__ W_lo,
+                      int ldw, float* __restrict__ C, int ldc, int M, int N, int K, const float* __restrict__ rowscale,
+                      const float* __restrict__ bias, int relu, const GnFuse gnf) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  constexpr int kATile = BM * BK * 4, kBTile = BN * BK * 4;
+  constexpr int kStageBytes = 2 * kATile + 2 * kBTile;
+  constexpr int kProd = kWsProducerWarps * 32;
+  __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], acc_full[2], acc_empty[2];
+  __shared__ uint32_t tmem_base_s;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nk = K / BK;
+  const int tiles_n = (N + BN - 1) / BN;
+  const int tiles = ((M + BM - 1) / BM) * tiles_n;
+  const int my_tiles = ((int)blockIdx.x < tiles) ? (tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const int n_chunks = (nk + kWsChunk - 1) / kWsChunk;     // per tile
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; s++) {
+      mbar_init(&full_bar[s], kWsProducerWarps);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int b = 0; b < 2; b++) {
+      mbar_init(&acc_full[b], 1);
+      mbar_init(&acc_empty[b], kWsEpilogueWarps);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;
+  constexpr int kMmaWarp = kWsEpilogueWarps + kWsProducerWarps;
+  if (warp == kMmaWarp) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
+                 "n"(kTmemCols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp >= kWsEpilogueWarps && warp < kMmaWarp) {
+    // ================================================================ producers
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kWsProducerRegs));
+    const int tid = (int)threadIdx.x - kWsEpilogueWarps * 32;   // index among the producer threads
+    const int total = my_tiles * nk;                       // blocks this CTA streams, tile-major
+    constexpr int kALoads = BM * 8 / kProd, kBLoads = (BN * 8 + kProd - 1) / kProd;
+    auto issue_block = [&](int g) {
+      if (g < total) {
+        const int t = (int)blockIdx.x + (g / nk) * (int)gridDim.x;
+        const int m0 = (t / tiles_n) * BM, n0 = (t % tiles_n) * BN, k0 = (g % nk) * BK;
+        const int s = g % STAGES;
+        const uint32_t a_hi = smem_u32(base + s * kStageBytes), b_hi = a_hi + 2 * kATile;
+#pragma unroll
+        for (int i = 0; i < kALoads; i++) {
+          const int idx = tid + i * kProd;
+          const int row = idx >> 3, chunk = idx & 7;
+          const int gm = m0 + row;
+          const float* src = A + (size_t)(gm < M ? gm : 0) * lda + k0 + chunk * 4;
+          const uint32_t dst = a_hi + row * 128 + ((chunk ^ (row & 7)) << 4);
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(gm < M ? 16 : 0));
+        }
+#pragma unroll
+        for (int i = 0; i < kBLoads; i++) {
+          const int idx = tid + i * kProd;
+          if (BN * 8 % kProd == 0 || idx < BN * 8) {
+            const int row = idx >> 3, chunk = idx & 7;
+            const int gn = n0 + row;
+            const size_t goff = (size_t)(gn < N ? gn : 0) * ldw + k0 + chunk * 4;
+            const uint32_t dst = b_hi + row * 128 + ((chunk ^ (row & 7)) << 4);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(W + goff), "r"(gn < N ? 16 : 0));
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + kBTile), "l"(W_lo + goff),
+                         "r"(gn < N ? 16 : 0));
+          }
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");   // always: keeps the group count uniform
+    };
+#pragma unroll
+    for (int g = 0; g < STAGES - 1; g++) issue_block(g);
+    for (int g = 0; g < total; g++) {
+      const int s = g % STAGES;
+      asm volatile("cp.async.wait_group %0;" ::"n"(STAGES - 2) : "memory");   // this thread's part of block g landed
+      float* a_hi = reinterpret_cast<float*>(base + s * kStageBytes);
+      float* a_lo = a_hi + BM * BK;
+#pragma unroll
+      for (int i = 0; i < kALoads; i++) {
+        const int idx = tid + i * kProd;
+        const int row = idx >> 3, chunk = idx & 7;
+        const int off = row * 32 + ((chunk ^ (row & 7)) << 2);
+        const float4 v = *reinterpret_cast<const float4*>(a_hi + off);
+        float4 l;
+        l.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+        l.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+        l.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+        l.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+        *reinterpret_cast<float4*>(a_lo + off) = l;
+      }
+      // generic-proxy writes (lo block) and this thread's landed cp.async data -> visible to the async proxy
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full_bar[s]);
+      const int nb = g + STAGES - 1;                       // refill the stage block g-1 occupied
+      if (nb < total && g >= 1) mbar_wait(&empty_bar[nb % STAGES], ((nb / STAGES) - 1) & 1);
+      issue_block(nb);
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+  } else if (warp == kMmaWarp) {
+    // ================================================================ MMA issuer (one lane)
+    if (lane == 0) {
+      constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) |
+                                 ((uint32_t)(BM >> 4) << 24);
+      int g = 0, gc = 0;                                   // running block / chunk counters
+      for (int ti = 0; ti < my_tiles; ti++) {
+        for (int c = 0; c < n_chunks; c++, gc++) {
+          const int b = gc & 1;
+          if (gc >= 2) {
+            mbar_wait(&acc_empty[b], ((gc >> 1) - 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          }
+          const uint32_t tmem_d = tmem_base + (uint32_t)(b * BN);
+          const int kb_end = min((c + 1) * kWsChunk, nk);
+          for (int kb = c * kWsChunk; kb < kb_end; kb++, g++) {
+            const int s = g % STAGES;
+            mbar_wait(&full_bar[s], (g / STAGES) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t a_hi = smem_u32(base + s * kStageBytes);
+            const uint32_t a_lo = a_hi + kATile, b_hi = a_lo + kATile, b_lo = b_hi + kBTile;
+#pragma unroll
+            for (int k = 0; k < BK / 8; k++) {
+              const uint32_t koff = k * 32;
+              mma_tf32(tmem_d, make_desc(a_hi + koff), make_desc(b_hi + koff), idesc, (kb > c * kWsChunk) || k != 0);
+              mma_tf32(tmem_d, make_desc(a_hi + koff), make_desc(b_lo + koff), idesc, 1);
+              mma_tf32(tmem_d, make_desc(a_lo + koff), make_desc(b_hi + koff), idesc, 1);
+            }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                             smem_u32(&empty_bar[s]))
+                         : "memory");
+          }
+          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                           smem_u32(&acc_full[b]))
+                       : "memory");
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ================================================================ epilogue warps
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kWsEpilogueRegs));
+    const int q = warp & 3;                                // TMEM lane quarter this warp may access
+    float* tb = reinterpret_cast<float*>(base + STAGES * kStageBytes) + warp * (32 * 33);
+    int gc = 0;
+    for (int ti = 0; ti < my_tiles; ti++) {
+      const int t = (int)blockIdx.x + ti * (int)gridDim.x;
+      const int m0 = (t / tiles_n) * BM, n0 = (t % tiles_n) * BN;
+      float acc[BN];
+#pragma unroll
+      for (int j = 0; j < BN; j++) acc[j] = 0.f;
+      for (int c = 0; c < n_chunks; c++, gc++) {
+        const int b = gc & 1;
+        mbar_wait(&acc_full[b], (gc >> 1) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * BN + c0), r);
+#pragma unroll
+          for (int j = 0; j < 32; j++) acc[c0 + j] += __uint_as_float(r[j]);
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[b]);
+      }
+      const int row0 = m0 + q * 32;
+      const float rs = (rowscale && row0 + lane < M) ? rowscale[row0 + lane] : 1.f;
+      const int split = gn_split(gnf, row0, M);
+#pragma unroll
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+#pragma unroll
+        for (int j = 0; j < 32; j++) tb[lane * 33 + j] = acc[c0 + j] * rs;
+        __syncwarp();
+        store_chunk(tb, lane, row0, M, n0 + c0 + lane, N, bias, relu, C, ldc, gnf, split);
+        __syncwarp();
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == kMmaWarp) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols));
+  }
+}
+
+template <int BN, int STAGES>
+int launch_tc_ws(const float* A, int lda, const float* W, const float* W_lo, int ldw, float* C, int ldc, int M, int N,
+                 int K, const float* rowscale, const float* bias, int relu, const GnFuse& gnf, cudaStream_t stream) {
+  constexpr size_t smem = (size_t)STAGES * (2 * BM * BK * 4 + 2 * BN * BK * 4) + kWsEpilogueWarps * 32 * 33 * 4 + 1024;
+  static_assert(smem <= 227 * 1024, "shared memory budget");
+  static bool attr_done = false;
+  if (!attr_done) {
+    LCR_CUDA_TRY(cudaFuncSetAttribute(gemm_tf32x3_ws_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)smem));
+    attr_done = true;
+  }
+  const long tiles = (long)((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+  const unsigned grid = (unsigned)(tiles < LCR_SM_COUNT ? tiles : LCR_SM_COUNT);
+  gemm_tf32x3_ws_kernel<BN, STAGES><<<grid, kWsThreads, smem, stream>>>(A, lda, W, W_lo, ldw, C, ldc, M, N, K, rowscale,
+                                                                         bias, relu, gnf);
+  return LCR_OK;
+}
+
 template <int BN, bool PS>
 int launch_tc_small(const float* A, int lda, const float* W, const float* W_lo, int ldw, float* C, int ldc, int M, int N,
-                    int K, const float* rowscale, const float* bias, int relu, cudaStream_t stream) {
+                    int K, const float* rowscale, const float* bias, int relu, const GnFuse& gnf, cudaStream_t stream) {
   constexpr size_t stage = 2 * BM * BK * 4 + 2 * BN * BK * 4;
   constexpr size_t smem = (stage > 8 * 32 * 33 * 4 ? stage : 8 * 32 * 33 * 4) + 1024;
   static bool attr_done = false;
@@ -473,23 +770,23 @@ int launch_tc_small(const float* A, int lda, const float* W, const float* W_lo, 
   }
   dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
   gemm_tf32x3_small_kernel<BN, PS><<<grid, kThreads, smem, stream>>>(A, lda, W, W_lo, ldw, C, ldc, M, N, K, rowscale,
-                                                                     bias, relu);
+                                                                     bias, relu, gnf);
   return LCR_OK;
 }
 
-template <int BN, int STAGES, bool PS>
+template <int BN, int STAGES, bool PS, int MINB = 1>
 int launch_tc(const float* A, int lda, const float* W, const float* W_lo, int ldw, float* C, int ldc, int M, int N, int K,
-              const float* rowscale, const float* bias, int relu, cudaStream_t stream) {
+              const float* rowscale, const float* bias, int relu, const GnFuse& gnf, cudaStream_t stream) {
   constexpr size_t smem = (size_t)STAGES * (2 * BM * BK * 4 + 2 * BN * BK * 4) + 1024;
   static bool attr_done = false;
   if (!attr_done) {
-    LCR_CUDA_TRY(cudaFuncSetAttribute(gemm_tf32x3_kernel<BN, STAGES, PS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    LCR_CUDA_TRY(cudaFuncSetAttribute(gemm_tf32x3_kernel<BN, STAGES, PS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)smem));
     attr_done = true;
   }
   dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
-  gemm_tf32x3_kernel<BN, STAGES, PS><<<grid, kThreads, smem, stream>>>(A, lda, W, W_lo, ldw, C, ldc, M, N, K, rowscale,
-                                                                       bias, relu);
+  gemm_tf32x3_kernel<BN, STAGES, PS, MINB><<<grid, kThreads, smem, stream>>>(A, lda, W, W_lo, ldw, C, ldc, M, N, K, rowscale,
+                                                                       bias, relu, gnf);
   return LCR_OK;
 }
 
@@ -505,44 +802,65 @@ __global__ void tf32_split_kernel(const float* __restrict__ w, int64_t n, float*
 
 template <bool PS>
 int gemm_dispatch(const float* A, int lda, const float* W, const float* W_lo, int ldw, float* C, int ldc, int M, int N,
-                  int K, const float* rowscale, const float* bias, int relu, cudaStream_t stream) {
-  if (K <= 4 * BK) {  // bandwidth-bound unary layers: occupancy-oriented kernel
-    if (N <= 32) return launch_tc_small<32, PS>(A, lda, W, W_lo, ldw, C, ldc, M, N, K, rowscale, bias, relu, stream);
-    if (N <= 64) return launch_tc_small<64, PS>(A, lda, W, W_lo, ldw, C, ldc, M, N, K, rowscale, bias, relu, stream);
-    if (N <= 128) return launch_tc_small<128, PS>(A, lda, W, W_lo, ldw, C, ldc, M, N, K, rowscale, bias, relu, stream);
-    return launch_tc_small<256, PS>(A, lda, W, W_lo, ldw, C, ldc, M, N, K, rowscale, bias, relu, stream);
+                  int K, const float* rowscale, const float* bias, int relu, const GnFuse& gnf, cudaStream_t stream) {
+  static const int ws = getenv("LCR_GEMM_WS") ? atoi(getenv("LCR_GEMM_WS")) : 1;
+  if (PS && (ws == 2 || (ws == 1 && K > 4 * BK))) {   // persistent warp-specialised kernel (needs the pre-split weights)
+    if (N <= 32) return launch_tc_ws<32, 5>(A, lda, W, W_lo, ldw, C, ldc, M, N, K, rowscale, bias, relu, gnf, stream);
+    if (N <= 64) return launch_tc_ws<64, 4>(A, lda, W, W_lo, ldw, C, ldc, M, N, K, rowscale, bias, relu, gnf, stream);
+    return launch_tc_ws<128, 3>(A, lda, W, W_lo, ldw, C, ldc, M, N, K, rowscale, bias, relu, gnf, stream);
   }
-  if (N <= 32) return launch_tc<32, 4, PS>(A, lda, W, W_lo, ldw, C, ldc, M, N, K, rowscale, bias, relu, stream);
-  if (N <= 64) return launch_tc<64, 4, PS>(A, lda, W, W_lo, ldw, C, ldc, M, N, K, rowscale, bias, relu, stream);
+  if (K <= 4 * BK) {  // bandwidth-bound unary layers: occupancy-oriented kernel
+    if (N <= 32) return launch_tc_small<32, PS>(A, lda, W, W_lo, ldw, C, ldc, M, N, K, rowscale, bias, relu, gnf, stream);
+    if (N <= 64) return launch_tc_small<64, PS>(A, lda, W, W_lo, ldw, C, ldc, M, N, K, rowscale, bias, relu, gnf, stream);
+    if (N <= 128) return launch_tc_small<128, PS>(A, lda, W, W_lo, ldw, C, ldc, M, N, K, rowscale, bias, relu, gnf, stream);
+    return launch_tc_small<256, PS>(A, lda, W, W_lo, ldw, C, ldc, M, N, K, rowscale, bias, relu, gnf, stream);
+  }
+  static const int occ = getenv("LCR_GEMM_OCC") ? atoi(getenv("LCR_GEMM_OCC")) : 0;
+  if (occ) {   // experiment: two co-resident CTAs per SM with a 2-stage ring instead of one CTA with 4 stages
+    if (N <= 32) return launch_tc<32, 2, PS, 2>(A, lda, W, W_lo, ldw, C, ldc, M, N, K, rowscale, bias, relu, gnf, stream);
+    if (N <= 64) return launch_tc<64, 2, PS, 2>(A, lda, W, W_lo, ldw, C, ldc, M, N, K, rowscale, bias, relu, gnf, stream);
+  }
+  if (N <= 32) return launch_tc<32, 4, PS>(A, lda, W, W_lo, ldw, C, ldc, M, N, K, rowscale, bias, relu, gnf, stream);
+  if (N <= 64) return launch_tc<64, 4, PS>(A, lda, W, W_lo, ldw, C, ldc, M, N, K, rowscale, bias, relu, gnf, stream);
   // wide tiles amortise the A-operand staging (each 128 x 32 A block is split once per N tile); when
   // 256-wide tiles would leave the last wave of the 148 SMs mostly empty, 128-wide tiles fill it better
   const long tiles_m = (M + 127) / 128;
   const long t256 = tiles_m * ((N + 255) / 256), t128 = tiles_m * ((N + 127) / 128);
   const long w256 = (t256 + LCR_SM_COUNT - 1) / LCR_SM_COUNT, w128 = (t128 + LCR_SM_COUNT - 1) / LCR_SM_COUNT;
   if (N <= 128 || w128 < 2 * w256)   // a 128-wide tile costs about half a 256-wide one
-    return launch_tc<128, 3, PS>(A, lda, W, W_lo, ldw, C, ldc, M, N, K, rowscale, bias, relu, stream);
-  return launch_tc<256, 2, PS>(A, lda, W, W_lo, ldw, C, ldc, M, N, K, rowscale, bias, relu, stream);
+    return launch_tc<128, 3, PS>(A, lda, W, W_lo, ldw, C, ldc, M, N, K, rowscale, bias, relu, gnf, stream);
+  return launch_tc<256, 2, PS>(A, lda, W, W_lo, ldw, C, ldc, M, N, K, rowscale, bias, relu, gnf, stream);
 }
 
 }  // namespace
 
 // Internal entry: tensor-core GEMM.  Requirements: K % 32 == 0, N % 4 == 0, 16-byte aligned rows.
 // W_lo != NULL: W / W_lo are the pre-split tf32 hi / lo parts of the weights (lcr_tf32_split).
-int lcr_gemm_tf32x3(const float* A, int lda, const float* W, const float* W_lo, int ldw, float* C, int ldc, int M, int N,
-                    int K, const float* rowscale, const float* bias, int relu, cudaStream_t stream) {
+// gn_partial != NULL: also write the per-32-row-block column statistics of the output (GnFuse).
+int lcr_gemm_tf32x3_gn(const float* A, int lda, const float* W, const float* W_lo, int ldw, float* C, int ldc, int M,
+                       int N, int K, const float* rowscale, const float* bias, int relu, float* gn_partial,
+                       const int64_t* stack_off, int n_stacks, cudaStream_t stream) {
   LCR_REQUIRE(M >= 0 && N > 0 && K > 0, "gemm_tc: bad shape");
   LCR_REQUIRE((K % BK) == 0 && (N % 4) == 0 && (lda % 4) == 0 && (ldw % 4) == 0 && (ldc % 4) == 0,
               "gemm_tc: K must be a multiple of 32; N and leading dimensions multiples of 4");
   LCR_REQUIRE((((uintptr_t)A | (uintptr_t)W | (uintptr_t)W_lo | (uintptr_t)C | (uintptr_t)bias) & 15) == 0,
               "gemm_tc: pointers must be 16-byte aligned");
+  LCR_REQUIRE(!gn_partial || (stack_off && n_stacks >= 1 && ((uintptr_t)gn_partial & 7) == 0),
+              "gemm_tc: fused GroupNorm statistics need the stack offsets");
   if (M == 0) return LCR_OK;
   LcrProfScope prof("gemm_tf32x3", 2.0 * M * N * K, 4.0 * ((double)M * K + (double)K * N + (double)M * N), stream);
-  const int rc = W_lo ? gemm_dispatch<true>(A, lda, W, W_lo, ldw, C, ldc, M, N, K, rowscale, bias, relu, stream)
-                      : gemm_dispatch<false>(A, lda, W, nullptr, ldw, C, ldc, M, N, K, rowscale, bias, relu, stream);
+  GnFuse gnf{reinterpret_cast<float2*>(gn_partial), stack_off, n_stacks};
+  const int rc = W_lo ? gemm_dispatch<true>(A, lda, W, W_lo, ldw, C, ldc, M, N, K, rowscale, bias, relu, gnf, stream)
+                      : gemm_dispatch<false>(A, lda, W, nullptr, ldw, C, ldc, M, N, K, rowscale, bias, relu, gnf, stream);
   if (rc != LCR_OK) return rc;
   LCR_LAUNCHED(1);
   LCR_CUDA_CHECK_LAUNCH();
   return LCR_OK;
+}
+
+int lcr_gemm_tf32x3(const float* A, int lda, const float* W, const float* W_lo, int ldw, float* C, int ldc, int M, int N,
+                    int K, const float* rowscale, const float* bias, int relu, cudaStream_t stream) {
+  return lcr_gemm_tf32x3_gn(A, lda, W, W_lo, ldw, C, ldc, M, N, K, rowscale, bias, relu, nullptr, nullptr, 0, stream);
 }
 
 // C ABI: out = act(rowscale * (x . weight^T) + bias) with weight in nn.Linear layout [c_out, c_in];
@@ -553,6 +871,16 @@ extern "C" int lcr_linear_tc(const float* x, int64_t n_rows, int c_in, int ld_x,
   LCR_REQUIRE(n_rows >= 0 && n_rows < (1ll << 31), "linear_tc: n_rows out of range");
   return lcr_gemm_tf32x3(x, ld_x, weight, weight_lo, ld_w, out, ld_out, (int)n_rows, c_out, c_in, rowscale, bias, act,
                          (cudaStream_t)stream);
+}
+
+// lcr_linear_tc + fused GroupNorm statistics of the output (see lcr_group_norm_finalize_blocks).
+extern "C" int lcr_linear_tc_gn(const float* x, int64_t n_rows, int c_in, int ld_x, const float* weight,
+                                const float* weight_lo, int c_out, int ld_w, const float* bias, float* out, int ld_out,
+                                float* gn_partial, const int64_t* stack_off, int n_stacks, void* stream) {
+  LCR_REQUIRE(n_rows >= 0 && n_rows < (1ll << 31), "linear_tc_gn: n_rows out of range");
+  LCR_REQUIRE(gn_partial && ld_out == c_out, "linear_tc_gn: needs the partial buffer and a dense output");
+  return lcr_gemm_tf32x3_gn(x, ld_x, weight, weight_lo, ld_w, out, ld_out, (int)n_rows, c_out, c_in, nullptr, bias, 0,
+                            gn_partial, stack_off, n_stacks, (cudaStream_t)stream);
 }
 
 extern "C" int lcr_tf32_split(const float* w, int64_t count, float* hi, float* lo, void* stream) {

@@ -53,10 +53,12 @@ class KPConv(nn.Module):
             self._w_nk = (key, w.detach().reshape(-1, w.shape[2]).t().contiguous())
         return self._w_nk[1]
 
-    def forward(self, s_feats, q_points, s_points, neighbor_indices, s_flags=None):
+    def forward(self, s_feats, q_points, s_points, neighbor_indices, s_flags=None, gn=None):
+        """``gn`` = (stacks, eps, groups) of the GroupNorm that follows: returns (out, stats), the statistics
+        coming out of the GEMM epilogue when the shapes allow (ops.gn_fusable)."""
         return ops.kpconv(s_feats, q_points, s_points, neighbor_indices, self.kernel_points, self.sigma,
                           self.weights, self.bias, s_flags, self.weights_nk() if self.in_channels > 1 else None,
-                          self.kernel_points_host())
+                          self.kernel_points_host(), gn=gn)
 
 
 class GroupNorm(nn.Module):
@@ -70,9 +72,13 @@ class GroupNorm(nn.Module):
     def stats(self, x, stacks):
         return ops.group_norm_stats(x, stacks, self.norm.eps, self.num_groups)
 
-    def forward(self, x, stacks, leaky=False, want_flags=False):
-        return ops.group_norm_apply(x, self.stats(x, stacks), self.norm.weight, self.norm.bias, stacks, leaky=leaky,
-                                    want_flags=want_flags, groups=self.num_groups)
+    def spec(self, stacks):
+        """(stacks, eps, groups): what a fused producer needs to emit this norm's statistics."""
+        return (stacks, self.norm.eps, self.num_groups)
+
+    def forward(self, x, stacks, leaky=False, want_flags=False, stats=None):
+        return ops.group_norm_apply(x, self.stats(x, stacks) if stats is None else stats, self.norm.weight,
+                                    self.norm.bias, stacks, leaky=leaky, want_flags=want_flags, groups=self.num_groups)
 
 
 class UnaryBlock(nn.Module):
@@ -95,8 +101,13 @@ class UnaryBlock(nn.Module):
     def linear(self, x):
         return ops.linear(x, self.weight_t(), self.mlp.bias, self.mlp.weight)
 
+    def linear_stats(self, x, stacks):
+        """Linear output and the statistics of the GroupNorm that follows it (fused when possible)."""
+        return ops.linear(x, self.weight_t(), self.mlp.bias, self.mlp.weight, gn=self.norm.spec(stacks))
+
     def forward(self, x, stacks, want_flags=False):
-        return self.norm(self.linear(x), stacks, leaky=self.has_relu, want_flags=want_flags)
+        y, stats = self.linear_stats(x, stacks)
+        return self.norm(y, stacks, leaky=self.has_relu, want_flags=want_flags, stats=stats)
 
 
 class ConvBlock(nn.Module):
@@ -108,6 +119,9 @@ class ConvBlock(nn.Module):
         self.norm = GroupNorm(group_norm, out_channels)
 
     def forward(self, s_feats, q_points, s_points, neighbor_indices, stacks):
+        if self.KPConv.in_channels > 1:
+            x, stats = self.KPConv(s_feats, q_points, s_points, neighbor_indices, gn=self.norm.spec(stacks))
+            return self.norm(x, stacks, leaky=True, stats=stats)
         x = self.KPConv(s_feats, q_points, s_points, neighbor_indices)
         return self.norm(x, stacks, leaky=True)
 
@@ -133,18 +147,17 @@ class ResidualBlock(nn.Module):
             x, flags = s_feats, None
         else:
             x, flags = self.unary1(s_feats, s_stacks, want_flags=True)
-        x = self.KPConv(x, q_points, s_points, neighbor_indices, flags)
-        x = self.norm_conv(x, q_stacks, leaky=True)
-        x = self.unary2.linear(x)
-        stats = self.unary2.norm.stats(x, q_stacks)
+        x, cstats = self.KPConv(x, q_points, s_points, neighbor_indices, flags, gn=self.norm_conv.spec(q_stacks))
+        x = self.norm_conv(x, q_stacks, leaky=True, stats=cstats)
+        x, stats = self.unary2.linear_stats(x, q_stacks)
         shortcut = ops.maxpool(s_feats, neighbor_indices) if self.strided else s_feats
         n2 = self.unary2.norm.norm
         if isinstance(self.unary_shortcut, nn.Identity):
             return ops.group_norm_apply(x, stats, n2.weight, n2.bias, q_stacks, leaky=True, other=shortcut)
-        sc = self.unary_shortcut.linear(shortcut)
+        sc, sstats = self.unary_shortcut.linear_stats(shortcut, q_stacks)
         ns = self.unary_shortcut.norm
         return ops.group_norm_apply(x, stats, n2.weight, n2.bias, q_stacks, leaky=True, other=sc,
-                                    other_norm=(ns.stats(sc, q_stacks), ns.norm.weight, ns.norm.bias))
+                                    other_norm=(sstats, ns.norm.weight, ns.norm.bias))
 
 
 def make_stacks(data_dict, device):

@@ -79,10 +79,27 @@ def row_flags(x):
     return flags
 
 
+def gn_fusable(stacks):
+    """GroupNorm statistics can ride in the tensor-core GEMM epilogue (gemm_tc.cu GnFuse) when every stack
+    has at least one 32-row block to itself; LCR_GN_FUSE=0 selects the separate statistics pass."""
+    import os
+    return (stacks is not None and stacks.min_rows >= 32 and use_tensor_cores()
+            and os.environ.get('LCR_GN_FUSE', '1') != '0')
+
+
+def _finalize_blocks(partial, rows, channels, stacks, eps, groups, device):
+    stats = torch.empty((stacks.n, groups, 2), dtype=torch.float32, device=device)
+    _lib.check(_lib.lib().lcr_group_norm_finalize_blocks(_lib.ptr(partial), rows, channels, groups,
+                                                         _lib.ptr(stacks.off), stacks.n, eps, _lib.ptr(stats),
+                                                         _lib.stream_ptr(device)))
+    return stats
+
+
 def kpconv(s_feats, q_points, s_points, idx, kernel_points, sigma, weights, bias, s_flags=None, weights_nk=None,
-           kernel_points_host=None):
+           kernel_points_host=None, gn=None):
     """KPConv.forward (kpconv.py:79-122).  ``s_flags``: row-sum>0 flags of s_feats (computed if None).
-    ``kernel_points_host``: contiguous float32 CPU copy of kernel_points (selects the sparse gather)."""
+    ``kernel_points_host``: contiguous float32 CPU copy of kernel_points (selects the sparse gather).
+    ``gn`` = (stacks, eps, groups): also return the GroupNorm statistics of the output -> (out, stats)."""
     _lib.require_cuda(s_feats, q_points, s_points, idx)
     L = _lib.lib()
     idx = as_index32(idx)
@@ -96,17 +113,48 @@ def kpconv(s_feats, q_points, s_points, idx, kernel_points, sigma, weights, bias
         w_hi, w_lo = tf32_split(weights_nk)
     ws_bytes = L.lcr_kpconv_ws_bytes(m, c_in)
     ws = _lib.workspace.get(ws_bytes, s_feats.device, slot=1)
+    if gn is not None and w_hi is not None and gn_fusable(gn[0]) and m > 0:
+        stacks, eps, groups = gn
+        assert stacks.rows == m
+        part = _lib.workspace.get(L.lcr_gn_blocks_ws_bytes(m, c_out), s_feats.device, slot=4)
+        _lib.check(L.lcr_kpconv_gn(_lib.ptr(_f32c(s_feats)), _lib.ptr(s_flags), n, _lib.ptr(_f32c(q_points)), m,
+                                   _lib.ptr(_f32c(s_points)), _lib.ptr(idx), idx.stride(0), idx.shape[1],
+                                   _lib.ptr(_f32c(kernel_points)), _host_ptr(kernel_points_host), float(sigma),
+                                   _lib.ptr(_f32c(weights)), _lib.ptr(w_hi), _lib.ptr(w_lo), _lib.ptr(bias), c_in, c_out,
+                                   _lib.ptr(out), _lib.ptr(ws), ws.numel(), _lib.ptr(part), _lib.ptr(stacks.off),
+                                   stacks.n, _lib.stream_ptr(s_feats.device)))
+        return out, _finalize_blocks(part, m, c_out, stacks, eps, groups, s_feats.device)
     _lib.check(L.lcr_kpconv(_lib.ptr(_f32c(s_feats)), _lib.ptr(s_flags), n, _lib.ptr(_f32c(q_points)), m,
                             _lib.ptr(_f32c(s_points)), _lib.ptr(idx), idx.stride(0), idx.shape[1],
                             _lib.ptr(_f32c(kernel_points)), _host_ptr(kernel_points_host), float(sigma), _lib.ptr(_f32c(weights)),
                             _lib.ptr(w_hi), _lib.ptr(w_lo), _lib.ptr(bias), c_in, c_out, _lib.ptr(out), _lib.ptr(ws), ws.numel(), _lib.stream_ptr(s_feats.device)))
+    if gn is not None:
+        return out, group_norm_stats(out, gn[0], gn[1], gn[2])
     return out
 
 
-def linear(x, weight_t, bias, weight_nk=None):
+def linear(x, weight_t, bias, weight_nk=None, gn=None):
     """nn.Linear: weight_t = weight transposed to [c_in, c_out] (SIMT kernel); weight_nk = the
-    nn.Linear layout [c_out, c_in] (tensor-core kernel, used when c_in % 32 == 0)."""
+    nn.Linear layout [c_out, c_in] (tensor-core kernel, used when c_in % 32 == 0).
+    ``gn`` = (stacks, eps, groups): also return the GroupNorm statistics of the output -> (out, stats)."""
     _lib.require_cuda(x)
+    if gn is not None:
+        stacks, eps, groups = gn
+        if (weight_nk is not None and x.shape[1] % 32 == 0 and weight_nk.shape[0] % 4 == 0 and gn_fusable(stacks)
+                and x.shape[0] > 0):
+            assert stacks.rows == x.shape[0]
+            L = _lib.lib()
+            c_out = weight_nk.shape[0]
+            out = torch.empty((x.shape[0], c_out), dtype=torch.float32, device=x.device)
+            w_hi, w_lo = tf32_split(weight_nk)
+            part = _lib.workspace.get(L.lcr_gn_blocks_ws_bytes(x.shape[0], c_out), x.device, slot=4)
+            _lib.check(L.lcr_linear_tc_gn(_lib.ptr(_f32c(x)), x.shape[0], x.shape[1], x.stride(0), _lib.ptr(w_hi),
+                                          _lib.ptr(w_lo), c_out, w_hi.stride(0), _lib.ptr(bias), _lib.ptr(out),
+                                          out.stride(0), _lib.ptr(part), _lib.ptr(stacks.off), stacks.n,
+                                          _lib.stream_ptr(x.device)))
+            return out, _finalize_blocks(part, x.shape[0], c_out, stacks, eps, groups, x.device)
+        out = linear(x, weight_t, bias, weight_nk)
+        return out, group_norm_stats(out, stacks, eps, groups)
     if weight_nk is not None and x.shape[1] % 32 == 0 and weight_nk.shape[0] % 4 == 0 and use_tensor_cores():
         out = torch.empty((x.shape[0], weight_nk.shape[0]), dtype=torch.float32, device=x.device)
         w_hi, w_lo = tf32_split(weight_nk)
@@ -130,6 +178,7 @@ class Stacks:
         self.n = len(off) - 1
         self.rows = off[-1]
         self.max_rows = max([b - a for a, b in zip(off[:-1], off[1:])] + [1])
+        self.min_rows = min([b - a for a, b in zip(off[:-1], off[1:])] + [self.rows])
         self.off = torch.tensor(off, dtype=torch.int64, device=device)
 
 
