@@ -217,46 +217,60 @@ __global__ void bbox_init_kernel(unsigned* __restrict__ bbox, int batch) {
   if (i < batch * 6) bbox[i] = (i % 6) < 3 ? 0xFFFFFFFFu : 0u;
 }
 
-__global__ void bbox_kernel(const float* __restrict__ pts, int64_t n, const int64_t* __restrict__ off, int batch,
-                            unsigned* __restrict__ bbox) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  bool valid = i < n;
-  int b = valid ? lcr_find_segment(off, batch, i) : -1;
-  float x = 0, y = 0, z = 0;
-  if (valid) {
-    x = pts[3 * i];
-    y = pts[3 * i + 1];
-    z = pts[3 * i + 2];
-  }
-  int b0 = __shfl_sync(0xffffffffu, b, 0);
-  if (__all_sync(0xffffffffu, b == b0) && b0 >= 0) {
-    float mnx = x, mny = y, mnz = z, mxx = x, mxy = y, mxz = z;
+// Every thread folds kBboxPer points (strided by the block size: coalesced) into a running box and
+// flushes it when the cloud changes; at the end a warp whose lanes all sit in the same cloud reduces by
+// shuffle and issues one set of atomics.  ~30 same-address atomics per cloud instead of one per warp of
+// points (which serialised in L2: 22 us per call for 470 k points).
+constexpr int kBboxPer = 16;
+__device__ __forceinline__ void bbox_flush(unsigned* __restrict__ bbox, int b, const float* mn, const float* mx) {
+  unsigned* bb = bbox + 6 * b;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      mnx = fminf(mnx, __shfl_xor_sync(0xffffffffu, mnx, o));
-      mny = fminf(mny, __shfl_xor_sync(0xffffffffu, mny, o));
-      mnz = fminf(mnz, __shfl_xor_sync(0xffffffffu, mnz, o));
-      mxx = fmaxf(mxx, __shfl_xor_sync(0xffffffffu, mxx, o));
-      mxy = fmaxf(mxy, __shfl_xor_sync(0xffffffffu, mxy, o));
-      mxz = fmaxf(mxz, __shfl_xor_sync(0xffffffffu, mxz, o));
+  for (int d = 0; d < 3; d++) {
+    atomicMin(bb + d, lcr_f2ord(mn[d]));
+    atomicMax(bb + 3 + d, lcr_f2ord(mx[d]));
+  }
+}
+
+__global__ void __launch_bounds__(256)
+bbox_kernel(const float* __restrict__ pts, int64_t n, const int64_t* __restrict__ off, int batch,
+            unsigned* __restrict__ bbox) {
+  const int64_t base = (int64_t)blockIdx.x * (blockDim.x * kBboxPer) + threadIdx.x;
+  int b = -1;
+  int64_t next = 0;
+  float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+  for (int k = 0; k < kBboxPer; k++) {
+    const int64_t i = base + (int64_t)k * blockDim.x;
+    if (i >= n) break;
+    if (b < 0 || i >= next) {
+      if (b >= 0) bbox_flush(bbox, b, mn, mx);
+      b = lcr_find_segment(off, batch, i);
+      next = off[b + 1];
+#pragma unroll
+      for (int d = 0; d < 3; d++) {
+        mn[d] = INFINITY;
+        mx[d] = -INFINITY;
+      }
     }
-    if (lcr_lane() == 0) {
-      unsigned* bb = bbox + 6 * b0;
-      atomicMin(bb + 0, lcr_f2ord(mnx));
-      atomicMin(bb + 1, lcr_f2ord(mny));
-      atomicMin(bb + 2, lcr_f2ord(mnz));
-      atomicMax(bb + 3, lcr_f2ord(mxx));
-      atomicMax(bb + 4, lcr_f2ord(mxy));
-      atomicMax(bb + 5, lcr_f2ord(mxz));
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+      const float v = pts[3 * i + d];
+      mn[d] = fminf(mn[d], v);
+      mx[d] = fmaxf(mx[d], v);
     }
-  } else if (valid) {
-    unsigned* bb = bbox + 6 * b;
-    atomicMin(bb + 0, lcr_f2ord(x));
-    atomicMin(bb + 1, lcr_f2ord(y));
-    atomicMin(bb + 2, lcr_f2ord(z));
-    atomicMax(bb + 3, lcr_f2ord(x));
-    atomicMax(bb + 4, lcr_f2ord(y));
-    atomicMax(bb + 5, lcr_f2ord(z));
+  }
+  const int b0 = __shfl_sync(0xffffffffu, b, 0);
+  if (__all_sync(0xffffffffu, b == b0)) {
+    if (b0 < 0) return;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int d = 0; d < 3; d++) {
+        mn[d] = fminf(mn[d], __shfl_xor_sync(0xffffffffu, mn[d], o));
+        mx[d] = fmaxf(mx[d], __shfl_xor_sync(0xffffffffu, mx[d], o));
+      }
+    if (lcr_lane() == 0) bbox_flush(bbox, b0, mn, mx);
+  } else if (b >= 0) {
+    bbox_flush(bbox, b, mn, mx);
   }
 }
 }  // namespace
@@ -269,6 +283,6 @@ void lcr_offsets_launch(const int64_t* lengths, int batch, int64_t* off, cudaStr
 void lcr_bbox_launch(const float* pts, int64_t n, const int64_t* off, int batch, unsigned* bbox, cudaStream_t stream) {
   const int T = 256;
   bbox_init_kernel<<<(batch * 6 + T - 1) / T, T, 0, stream>>>(bbox, batch);
-  if (n > 0) bbox_kernel<<<(unsigned)((n + T - 1) / T), T, 0, stream>>>(pts, n, off, batch, bbox);
+  if (n > 0) bbox_kernel<<<(unsigned)((n + T * kBboxPer - 1) / (T * kBboxPer)), T, 0, stream>>>(pts, n, off, batch, bbox);
   LCR_LAUNCHED(n > 0 ? 2 : 1);
 }
