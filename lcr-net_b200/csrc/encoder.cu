@@ -45,8 +45,8 @@ __global__ void __launch_bounds__(128)
 kpconv_gather_kernel(const float* __restrict__ s_feats, const float* __restrict__ q_pts,
                      const float* __restrict__ s_pts, const int32_t* __restrict__ idx, int ld_idx, int H,
                      const float* __restrict__ kpts, const KpArg kp, float sigma,
-                     const uint8_t* __restrict__ flags, int M, int N, float* __restrict__ wf,
-                     float* __restrict__ rowscale) {
+                     const uint8_t* __restrict__ flags, const float4* __restrict__ s_pts4, int M, int N,
+                     float* __restrict__ wf, float* __restrict__ rowscale) {
   constexpr int C = 32 * CPL;
   // influences of 32 neighbours, packed as float4 groups of kernel points: [k/4][neighbour] so that
   // lanes write conflict-free 16-B vectors and the accumulation loop reads 4 broadcast LDS.128
@@ -79,8 +79,17 @@ kpconv_gather_kernel(const float* __restrict__ s_feats, const float* __restrict_
     const int slot = __popc(vmask & ((1u << lane) - 1u));
     const int nv = __popc(vmask);
     if (valid) {
-      const float rx = s_pts[3 * (size_t)j] - qx, ry = s_pts[3 * (size_t)j + 1] - qy,
-                  rz = s_pts[3 * (size_t)j + 2] - qz;
+      // FAST: one 16-byte load of (x, y, z, row flag) per neighbour instead of three scattered 4-byte loads
+      // plus a scattered byte load: the kernel is bound by L1 wavefronts (ncu: l1tex data-pipe 72-88 %), and a
+      // scattered load costs one wavefront per lane whatever its width
+      float4 sp;
+      if (FAST) {
+        sp = s_pts4[j];
+      } else {
+        sp = make_float4(s_pts[3 * (size_t)j], s_pts[3 * (size_t)j + 1], s_pts[3 * (size_t)j + 2],
+                         flags ? (float)flags[j] : 1.f);
+      }
+      const float rx = sp.x - qx, ry = sp.y - qy, rz = sp.z - qz;
       float w[16];
 #pragma unroll
       for (int k = 0; k < KP; k++) {
@@ -98,7 +107,7 @@ kpconv_gather_kernel(const float* __restrict__ s_feats, const float* __restrict_
 #pragma unroll
       for (int g = 0; g < 4; g++) s_w[warp][g][slot] = make_float4(w[4 * g], w[4 * g + 1], w[4 * g + 2], w[4 * g + 3]);
       s_j[warp][slot] = j;
-      cnt += flags ? (int)flags[j] : 1;
+      cnt += sp.w != 0.f;
     }
     __syncwarp();
     constexpr int UN = CPL >= 4 ? 2 : 4;  // neighbours whose feature rows are in flight together
@@ -149,6 +158,236 @@ kpconv_gather_kernel(const float* __restrict__ s_feats, const float* __restrict_
   for (int k = 0; k < KP; k++)
 #pragma unroll
     for (int i = 0; i < CPL; i++) o[k * C + 32 * i] = acc[k][i];
+  if (lane == 0) rowscale[m] = 1.f / (float)max(cnt, 1);
+}
+
+// (x, y, z, flag) per support point for the fast gather
+__global__ void pack_points_kernel(const float* __restrict__ pts, const uint8_t* __restrict__ flags, int N,
+                                   float4* __restrict__ out) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < N) out[j] = make_float4(pts[3 * j], pts[3 * j + 1], pts[3 * j + 2], flags ? (float)flags[j] : 1.f);
+}
+
+// ------------------------------------------------------------------ KPConv gather, packed-FMA form
+// The dense loop above is bound by instruction issue (ncu: issue slots ~70 % busy, FMA pipe 40-48 %): per
+// neighbour and channel it issues 15 FFMA.  Blackwell has a packed fp32 FMA (fma.rn.f32x2, SASS FFMA2: two
+// independent IEEE fp32 FMAs per lane and instruction, same results as two FFMA), so the 15 kernel points
+// are accumulated as 8 PAIRS: a = (w[2p], w[2p+1]) -- adjacent registers of the influence vector as it comes
+// out of shared memory --, b = (f, f), c = (acc[2p], acc[2p+1]); the 16th weight is a zero pad.  8 FFMA2 + 1
+// MOV per neighbour and channel instead of 15 FFMA.  For wide channel slices (C >= 128) a pair whose two
+// influences are both zero is skipped (a neighbour is reached by ~1.6 of the 15 kernel points).
+template <int CPL>
+__global__ void __launch_bounds__(128)
+kpconv_gather_packed_kernel(const float* __restrict__ s_feats, const float* __restrict__ q_pts,
+                            const float* __restrict__ s_pts, const int32_t* __restrict__ idx, int ld_idx, int H,
+                            const KpArg kp, float sigma, const uint8_t* __restrict__ flags, int M, int N,
+                            float* __restrict__ wf, float* __restrict__ rowscale) {
+  constexpr int C = 32 * CPL;
+  constexpr int KPP = (KP + 1) / 2;   // kernel-point pairs
+  __shared__ __align__(16) float4 s_w[4][4][32];
+  __shared__ int s_j[4][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int m = blockIdx.x * 4 + warp;
+  if (m >= M) return;
+  const float qx = q_pts[3 * m], qy = q_pts[3 * m + 1], qz = q_pts[3 * m + 2];
+  const float inv_sigma = 1.f / sigma;
+  float2 acc[KPP][CPL];
+#pragma unroll
+  for (int k = 0; k < KPP; k++)
+#pragma unroll
+    for (int i = 0; i < CPL; i++) acc[k][i] = make_float2(0.f, 0.f);
+  int cnt = 0;
+  const int32_t* row = idx + (size_t)m * ld_idx;
+  for (int h0 = 0; h0 < H; h0 += 32) {
+    const int h = h0 + lane;
+    const int j = h < H ? row[h] : N;
+    const bool valid = j < N;
+    const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+    const int slot = __popc(vmask & ((1u << lane) - 1u));
+    const int nv = __popc(vmask);
+    if (valid) {
+      const float rx = s_pts[3 * (size_t)j] - qx, ry = s_pts[3 * (size_t)j + 1] - qy,
+                  rz = s_pts[3 * (size_t)j + 2] - qz;
+      float w[16];
+#pragma unroll
+      for (int k = 0; k < KP; k++) {
+        const float dx = rx - kp.v[3 * k], dy = ry - kp.v[3 * k + 1], dz = rz - kp.v[3 * k + 2];
+        const float d2 = dx * dx + dy * dy + dz * dz;
+        w[k] = fmaxf(fmaf(-d2 * rsqrtf(fmaxf(d2, 1e-30f)), inv_sigma, 1.f), 0.f);
+      }
+      w[15] = 0.f;
+#pragma unroll
+      for (int g = 0; g < 4; g++) s_w[warp][g][slot] = make_float4(w[4 * g], w[4 * g + 1], w[4 * g + 2], w[4 * g + 3]);
+      s_j[warp][slot] = j;
+      cnt += flags ? (int)flags[j] : 1;
+    }
+    __syncwarp();
+    constexpr int UN = CPL >= 4 ? 2 : 4;  // neighbours whose feature rows are in flight together
+    auto accumulate = [&](const float (&f)[CPL], int hh) {
+      float2 wp[KPP];
+#pragma unroll
+      for (int g = 0; g < 4; g++) {
+        const float4 t = s_w[warp][g][hh];
+        wp[2 * g] = make_float2(t.x, t.y);
+        wp[2 * g + 1] = make_float2(t.z, t.w);
+      }
+#pragma unroll
+      for (int k = 0; k < KPP; k++) {
+        if (CPL >= 4 && wp[k].x == 0.f && wp[k].y == 0.f) continue;   // warp-uniform
+#pragma unroll
+        for (int i = 0; i < CPL; i++) acc[k][i] = __ffma2_rn(wp[k], make_float2(f[i], f[i]), acc[k][i]);
+      }
+    };
+    int hh = 0;
+    for (; hh + UN <= nv; hh += UN) {
+      float fv[UN][CPL];
+#pragma unroll
+      for (int u = 0; u < UN; u++) {
+        const float* f = s_feats + (size_t)s_j[warp][hh + u] * C + lane;
+#pragma unroll
+        for (int i = 0; i < CPL; i++) fv[u][i] = f[32 * i];
+      }
+#pragma unroll
+      for (int u = 0; u < UN; u++) accumulate(fv[u], hh + u);
+    }
+    for (; hh < nv; hh++) {
+      const float* f = s_feats + (size_t)s_j[warp][hh] * C + lane;
+      float fv[CPL];
+#pragma unroll
+      for (int i = 0; i < CPL; i++) fv[i] = f[32 * i];
+      accumulate(fv, hh);
+    }
+    __syncwarp();
+  }
+  cnt = lcr_warp_sum(cnt);
+  float* o = wf + (size_t)m * (KP * C) + lane;
+#pragma unroll
+  for (int k = 0; k < KPP; k++)
+#pragma unroll
+    for (int i = 0; i < CPL; i++) {
+      o[(2 * k) * C + 32 * i] = acc[k][i].x;
+      if (2 * k + 1 < KP) o[(2 * k + 1) * C + 32 * i] = acc[k][i].y;
+    }
+  if (lane == 0) rowscale[m] = 1.f / (float)max(cnt, 1);
+}
+
+// ------------------------------------------------------------------ KPConv gather on the warp-level tensor path
+// wf[m][k][c] = sum_h w[m][h][k] * feat[idx[m][h]][c] is, per query, a [16 x H] x [H x C] product whose M = 15
+// kernel points (+1 pad) fits mma.sync.m16n8k8 exactly (the 128-row tcgen05 tile would need a block-diagonal
+// operand with 7/8 structural zeros).  fp32-class accuracy by the same 3xTF32 operand split as the GEMMs
+// (hi = upper 19 bits, lo = x - hi; hi*hi + hi*lo + lo*hi, fp32 accumulate).  Measured on B200: the legacy
+// mma.sync TF32 path sustains 278 TFLOP/s (scripts/micro/mma_sync_tf32.cu), 3.9x the FFMA rate, i.e. 1.3x after
+// the 3-fold split -- but, more important here, it removes the shared-memory influence broadcast that made the
+// FFMA loop L1-wavefront bound (ncu: l1tex data pipe 72-88 %): every influence is computed by exactly the lane
+// whose A fragment needs it, and the B fragments come straight from 16-byte feature loads.
+//   A fragment (weights): lane (g = lane / 4, t = lane % 4) holds k in {g, g + 8} x h in {8 s + t, 8 s + t + 4}
+//   B fragments (features): n-tile j of a 32-channel set covers channels {4 g' + j}: the lane's float4 load of
+//   channels 4 g .. 4 g + 3 of row h feeds the four n-tiles j = 0..3 (one 128-byte row = 8 lanes x 16 B)
+//   D fragments: lane ends with channels 8 t .. 8 t + 7 of rows k = g and g + 8 -> two float4 stores each
+__device__ __forceinline__ void mma_tf32_16x8x8(float (&d)[4], const unsigned (&a)[4], unsigned b0, unsigned b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void split_tf32(float x, unsigned& hi, unsigned& lo) {
+  hi = __float_as_uint(x) & 0xFFFFE000u;
+  lo = __float_as_uint(x - __uint_as_float(hi));
+}
+
+template <int CPL>
+__global__ void __launch_bounds__(128)
+kpconv_gather_mma_kernel(const float* __restrict__ s_feats, const float* __restrict__ q_pts,
+                         const float4* __restrict__ s_pts4, const int32_t* __restrict__ idx, int ld_idx, int H,
+                         const float* __restrict__ kpts, float sigma, int M, int N, float* __restrict__ wf,
+                         float* __restrict__ rowscale) {
+  constexpr int C = 32 * CPL;
+  constexpr int NT = 4 * CPL;          // 8-channel n-tiles
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int m = blockIdx.x * 4 + warp;
+  if (m >= M) return;
+  const int g = lane >> 2, t = lane & 3;
+  const float qx = q_pts[3 * m], qy = q_pts[3 * m + 1], qz = q_pts[3 * m + 2];
+  const float inv_sigma = 1.f / sigma;
+  // kernel points g and g + 8 (row 15 is the pad: its weights are forced to zero)
+  const float k0x = kpts[3 * g], k0y = kpts[3 * g + 1], k0z = kpts[3 * g + 2];
+  const int g1 = g + 8 < KP ? g + 8 : g;
+  const float k1x = kpts[3 * g1], k1y = kpts[3 * g1 + 1], k1z = kpts[3 * g1 + 2];
+  const float pad1 = g + 8 < KP ? 1.f : 0.f;
+  float d[NT][4];
+#pragma unroll
+  for (int n = 0; n < NT; n++)
+#pragma unroll
+    for (int i = 0; i < 4; i++) d[n][i] = 0.f;
+  int cnt = 0;
+  const int32_t* row = idx + (size_t)m * ld_idx;
+  auto influence = [&](float rx, float ry, float rz, float kx, float ky, float kz) {
+    const float dx = rx - kx, dy = ry - ky, dz = rz - kz;
+    const float d2 = dx * dx + dy * dy + dz * dz;
+    return fmaxf(fmaf(-d2 * rsqrtf(fmaxf(d2, 1e-30f)), inv_sigma, 1.f), 0.f);
+  };
+  // (an explicitly software-pipelined variant -- indices two k-steps ahead, rows one ahead -- measured 20-30 %
+  // slower: more registers, fewer resident warps; the hardware overlaps the k-steps of the 32 warps per SM)
+  for (int h0 = 0; h0 < H; h0 += 32) {
+    const int jl = h0 + lane < H ? row[h0 + lane] : N;       // 32 neighbour indices, one coalesced load
+    const unsigned vmask = __ballot_sync(0xffffffffu, jl < N);
+    if (vmask == 0) continue;
+#pragma unroll
+    for (int s = 0; s < 4; s++) {                             // k-steps of 8 neighbours
+      if (((vmask >> (8 * s)) & 0xFFu) == 0) continue;        // warp-uniform
+      const int ja = __shfl_sync(0xffffffffu, jl, 8 * s + t), jb = __shfl_sync(0xffffffffu, jl, 8 * s + t + 4);
+      const bool va = ja < N, vb = jb < N;
+      const float4 pa = va ? s_pts4[ja] : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 pb = vb ? s_pts4[jb] : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float* fa_p = s_feats + (size_t)(va ? ja : 0) * C + 4 * g;
+      const float* fb_p = s_feats + (size_t)(vb ? jb : 0) * C + 4 * g;
+      float4 fa[CPL], fb[CPL];
+#pragma unroll
+      for (int c = 0; c < CPL; c++) {
+        fa[c] = *reinterpret_cast<const float4*>(fa_p + 32 * c);
+        fb[c] = *reinterpret_cast<const float4*>(fb_p + 32 * c);
+      }
+      if (g == 0) cnt += (va && pa.w != 0.f) + (vb && pb.w != 0.f);
+      const float ax = pa.x - qx, ay = pa.y - qy, az = pa.z - qz;
+      const float bx = pb.x - qx, by = pb.y - qy, bz = pb.z - qz;
+      float w[4];
+      w[0] = va ? influence(ax, ay, az, k0x, k0y, k0z) : 0.f;            // (k = g,     h = 8 s + t)
+      w[1] = va ? influence(ax, ay, az, k1x, k1y, k1z) * pad1 : 0.f;     // (k = g + 8, h = 8 s + t)
+      w[2] = vb ? influence(bx, by, bz, k0x, k0y, k0z) : 0.f;            // (k = g,     h = 8 s + t + 4)
+      w[3] = vb ? influence(bx, by, bz, k1x, k1y, k1z) * pad1 : 0.f;     // (k = g + 8, h = 8 s + t + 4)
+      unsigned a_hi[4], a_lo[4];
+#pragma unroll
+      for (int i = 0; i < 4; i++) split_tf32(w[i], a_hi[i], a_lo[i]);
+#pragma unroll
+      for (int c = 0; c < CPL; c++) {
+        const float va4[4] = {fa[c].x, fa[c].y, fa[c].z, fa[c].w}, vb4[4] = {fb[c].x, fb[c].y, fb[c].z, fb[c].w};
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          unsigned b0h, b0l, b1h, b1l;
+          split_tf32(va ? va4[j] : 0.f, b0h, b0l);
+          split_tf32(vb ? vb4[j] : 0.f, b1h, b1l);
+          mma_tf32_16x8x8(d[4 * c + j], a_hi, b0h, b1h);
+          mma_tf32_16x8x8(d[4 * c + j], a_hi, b0l, b1l);
+          mma_tf32_16x8x8(d[4 * c + j], a_lo, b0h, b1h);
+        }
+      }
+    }
+  }
+  cnt = lcr_warp_sum(cnt);
+  // D fragment of n-tile j: d[0] (k = g, col 2t), d[1] (k = g, col 2t + 1), d[2] / d[3] the same for k = g + 8;
+  // column col of n-tile j of channel set c is channel 32 c + 4 col + j
+  float* o = wf + (size_t)m * (KP * C);
+#pragma unroll
+  for (int c = 0; c < CPL; c++) {
+    float* o0 = o + (size_t)g * C + 32 * c + 8 * t;
+    *reinterpret_cast<float4*>(o0) = make_float4(d[4 * c][0], d[4 * c + 1][0], d[4 * c + 2][0], d[4 * c + 3][0]);
+    *reinterpret_cast<float4*>(o0 + 4) = make_float4(d[4 * c][1], d[4 * c + 1][1], d[4 * c + 2][1], d[4 * c + 3][1]);
+    if (g + 8 < KP) {
+      float* o1 = o + (size_t)(g + 8) * C + 32 * c + 8 * t;
+      *reinterpret_cast<float4*>(o1) = make_float4(d[4 * c][2], d[4 * c + 1][2], d[4 * c + 2][2], d[4 * c + 3][2]);
+      *reinterpret_cast<float4*>(o1 + 4) = make_float4(d[4 * c][3], d[4 * c + 1][3], d[4 * c + 2][3], d[4 * c + 3][3]);
+    }
+  }
   if (lane == 0) rowscale[m] = 1.f / (float)max(cnt, 1);
 }
 
@@ -274,6 +513,113 @@ kpconv_gather_sparse_kernel(const float* __restrict__ s_feats, const float* __re
       else
         o[k * C] = acc[k][0];
     }
+  if (lane == 0) rowscale[m] = 1.f / (float)max(cnt, 1);
+}
+
+// ------------------------------------------------------------------ KPConv gather, mask-dispatch form
+// Same register layout as the dense kernel (lane owns C/32 channels, 15 x C/32 accumulators), but the
+// accumulation visits only the NON-ZERO influences: the influence pass leaves, per neighbour, a 15-bit mask
+// of the kernel points that reach it (~1.6 of 15) and drops neighbours no kernel point reaches; the
+// accumulation walks the set bits (warp-uniform), and a 15-way switch (one indirect branch, no divergence)
+// selects the statically-indexed accumulator row.  Per neighbour: 1 feature-row load + ~1.6 x (bit scan,
+// weight broadcast, branch, C/32 FFMA) instead of 15 x C/32 FFMA (or 15 compare-and-skip pairs).
+template <int CPL>
+__global__ void __launch_bounds__(128)
+kpconv_gather_mask_kernel(const float* __restrict__ s_feats, const float* __restrict__ q_pts,
+                          const float* __restrict__ s_pts, const int32_t* __restrict__ idx, int ld_idx, int H,
+                          const KpArg kp, float sigma, const uint8_t* __restrict__ flags, int M, int N,
+                          float* __restrict__ wf, float* __restrict__ rowscale) {
+  constexpr int C = 32 * CPL;
+  __shared__ float s_w[4][KP][32];
+  __shared__ int s_j[4][32];
+  __shared__ unsigned s_m[4][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int m = blockIdx.x * 4 + warp;
+  if (m >= M) return;
+  const float qx = q_pts[3 * m], qy = q_pts[3 * m + 1], qz = q_pts[3 * m + 2];
+  const float inv_sigma = 1.f / sigma;
+  float acc[KP][CPL];
+#pragma unroll
+  for (int k = 0; k < KP; k++)
+#pragma unroll
+    for (int i = 0; i < CPL; i++) acc[k][i] = 0.f;
+  int cnt = 0;
+  const int32_t* row = idx + (size_t)m * ld_idx;
+  for (int h0 = 0; h0 < H; h0 += 32) {
+    const int h = h0 + lane;
+    const int j = h < H ? row[h] : N;
+    const bool valid = j < N;
+    float w[KP];
+    unsigned mask = 0;
+    if (valid) {
+      const float rx = s_pts[3 * (size_t)j] - qx, ry = s_pts[3 * (size_t)j + 1] - qy,
+                  rz = s_pts[3 * (size_t)j + 2] - qz;
+#pragma unroll
+      for (int k = 0; k < KP; k++) {
+        const float dx = rx - kp.v[3 * k], dy = ry - kp.v[3 * k + 1], dz = rz - kp.v[3 * k + 2];
+        const float d2 = dx * dx + dy * dy + dz * dz;
+        w[k] = fmaxf(fmaf(-d2 * rsqrtf(fmaxf(d2, 1e-30f)), inv_sigma, 1.f), 0.f);
+        mask |= (w[k] > 0.f ? 1u : 0u) << k;
+      }
+      cnt += flags ? (int)flags[j] : 1;
+    }
+    const unsigned vmask = __ballot_sync(0xffffffffu, mask != 0);
+    const int slot = __popc(vmask & ((1u << lane) - 1u));
+    const int nv = __popc(vmask);
+    if (mask != 0) {
+#pragma unroll
+      for (int k = 0; k < KP; k++) s_w[warp][k][slot] = w[k];
+      s_j[warp][slot] = j;
+      s_m[warp][slot] = mask;
+    }
+    __syncwarp();
+    constexpr int UN = CPL >= 4 ? 2 : 4;  // neighbours whose feature rows are in flight together
+#define LCR_ACC_CASE(K)                                                         \
+  case K:                                                                       \
+    _Pragma("unroll") for (int i = 0; i < CPL; i++) acc[K][i] = fmaf(wk, f[i], acc[K][i]); \
+    break;
+    auto accumulate = [&](const float (&f)[CPL], int hh) {
+      unsigned mm = s_m[warp][hh];
+      while (mm) {
+        const int k = __ffs(mm) - 1;
+        mm &= mm - 1;
+        const float wk = s_w[warp][k][hh];
+        switch (k) {
+          LCR_ACC_CASE(0) LCR_ACC_CASE(1) LCR_ACC_CASE(2) LCR_ACC_CASE(3) LCR_ACC_CASE(4) LCR_ACC_CASE(5)
+          LCR_ACC_CASE(6) LCR_ACC_CASE(7) LCR_ACC_CASE(8) LCR_ACC_CASE(9) LCR_ACC_CASE(10) LCR_ACC_CASE(11)
+          LCR_ACC_CASE(12) LCR_ACC_CASE(13) LCR_ACC_CASE(14)
+          default: break;
+        }
+      }
+    };
+#undef LCR_ACC_CASE
+    int hh = 0;
+    for (; hh + UN <= nv; hh += UN) {
+      float fv[UN][CPL];
+#pragma unroll
+      for (int u = 0; u < UN; u++) {
+        const float* f = s_feats + (size_t)s_j[warp][hh + u] * C + lane;
+#pragma unroll
+        for (int i = 0; i < CPL; i++) fv[u][i] = f[32 * i];
+      }
+#pragma unroll
+      for (int u = 0; u < UN; u++) accumulate(fv[u], hh + u);
+    }
+    for (; hh < nv; hh++) {
+      const float* f = s_feats + (size_t)s_j[warp][hh] * C + lane;
+      float fv[CPL];
+#pragma unroll
+      for (int i = 0; i < CPL; i++) fv[i] = f[32 * i];
+      accumulate(fv, hh);
+    }
+    __syncwarp();
+  }
+  cnt = lcr_warp_sum(cnt);
+  float* o = wf + (size_t)m * (KP * C) + lane;
+#pragma unroll
+  for (int k = 0; k < KP; k++)
+#pragma unroll
+    for (int i = 0; i < CPL; i++) o[k * C + 32 * i] = acc[k][i];
   if (lane == 0) rowscale[m] = 1.f / (float)max(cnt, 1);
 }
 
@@ -656,15 +1002,19 @@ static int g_gather_mode = -1;
 static int gather_mode() {
   if (g_gather_mode < 0) {
     const char* e = getenv("LCR_GATHER");
-    g_gather_mode = !e ? 3 : !strcmp(e, "exact") ? 0 : !strcmp(e, "dense") ? 1 : !strcmp(e, "sparse") ? 2 : 3;
+    g_gather_mode = !e ? 3 : !strcmp(e, "exact") ? 0 : !strcmp(e, "dense") ? 1 : !strcmp(e, "sparse") ? 2 : !strcmp(e, "mask") ? 4 : !strcmp(e, "packed") ? 5 : !strcmp(e, "mma") ? 6 : 3;
   }
   return g_gather_mode;
 }
-extern "C" void lcr_set_gather_mode(int mode) { g_gather_mode = mode < 0 || mode > 3 ? 3 : mode; }
+extern "C" void lcr_set_gather_mode(int mode) { g_gather_mode = mode < 0 || mode > 6 ? 3 : mode; }
 
 // ================================================================== C ABI
 extern "C" size_t lcr_kpconv_ws_bytes(int64_t m_rows, int c_in) {
   return lcr_align_up((size_t)m_rows * KP * c_in * sizeof(float)) + lcr_align_up((size_t)m_rows * sizeof(float)) + 256;
+}
+// with room for the packed (x, y, z, flag) copy of the n_support points the fast gather reads
+extern "C" size_t lcr_kpconv_ws_bytes2(int64_t m_rows, int64_t n_support, int c_in) {
+  return lcr_kpconv_ws_bytes(m_rows, c_in) + lcr_align_up((size_t)n_support * sizeof(float4));
 }
 
 static int kpconv_impl(const float* s_feats, const uint8_t* s_flags, int64_t n_support, const float* q_points,
@@ -701,22 +1051,43 @@ static int kpconv_impl(const float* s_feats, const uint8_t* s_flags, int64_t n_s
   LcrArena a(ws, ws_bytes);
   float* wf = a.take<float>((size_t)M * KP * c_in);
   float* rowscale = a.take<float>(M);
+  float4* pts4 = a.take<float4>((size_t)N);
+  const bool have_pts4 = a.ok();      // callers that sized the workspace with lcr_kpconv_ws_bytes2
   {
   LcrProfScope prof("kpconv_gather", 2.0 * M * KP * (double)H * c_in,
                     4.0 * M * H + 4.0 * (double)N * c_in + 12.0 * (M + N) + 4.0 * (double)M * KP * c_in, stream);
   // variant (see gather_mode): exact dense / fast dense / sparse lists
   int mode = kernel_points_host == nullptr ? 0 : gather_mode();
-  if (mode == 3) mode = 1;   // auto: measured on B200, the fast dense loop wins or ties for every width (scripts/bench_gather.py)
+  // auto, measured on B200 (scripts/bench_gather.py): the warp-MMA kernel wins for C = 32 (0.67 vs 0.79 ms on 465 k
+  // queries), ties at C = 64 and loses above (register pressure); the fast dense loop wins or ties over the sparse /
+  // mask / packed-FMA forms for every width
+  if (mode == 3) mode = c_in == 32 ? 6 : 1;
+  if ((mode == 1 || mode == 6) && !have_pts4) mode = 5;   // no room for the packed points: the packed-FMA loop reads the 12-byte points
+  if (mode == 1 || mode == 6) {
+    pack_points_kernel<<<(N + 255) / 256, 256, 0, stream>>>(s_points, s_flags, N, pts4);
+    LCR_LAUNCHED(1);
+  }
   KpArg kp;
   if (mode != 0) memcpy(kp.v, kernel_points_host, sizeof(kp.v));
   else memset(kp.v, 0, sizeof(kp.v));
 #define LCR_GATHER(CPL)                                                                                             \
   if (mode == 0)                                                                                                    \
     kpconv_gather_kernel<CPL, false><<<grid, 128, 0, stream>>>(s_feats, q_points, s_points, idx, ld_idx, H,         \
-                                                               kernel_points, kp, sigma, s_flags, M, N, wf, rowscale); \
+                                                               kernel_points, kp, sigma, s_flags, nullptr, M, N, wf, \
+                                                               rowscale);                                           \
   else if (mode == 1)                                                                                               \
     kpconv_gather_kernel<CPL, true><<<grid, 128, 0, stream>>>(s_feats, q_points, s_points, idx, ld_idx, H,          \
-                                                              kernel_points, kp, sigma, s_flags, M, N, wf, rowscale); \
+                                                              kernel_points, kp, sigma, s_flags, pts4, M, N, wf,    \
+                                                              rowscale);                                            \
+  else if (mode == 6)                                                                                               \
+    kpconv_gather_mma_kernel<CPL><<<grid, 128, 0, stream>>>(s_feats, q_points, pts4, idx, ld_idx, H, kernel_points, \
+                                                            sigma, M, N, wf, rowscale);                             \
+  else if (mode == 5)                                                                                               \
+    kpconv_gather_packed_kernel<CPL><<<grid, 128, 0, stream>>>(s_feats, q_points, s_points, idx, ld_idx, H, kp,     \
+                                                               sigma, s_flags, M, N, wf, rowscale);                 \
+  else if (mode == 4)                                                                                               \
+    kpconv_gather_mask_kernel<CPL><<<grid, 128, 0, stream>>>(s_feats, q_points, s_points, idx, ld_idx, H, kp,       \
+                                                             sigma, s_flags, M, N, wf, rowscale);                   \
   else                                                                                                              \
     kpconv_gather_sparse_kernel<CPL><<<grid, 128, 0, stream>>>(s_feats, q_points, s_points, idx, ld_idx, H, kp,     \
                                                                sigma, s_flags, M, N, wf, rowscale)

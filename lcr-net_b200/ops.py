@@ -111,7 +111,7 @@ def kpconv(s_feats, q_points, s_points, idx, kernel_points, sigma, weights, bias
     w_hi = w_lo = None
     if weights_nk is not None and c_in > 1 and use_tensor_cores():
         w_hi, w_lo = tf32_split(weights_nk)
-    ws_bytes = L.lcr_kpconv_ws_bytes(m, c_in)
+    ws_bytes = L.lcr_kpconv_ws_bytes2(m, n, c_in)
     ws = _lib.workspace.get(ws_bytes, s_feats.device, slot=1)
     if gn is not None and w_hi is not None and gn_fusable(gn[0]) and m > 0:
         stacks, eps, groups = gn

@@ -79,10 +79,11 @@ def test_kpconv_vs_oracle(c_in, c_out):
                             t(b).cuda(), weights_nk=w_nk).cpu().numpy()
         assert max_err(got_tc, ref) < REL
         assert max_err(got_tc, got) < 1e-5
-        # gather variants with the kernel points as kernel arguments: fast dense loop, sparse lists, auto
+        # gather variants with the kernel points as kernel arguments: fast dense loop, sparse lists, auto,
+        # non-zero mask dispatch, packed FFMA2 loop, warp-level mma.sync (3xTF32)
         from lcrnet_b200 import _lib
         try:
-            for mode in (1, 2, 3):
+            for mode in (1, 2, 3, 4, 5, 6):
                 _lib.lib().lcr_set_gather_mode(mode)
                 got_v = ops.kpconv(t(feats).cuda(), t(q).cuda(), t(s).cuda(), t(idx).cuda(), t(kp).cuda(), 1.2,
                                    t(w).cuda(), t(b).cuda(), weights_nk=w_nk,
@@ -116,7 +117,7 @@ def test_kpconv_sparse_wide_table():
     w_nk = t(w).reshape(-1, 64).t().contiguous().cuda()
     from lcrnet_b200 import _lib
     try:
-        for mode in (1, 2):
+        for mode in (1, 2, 4, 5, 6):
             _lib.lib().lcr_set_gather_mode(mode)
             got = ops.kpconv(t(feats).cuda(), t(q).cuda(), t(s).cuda(), t(idx).cuda(), t(kp).cuda(), 1.2, t(w).cuda(),
                              None, weights_nk=w_nk, kernel_points_host=t(kp).contiguous()).cpu().numpy()
