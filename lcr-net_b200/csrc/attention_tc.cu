@@ -140,7 +140,9 @@ attention_tc_kernel(const float* __restrict__ q, int ld_q, const float* __restri
                     const int64_t* __restrict__ k_off, int heads, float scale_mul, float* __restrict__ out,
                     int ld_o) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // aligned by OFFSET arithmetic on the shared array (a uintptr_t round trip hides the address space from the
+  // compiler: every access through `base` became a generic LD/ST that it also had to order against global stores)
+  uint8_t* base = smem_raw + ((1024u - ((uint32_t)__cvta_generic_to_shared(smem_raw) & 1023u)) & 1023u);
   __shared__ uint64_t bar_tq, bar_tkv[2], bar_kv_ready, bar_s_full, bar_p_ready, bar_o_full;
   __shared__ uint32_t tmem_base_s;
   const int prob = blockIdx.y / heads, head = blockIdx.y % heads;

@@ -178,7 +178,9 @@ gemm_tf32x3_kernel(const float* __restrict__ A, int lda, const float* __restrict
                    const float* __restrict__ bias, int relu, const GnFuse gnf) {
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte aligned tiles (SWIZZLE_128B atom = 8 rows x 128 B)
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // aligned by OFFSET arithmetic on the shared array (a uintptr_t round trip hides the address space from the
+  // compiler: every access through `base` became a generic LD/ST that it also had to order against global stores)
+  uint8_t* base = smem_raw + ((1024u - ((uint32_t)__cvta_generic_to_shared(smem_raw) & 1023u)) & 1023u);
   constexpr int kATile = BM * BK * 4, kBTile = BN * BK * 4;
   constexpr int kStageBytes = 2 * kATile + 2 * kBTile;
   constexpr int CH = STAGES;                               // k-blocks per promotion chunk
@@ -391,7 +393,9 @@ gemm_tf32x3_small_kernel(const float* __restrict__ A, int lda, const float* __re
                          const float* __restrict__ rowscale, const float* __restrict__ bias, int relu,
                          const GnFuse gnf) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // aligned by OFFSET arithmetic on the shared array (a uintptr_t round trip hides the address space from the
+  // compiler: every access through `base` became a generic LD/ST that it also had to order against global stores)
+  uint8_t* base = smem_raw + ((1024u - ((uint32_t)__cvta_generic_to_shared(smem_raw) & 1023u)) & 1023u);
   constexpr int kATile = BM * BK * 4, kBTile = BN * BK * 4;
   __shared__ uint64_t full_bar, empty_bar, done_bar;
   __shared__ uint32_t tmem_base_s;
@@ -549,7 +553,9 @@ gemm_tf32x3_ws_kernel(const float* __restrict__ A, int lda, const float* __restr
                       int ldw, float* __restrict__ C, int ldc, int M, int N, int K, const float* __restrict__ rowscale,
                       const float* __restrict__ bias, int relu, const GnFuse gnf) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // aligned by OFFSET arithmetic on the shared array (a uintptr_t round trip hides the address space from the
+  // compiler: every access through `base` became a generic LD/ST that it also had to order against global stores)
+  uint8_t* base = smem_raw + ((1024u - ((uint32_t)__cvta_generic_to_shared(smem_raw) & 1023u)) & 1023u);
   constexpr int kATile = BM * BK * 4, kBTile = BN * BK * 4;
   constexpr int kStageBytes = 2 * kATile + 2 * kBTile;
   constexpr int kProd = kWsProducerWarps * 32;
