@@ -2,7 +2,7 @@
 """bench.py -- scan-pairs/sec of the LCR-Net descriptor hot path on B200.
 
 Workload (BASELINE.json configs[1], "single-scan encoder+global-descriptor forward, 64k
-synthetic pts"): every step processes a batch of P scan pairs (2P synthetic 65 536-point
+synthetic pts"): every step processes a batch of P = 32 scan pairs (2P synthetic 65 536-point
 KITTI-shaped scans) through raw points -> 0.3 m voxel pre-pass -> 3-level voxel pyramid ->
 7 radius-neighbour tables -> 11-block KPConv encoder -> NetVLAD descriptor, one descriptor per
 scan, plus the squared-L2 descriptor distance of every pair (the loop-detection score).
@@ -42,7 +42,7 @@ def parse():
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--pairs', type=int, default=16, help='scan pairs per step per GPU')
+    ap.add_argument('--pairs', type=int, default=32, help='scan pairs per step per GPU')
     ap.add_argument('--cpu-pairs', type=int, default=1, help='pairs in the CPU baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--ncu', action='store_true', help='one warm-up step + one step only (for ncu captures)')
@@ -175,7 +175,8 @@ def run_reference(args):
     line = {'impl': 'reference', 'metric': METRIC, 'value': base['value'], 'unit': UNIT, 'n_gpus': args.gpus,
             'steps': args.steps, 'warmup': min(args.warmup, 1), 'ms_per_step': dt * 1e3, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': workload_config(args.cpu_pairs, limits), 'cpu_baseline': base,
+            'config': dict(workload_config(args.pairs, limits, args.streams), reference_sample_pairs=args.cpu_pairs),
+            'cpu_baseline': base,
             'e2e': {'value': base['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
     print(json.dumps(line))
 
@@ -411,9 +412,10 @@ def ncu_traffic(group, launches):
 
 def run_db(args):
     """configs[3]/[4]: every rank builds the descriptors of its contiguous shard of `db_scans`
-    scans (a pool of 32 distinct synthetic scans cycled: descriptor cost does not depend on the
-    content), ONE all-gather assembles the database, then each rank answers its own shard's queries
-    with the brute-force L2 top-25 kernel.  One step = the whole build + search."""
+    scans (a pool of 64 distinct synthetic scans cycled with a small per-batch offset: descriptor cost
+    does not depend on the content; batches of 64 scans through the 2-stream DescriptorPipeline), ONE
+    all-gather assembles the database, then each rank answers its own shard's queries with the
+    brute-force L2 top-25 kernel.  One step = the whole build + search."""
     import torch
     import torch.distributed as dist
     from lcrnet_b200 import _lib, checkpoint, model, retrieval
@@ -428,19 +430,19 @@ def run_db(args):
     net = model.create_model(model.default_cfg()).eval()
     net.load_state_dict(checkpoint.random_state_dict('global_descriptor', 7351), strict=True)
     net = net.to(dev)
-    pool = make_scans(16, rank)
+    from lcrnet_b200 import pipeline
+    pool = make_scans(32, rank)
     limits = gdata.calibrate_neighbors_stack_mode(pool[:2], NUM_STAGES, VOXEL, RADIUS, pre_voxel=VOXEL, device=dev)
     pts = torch.from_numpy(np.concatenate(pool, 0)).to(dev)
-    lens = torch.tensor([len(s) for s in pool], dtype=torch.int64, device=dev)
+    lens_list = [len(s) for s in pool]
     n_local, batch = args.db_scans, len(pool)
     jitter = torch.linspace(0.0, 0.05, steps=(n_local + batch - 1) // batch, device=dev)
+    pipe = pipeline.DescriptorPipeline(net, limits, NUM_STAGES, VOXEL, RADIUS, pre_voxel=VOXEL, n_streams=args.streams)
 
     def step():
         out = []
         for b in range((n_local + batch - 1) // batch):
-            d = gdata.device_collate(pts + jitter[b], lens, NUM_STAGES, VOXEL, RADIUS, limits, pre_voxel=VOXEL,
-                                     stack_size=1, int32=True, upsampling=False)
-            out.append(net(d)['anc_global'])
+            out.append(pipe(pts + jitter[b], lens_list))
         local_db = torch.cat(out)[:n_local].contiguous()
         ev = torch.cuda.Event(enable_timing=True)
         ev.record()
@@ -505,10 +507,13 @@ def run_pairs(args):
     pts = torch.from_numpy(np.concatenate(scans, 0)).to(dev)
     lens = torch.tensor([len(s) for s in scans], dtype=torch.int64, device=dev)
 
-    def step():
-        d = gdata.device_collate(pts, lens, NUM_STAGES, VOXEL, RADIUS, limits, pre_voxel=VOXEL, stack_size=2,
-                                 int32=True, upsampling=True)
-        return net(d)
+    from lcrnet_b200 import pipeline
+    lens_list = [len(s) for s in scans]
+    pipe = pipeline.PairPipeline(net, limits, NUM_STAGES, VOXEL, RADIUS, pre_voxel=VOXEL, n_streams=args.streams)
+    pipe1 = pipeline.PairPipeline(net, limits, NUM_STAGES, VOXEL, RADIUS, pre_voxel=VOXEL, n_streams=1)
+
+    def step(p=None):
+        return (p or pipe)(pts, lens_list)
 
     for _ in range(max(1, min(args.warmup, 2))):
         out = step()
@@ -521,16 +526,15 @@ def run_pairs(args):
         b.record()
         torch.cuda.synchronize()
         times.append(a.elapsed_time(b))
-    roof = dominant_kernel_roofline(lambda p, l: step(), pts, lens, torch.empty(1 << 20, dtype=torch.uint8, device=dev))
-    T = out['estimated_transform']
-    n_corr = [int(c.shape[0]) for c in out['corr_scores']] if isinstance(out['corr_scores'], list) else \
-        [int(out['corr_scores'].shape[0])]
+    roof = dominant_kernel_roofline(lambda p, l: step(pipe1), pts, lens, torch.empty(1 << 20, dtype=torch.uint8, device=dev))
+    T = torch.stack([o['estimated_transform'] for o in out])
+    n_corr = [int(o['corr_scores'].shape[0]) for o in out]
     print(json.dumps({'metric': 'registration_pairs_per_sec', 'value': args.pairs * args.steps / (sum(times) * 1e-3),
                       'unit': 'pairs/s', 'n_gpus': 1, 'steps': args.steps, 'ms_per_step': sum(times) / args.steps,
                       'higher_is_better': True, 'dtype': 'f32', 'data': 'synthetic',
                       'config': {'workload': 'configs[2]: scan-pair registration (LCRNet full forward), batch %d pairs'
                                              % args.pairs, 'neighbor_limits': limits,
-                                 'weights': 'seeded random: correspondences are not meaningful'},
+                                 'weights': 'seeded random: correspondences are not meaningful', 'streams': args.streams},
                       'mean_correspondences': float(np.mean(n_corr)), 'finite': bool(torch.isfinite(T).all()),
                       'kernel_groups': roof['kernel_groups'] if roof else None}))
 

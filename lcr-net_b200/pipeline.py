@@ -73,3 +73,70 @@ class DescriptorPipeline:
         if self.pool is not None:
             self.pool.shutdown()
             self.pool = None
+
+
+class PairPipeline:
+    """``pipe(points, lengths)`` -> list of per-pair output dicts of ``LCRNet`` (registration path).
+
+    The batch of pairs (2 scans each, consecutive) is cut into ``n_streams`` chunks, each collated and
+    registered on its own CUDA stream from its own host thread.  The registration tail is a chain of
+    small per-pair launches with device->host size read-backs (correspondence counts); with two chunks
+    in flight one chunk's read-back stalls are filled by the other chunk's kernels.  Pairs are
+    independent units: results equal the single-stream path."""
+
+    def __init__(self, net, neighbor_limits, num_stages=4, voxel_size=0.3, search_radius=1.275, pre_voxel=0.3,
+                 n_streams=2, device=None):
+        self.net, self.limits = net, list(neighbor_limits)
+        self.num_stages, self.voxel, self.radius, self.pre_voxel = num_stages, voxel_size, search_radius, pre_voxel
+        self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+        self.n_streams = max(1, int(n_streams))
+        self.streams = [torch.cuda.Stream(self.device) for _ in range(self.n_streams)]
+        self.pool = ThreadPoolExecutor(self.n_streams) if self.n_streams > 1 else None
+
+    def _chunk(self, points, lens, lo, hi, row_lo, row_hi, stream, ready):
+        torch.cuda.set_device(self.device)
+        with torch.cuda.stream(stream):
+            stream.wait_event(ready)
+            p = points[row_lo:row_hi]
+            if not p.is_cuda:
+                p = p.to(self.device, non_blocking=True)
+            l = torch.tensor(lens[lo:hi], dtype=torch.int64).to(self.device, non_blocking=True)
+            d = gdata.device_collate(p, l, self.num_stages, self.voxel, self.radius, self.limits,
+                                     pre_voxel=self.pre_voxel, stack_size=2, int32=True, upsampling=True)
+            out = self.net(d)
+            done = torch.cuda.Event()
+            done.record(stream)
+        n_pairs = (hi - lo) // 2
+        if n_pairs == 1:
+            return [out], done
+        keys = list(out.keys())
+        return [{k: out[k][i] for k in keys} for i in range(n_pairs)], done
+
+    def __call__(self, points, lengths):
+        lens = [int(x) for x in (lengths.tolist() if torch.is_tensor(lengths) else lengths)]
+        assert len(lens) % 2 == 0, 'scans come in (reference, source) pairs'
+        n_pairs = len(lens) // 2
+        main = torch.cuda.current_stream(self.device)
+        ready = torch.cuda.Event()
+        ready.record(main)
+        k = min(self.n_streams, n_pairs)
+        bounds = [2 * (n_pairs * i // k) for i in range(k + 1)]
+        rows = [0]
+        for x in lens:
+            rows.append(rows[-1] + x)
+        jobs = [(points, lens, bounds[i], bounds[i + 1], rows[bounds[i]], rows[bounds[i + 1]], self.streams[i], ready)
+                for i in range(k)]
+        if self.pool is None or k == 1:
+            res = [self._chunk(*j) for j in jobs]
+        else:
+            res = [f.result() for f in [self.pool.submit(self._chunk, *j) for j in jobs]]
+        outs = []
+        for o, e in res:
+            main.wait_event(e)
+            outs += o
+        return outs
+
+    def close(self):
+        if self.pool is not None:
+            self.pool.shutdown()
+            self.pool = None
