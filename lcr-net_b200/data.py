@@ -17,8 +17,12 @@ def precompute_data_stack_mode(points, lengths, num_stages, voxel_size, radius, 
     """Same arguments / result dict as data.py:10-74.  Extra keys: ``lengths_host`` (list of
     python int lists, saves the model a device sync).  ``int32`` keeps the tables in the kernels'
     native index width; ``upsampling=False`` skips the three tables only the registration decoder
-    reads (the descriptor path never touches them)."""
+    reads (the descriptor path never touches them).  With ``int32`` the searches are queued back to back
+    (no per-table read-back: tables keep ``neighbor_limits[i]`` columns, pads = number of support rows) and their
+    status words ride on the single device->host read of the level lengths."""
     assert num_stages == len(neighbor_limits)
+    from . import ext
+    defer = [] if int32 and all(l and l > 0 for l in neighbor_limits) else None
     points_list, lengths_list, lengths_host = [], [], []
     neighbors_list, subsampling_list, upsampling_list = [], [], []
     for i in range(num_stages):
@@ -30,16 +34,22 @@ def precompute_data_stack_mode(points, lengths, num_stages, voxel_size, radius, 
     for i in range(num_stages):
         cur_points, cur_lengths = points_list[i], lengths_list[i]
         neighbors_list.append(ops.radius_search(cur_points, cur_points, cur_lengths, cur_lengths, radius,
-                                                neighbor_limits[i], int32=int32))
+                                                neighbor_limits[i], int32=int32, defer=defer))
         if i < num_stages - 1:
             sub_points, sub_lengths = points_list[i + 1], lengths_list[i + 1]
             subsampling_list.append(ops.radius_search(sub_points, cur_points, sub_lengths, cur_lengths, radius,
-                                                      neighbor_limits[i], int32=int32))
+                                                      neighbor_limits[i], int32=int32, defer=defer))
             if upsampling:
                 upsampling_list.append(ops.radius_search(cur_points, sub_points, cur_lengths, sub_lengths, radius * 2,
-                                                         neighbor_limits[i + 1], int32=int32))
+                                                         neighbor_limits[i + 1], int32=int32, defer=defer))
         radius *= 2
-    lengths_host = torch.stack(lengths_list).cpu().tolist()
+    if defer:
+        n_len = lengths_list[0].numel() * num_stages
+        both = torch.cat([torch.stack(lengths_list).reshape(-1)] + [m.to(torch.int64) for m in defer]).cpu()
+        lengths_host = both[:n_len].reshape(num_stages, -1).tolist()
+        ext.check_deferred(both[n_len:].reshape(-1, 2).tolist())
+    else:
+        lengths_host = torch.stack(lengths_list).cpu().tolist()
     return {
         'points': points_list,
         'lengths': lengths_list,

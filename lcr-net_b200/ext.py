@@ -60,9 +60,12 @@ def grid_subsampling(points, lengths, voxel_size, order='reference'):
     return [s_points, s_lengths]
 
 
-def radius_neighbors(q_points, s_points, q_lengths, s_lengths, radius, limit=0, int32=False):
+def radius_neighbors(q_points, s_points, q_lengths, s_lengths, radius, limit=0, int32=False, defer=None):
     """``utils.ext.radius_neighbors`` (radius_neighbors.cpp:5-68): (Nq, max_count) int64 table,
-    padded with Ns.  ``limit`` > 0 fuses the ``[:, :limit]`` cut of ops/radius_search.py:25-26."""
+    padded with Ns.  ``limit`` > 0 fuses the ``[:, :limit]`` cut of ops/radius_search.py:25-26.
+    ``defer`` (a list, with ``limit`` > 0): do not read the [max_count, status] words back -- the table keeps
+    ``limit`` columns (pads = Ns) and the device words are appended to the list for ONE later check
+    (``check_deferred``): the pyramid builder queues its 7-10 searches without draining the stream."""
     for name, t in (('q_points', q_points), ('s_points', s_points)):
         _check(t.dtype == torch.float32, '%s must be a float tensor' % name)
         _check(t.is_contiguous(), '%s must be contiguous' % name)
@@ -92,6 +95,9 @@ def radius_neighbors(q_points, s_points, q_lengths, s_lengths, radius, limit=0, 
     if limit and limit > 0:
         out = torch.empty((nq, limit), dtype=dtype, device=dev)
         run(limit, out)
+        if defer is not None and not on_cpu:
+            defer.append(meta)
+            return out
         mc, st = meta.tolist()
         if mc < limit:
             out = out[:, :mc]
@@ -107,6 +113,14 @@ def radius_neighbors(q_points, s_points, q_lengths, s_lengths, radius, limit=0, 
         raise RuntimeError('radius_neighbors: capacity exceeded (cloud spans > 16384 cells per axis or '
                            '> 8192 neighbours for one query)')
     return out.cpu() if on_cpu else out
+
+
+def check_deferred(status_words):
+    """Raise if any deferred search overflowed; ``status_words`` = host list of [max_count, status] pairs."""
+    for mc, st in status_words:
+        if st != 0:
+            raise RuntimeError('radius_neighbors: capacity exceeded (cloud spans > 16384 cells per axis or '
+                               '> 8192 neighbours for one query)')
 
 
 def radius_filter(*args, **kwargs):
