@@ -104,7 +104,8 @@ size_t lcr_kpconv_ws_bytes2(int64_t m_query, int64_t n_support, int c_in);
  * 0 = exact dense loop (IEEE sqrt / divide influences, also used without host kernel points), 1 = fast dense
  * loop (rsqrt influences, constant-bank kernel points), 2 = sparse influence lists, 3 = auto (default: 6 for
  * c_in = 32, 1 otherwise -- the measured winners on B200), 4 = non-zero-influence mask dispatch, 5 = packed
- * fp32 FMA (FFMA2) loop, 6 = warp-level tensor path (mma.sync m16n8k8, 3xTF32). */
+ * fp32 FMA (FFMA2) loop, 6 = warp-level tensor path (mma.sync m16n8k8, 3xTF32), 7 = fast dense loop that skips
+ * all-zero float4 groups of kernel points. */
 void lcr_set_gather_mode(int mode);
 int lcr_kpconv(const float* s_feats, const uint8_t* s_flags, int64_t n_support, const float* q_points,
                int64_t m_query, const float* s_points, const int32_t* idx, int ld_idx, int H,

@@ -40,7 +40,11 @@ struct KpArg { float v[KP * 3]; };
 // 1 - d/sigma with d = d2 * rsqrt(d2) and a multiply by 1/sigma instead of the IEEE sqrt + divide
 // sequences (<= 3e-7 absolute from the reference's weights; parity bar 1e-4): the influence pass is
 // ~2.5x shorter, which matters most for the narrow layers where it outweighs the accumulation.
-template <int CPL, bool FAST>  // channels per lane: C = 32 * CPL
+// GS ("group skip", FAST only): the influence pass also leaves a 4-bit mask per neighbour saying which of the four
+// float4 groups of kernel points hold a non-zero influence (~1.4 of 4); the accumulation loads and multiplies
+// only those groups.  The dense loop is bound by L1 wavefronts (4 broadcast LDS.128 + the feature row per
+// neighbour) and issue slots (15 FFMA per channel): both drop.
+template <int CPL, bool FAST, bool GS = false>  // channels per lane: C = 32 * CPL
 __global__ void __launch_bounds__(128)
 kpconv_gather_kernel(const float* __restrict__ s_feats, const float* __restrict__ q_pts,
                      const float* __restrict__ s_pts, const int32_t* __restrict__ idx, int ld_idx, int H,
@@ -53,6 +57,7 @@ kpconv_gather_kernel(const float* __restrict__ s_feats, const float* __restrict_
   __shared__ __align__(16) float4 s_w[4][4][32];
   __shared__ int s_j[4][32];
   __shared__ float s_kp[KP * 3];
+  __shared__ unsigned s_gm[4][32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (!FAST) {
     if (threadIdx.x < KP * 3) s_kp[threadIdx.x] = kpts[threadIdx.x];
@@ -107,6 +112,13 @@ kpconv_gather_kernel(const float* __restrict__ s_feats, const float* __restrict_
 #pragma unroll
       for (int g = 0; g < 4; g++) s_w[warp][g][slot] = make_float4(w[4 * g], w[4 * g + 1], w[4 * g + 2], w[4 * g + 3]);
       s_j[warp][slot] = j;
+      if (GS) {
+        unsigned gm = 0;
+#pragma unroll
+        for (int g = 0; g < 4; g++)
+          gm |= ((w[4 * g] > 0.f) | (w[4 * g + 1] > 0.f) | (w[4 * g + 2] > 0.f) | (w[4 * g + 3] > 0.f) ? 1u : 0u) << g;
+        s_gm[warp][slot] = gm;
+      }
       cnt += sp.w != 0.f;
     }
     __syncwarp();
@@ -119,6 +131,25 @@ kpconv_gather_kernel(const float* __restrict__ s_feats, const float* __restrict_
         const float* f = s_feats + (size_t)s_j[warp][hh + u] * C + lane;
 #pragma unroll
         for (int i = 0; i < CPL; i++) fv[u][i] = f[32 * i];
+      }
+      if (GS) {
+#pragma unroll
+        for (int u = 0; u < UN; u++) {
+          const unsigned gm = s_gm[warp][hh + u];
+#pragma unroll
+          for (int g = 0; g < 4; g++) {
+            if (!(gm & (1u << g))) continue;            // warp-uniform
+            const float4 t = s_w[warp][g][hh + u];
+            const float wv[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+            for (int kk = 0; kk < 4; kk++) {
+              if (4 * g + kk >= KP) continue;
+#pragma unroll
+              for (int i = 0; i < CPL; i++) acc[4 * g + kk][i] = fmaf(wv[kk], fv[u][i], acc[4 * g + kk][i]);
+            }
+          }
+        }
+        continue;
       }
 #pragma unroll
       for (int u = 0; u < UN; u++) {
@@ -1002,11 +1033,11 @@ static int g_gather_mode = -1;
 static int gather_mode() {
   if (g_gather_mode < 0) {
     const char* e = getenv("LCR_GATHER");
-    g_gather_mode = !e ? 3 : !strcmp(e, "exact") ? 0 : !strcmp(e, "dense") ? 1 : !strcmp(e, "sparse") ? 2 : !strcmp(e, "mask") ? 4 : !strcmp(e, "packed") ? 5 : !strcmp(e, "mma") ? 6 : 3;
+    g_gather_mode = !e ? 3 : !strcmp(e, "exact") ? 0 : !strcmp(e, "dense") ? 1 : !strcmp(e, "sparse") ? 2 : !strcmp(e, "mask") ? 4 : !strcmp(e, "packed") ? 5 : !strcmp(e, "mma") ? 6 : !strcmp(e, "group") ? 7 : 3;
   }
   return g_gather_mode;
 }
-extern "C" void lcr_set_gather_mode(int mode) { g_gather_mode = mode < 0 || mode > 6 ? 3 : mode; }
+extern "C" void lcr_set_gather_mode(int mode) { g_gather_mode = mode < 0 || mode > 7 ? 3 : mode; }
 
 // ================================================================== C ABI
 extern "C" size_t lcr_kpconv_ws_bytes(int64_t m_rows, int c_in) {
@@ -1062,8 +1093,8 @@ static int kpconv_impl(const float* s_feats, const uint8_t* s_flags, int64_t n_s
   // queries), ties at C = 64 and loses above (register pressure); the fast dense loop wins or ties over the sparse /
   // mask / packed-FMA forms for every width
   if (mode == 3) mode = c_in == 32 ? 6 : 1;
-  if ((mode == 1 || mode == 6) && !have_pts4) mode = 5;   // no room for the packed points: the packed-FMA loop reads the 12-byte points
-  if (mode == 1 || mode == 6) {
+  if ((mode == 1 || mode == 6 || mode == 7) && !have_pts4) mode = 5;   // no room for the packed points: the packed-FMA loop reads the 12-byte points
+  if (mode == 1 || mode == 6 || mode == 7) {
     pack_points_kernel<<<(N + 255) / 256, 256, 0, stream>>>(s_points, s_flags, N, pts4);
     LCR_LAUNCHED(1);
   }
@@ -1079,6 +1110,10 @@ static int kpconv_impl(const float* s_feats, const uint8_t* s_flags, int64_t n_s
     kpconv_gather_kernel<CPL, true><<<grid, 128, 0, stream>>>(s_feats, q_points, s_points, idx, ld_idx, H,          \
                                                               kernel_points, kp, sigma, s_flags, pts4, M, N, wf,    \
                                                               rowscale);                                            \
+  else if (mode == 7)                                                                                               \
+    kpconv_gather_kernel<CPL, true, true><<<grid, 128, 0, stream>>>(s_feats, q_points, s_points, idx, ld_idx, H,    \
+                                                                    kernel_points, kp, sigma, s_flags, pts4, M, N,  \
+                                                                    wf, rowscale);                                  \
   else if (mode == 6)                                                                                               \
     kpconv_gather_mma_kernel<CPL><<<grid, 128, 0, stream>>>(s_feats, q_points, pts4, idx, ld_idx, H, kernel_points, \
                                                             sigma, M, N, wf, rowscale);                             \

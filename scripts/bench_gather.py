@@ -24,7 +24,7 @@ kp = torch.from_numpy(checkpoint.default_kernel_points(1.275 * 2 ** level, rng))
 w_nk = w.reshape(-1, c_in).t().contiguous()
 L = _lib.lib()
 outs = []
-for mode, name in ((0, 'exact'), (1, 'dense'), (2, 'sparse'), (5, 'packed'), (6, 'mma')):
+for mode, name in ((0, 'exact'), (1, 'dense'), (2, 'sparse'), (6, 'mma'), (7, 'group')):
     L.lcr_set_gather_mode(mode)
     for it in range(3):
         L.lcr_profile_begin()
@@ -38,4 +38,4 @@ for mode, name in ((0, 'exact'), (1, 'dense'), (2, 'sparse'), (5, 'packed'), (6,
         L.lcr_profile_get(i, nm, 64, ctypes.byref(ms), ctypes.byref(fl), ctypes.byref(by))
         print('%-7s rows %d H %d C %d  %-14s %.3f ms' % (name, p.shape[0], nb.shape[1], c_in, nm.value.decode(), ms.value))
     outs.append(out)
-print('max |dense-exact| %.2e  |sparse-exact| %.2e  |packed-exact| %.2e |mma-exact| %.2e' % (float((outs[1] - outs[0]).abs().max()), float((outs[2] - outs[0]).abs().max()), float((outs[3] - outs[0]).abs().max()), float((outs[4] - outs[0]).abs().max())))
+print('max |dense-exact| %.2e  |sparse-exact| %.2e  |mma-exact| %.2e |group-exact| %.2e' % (float((outs[1] - outs[0]).abs().max()), float((outs[2] - outs[0]).abs().max()), float((outs[3] - outs[0]).abs().max()), float((outs[4] - outs[0]).abs().max())))

@@ -83,7 +83,7 @@ def test_kpconv_vs_oracle(c_in, c_out):
         # non-zero mask dispatch, packed FFMA2 loop, warp-level mma.sync (3xTF32)
         from lcrnet_b200 import _lib
         try:
-            for mode in (1, 2, 3, 4, 5, 6):
+            for mode in (1, 2, 3, 4, 5, 6, 7):
                 _lib.lib().lcr_set_gather_mode(mode)
                 got_v = ops.kpconv(t(feats).cuda(), t(q).cuda(), t(s).cuda(), t(idx).cuda(), t(kp).cuda(), 1.2,
                                    t(w).cuda(), t(b).cuda(), weights_nk=w_nk,
@@ -117,7 +117,7 @@ def test_kpconv_sparse_wide_table():
     w_nk = t(w).reshape(-1, 64).t().contiguous().cuda()
     from lcrnet_b200 import _lib
     try:
-        for mode in (1, 2, 4, 5, 6):
+        for mode in (1, 2, 4, 5, 6, 7):
             _lib.lib().lcr_set_gather_mode(mode)
             got = ops.kpconv(t(feats).cuda(), t(q).cuda(), t(s).cuda(), t(idx).cuda(), t(kp).cuda(), 1.2, t(w).cuda(),
                              None, weights_nk=w_nk, kernel_points_host=t(kp).contiguous()).cpu().numpy()
