@@ -357,12 +357,18 @@ class LCRNet(nn.Module):
             s['pkm'], s['akm'] = s['pos_km'][s['ci'].long()], s['anc_km'][s['cj'].long()]
         ot_all = self.optimal_transport(torch.cat(ms_all), torch.cat([s['pkm'] for s in st]),
                                         torch.cat([s['akm'] for s in st]))            # one launch, all patch pairs
-        outs, o0 = [], 0
+        # fine correspondences + LGR of every pair are queued first; the correspondence counts of all pairs come
+        # back in ONE device->host read (a read per pair drained the stream 32 times per batch)
+        launched, o0 = [], 0
         for p, s in enumerate(st):
-            a, b = 2 * p, 2 * p + 1
             ot = ot_all[o0:o0 + counts[p]]
             o0 += counts[p]
-            out = self._register(s, ot, node_ot[p])
+            launched.append((ot,) + self._register_launch(s, ot))
+        n_corr = torch.stack([l[4]['pair_off'][-1] for l in launched]).tolist()
+        outs = []
+        for p, s in enumerate(st):
+            a, b = 2 * p, 2 * p + 1
+            out = self._register_finish(s, launched[p], node_ot[p], n_corr[p])
             out.update({
                 'ori_pos_points_c': points_c[off_c[a]:off_c[a + 1]], 'ori_anc_points_c': points_c[off_c[b]:off_c[b + 1]],
                 'pos_points_f': s['pos_pf'], 'anc_points_f': s['anc_pf'],
@@ -379,14 +385,20 @@ class LCRNet(nn.Module):
         merged['estimated_transform'] = torch.stack(merged['estimated_transform'])
         return merged
 
-    def _register(self, s, ot, node_ot):
-        """Fine correspondences + local-to-global registration of one pair (LCRNet.py:251-262)."""
+    def _register_launch(self, s, ot):
+        """Queues fine correspondences + local-to-global registration of one pair (LCRNet.py:251-262); no
+        device->host traffic."""
         ci, cj = s['ci'], s['cj']
         corr = P.fine_correspondences(ot, s['pos_km'], ci, s['anc_km'], cj)
         ref_c, src_c = P.corr_points(corr, s['pos_pf'], s['pos_knn'], ci, s['anc_pf'], s['anc_knn'], cj)
         T = P.local_global_registration(ref_c, src_c, corr['score'], corr['pair_off'], self.acceptance_radius,
                                         self.correspondence_threshold, self.num_refinement_steps)
-        n = int(corr['pair_off'][-1])                                   # D2H: number of correspondences
+        return T, ref_c, src_c, corr
+
+    def _register_finish(self, s, launched, node_ot, n):
+        """Output dict of one pair; ``n`` = its number of fine correspondences (host int)."""
+        ot, T, ref_c, src_c, corr = launched
+        ci, cj = s['ci'], s['cj']
         pad3 = lambda x: torch.cat([x, torch.zeros_like(x[:1])], 0)
         m, k = s['pos_nf'].shape[0], s['anc_nf'].shape[0]
         return {'estimated_transform': T, 'pos_corr_points': ref_c[:n], 'anc_corr_points': src_c[:n],
