@@ -220,26 +220,41 @@ query_kernel(const float* __restrict__ q, int64_t nq, const int64_t* __restrict_
     }
     unsigned long long* keys = s_keys[warp];
     const bool want_idx = out_idx != nullptr;
-    for (int c = 0; c < 27; c++) {
-      const uint32_t st = __shfl_sync(0xffffffffu, c_start, c);
-      const uint32_t cn = __shfl_sync(0xffffffffu, c_count, c);
-      for (uint32_t base = 0; base < cn; base += 32) {
-        const uint32_t t = base + lane;
-        bool hit = false;
-        unsigned long long key = 0;
-        if (t < cn) {
-          const float4 p = sorted[st + t];
-          const float d2 = ref_d2(qx, qy, qz, p.x, p.y, p.z);
-          hit = d2 < r2;
-          key = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned long long)__float_as_uint(p.w);
-        }
-        const unsigned m = __ballot_sync(0xffffffffu, hit);
-        if (hit && want_idx) {
-          const int pos = total + __popc(m & ((1u << lane) - 1u));
-          if (pos < kWarpCap) keys[pos] = key;
-        }
-        total += __popc(m);
+    // The 27 candidate runs are walked as ONE flat stream of T candidates, 32 per step (a cell holds ~18 points:
+    // a per-cell loop left 44 % of the lanes idle and paid 27 loop iterations): an inclusive warp scan of the run
+    // lengths, then every lane finds the run of its candidate by a 5-step binary search over the lanes' exclusive
+    // prefixes (shuffles).  The hits of a query are sorted afterwards, so the visiting order does not matter.
+    uint32_t incl = c_count;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    const uint32_t excl = incl - c_count;
+    const uint32_t n_cand = __shfl_sync(0xffffffffu, incl, 31);
+    for (uint32_t base = 0; base < n_cand; base += 32) {
+      const uint32_t c = base + lane;
+      int run = 0;
+#pragma unroll
+      for (int step = 16; step > 0; step >>= 1) {
+        const uint32_t e = __shfl_sync(0xffffffffu, excl, run + step);
+        if (e <= c) run += step;
       }
+      const uint32_t st = __shfl_sync(0xffffffffu, c_start, run), ex = __shfl_sync(0xffffffffu, excl, run);
+      bool hit = false;
+      unsigned long long key = 0;
+      if (c < n_cand) {
+        const float4 p = sorted[st + (c - ex)];
+        const float d2 = ref_d2(qx, qy, qz, p.x, p.y, p.z);
+        hit = d2 < r2;
+        key = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned long long)__float_as_uint(p.w);
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, hit);
+      if (hit && want_idx) {
+        const int pos = total + __popc(m & ((1u << lane) - 1u));
+        if (pos < kWarpCap) keys[pos] = key;
+      }
+      total += __popc(m);
     }
     if (lane == 0) {
       if (out_counts) out_counts[qi] = total;
