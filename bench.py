@@ -183,23 +183,10 @@ def run_reference(args):
 
 def calibrated_limits_cpu(scans):
     """calibrate_neighbors_stack_mode (data.py:408-433) with the C oracle: 80 % quantile."""
+    from oracle import model_oracle as mo
     from oracle import native as on
-    hist_n = int(np.ceil(4 / 3 * np.pi * (RADIUS / VOXEL + 1) ** 3))
-    hists = np.zeros((NUM_STAGES, hist_n), dtype=np.int64)
-    for s in scans:
-        p, l = on.grid_subsample(s, np.array([len(s)], dtype=np.int64), VOXEL)
-        v, r = VOXEL, RADIUS
-        for i in range(NUM_STAGES):
-            if i > 0:
-                v *= 2
-                p, l = on.grid_subsample(p, l, v)
-            _, counts, _ = on.radius_neighbors(p, p, l, l, r, limit=1, return_counts=True)
-            hists[i] += np.bincount(np.minimum(counts, hist_n - 1), minlength=hist_n)[:hist_n]
-            r *= 2
-        if hists.sum(1).min() > 2000:
-            break
-    cum = np.cumsum(hists.T, axis=0)
-    return [int(x) for x in np.sum(cum < 0.8 * cum[hist_n - 1, :], axis=0)]
+    pre = [on.grid_subsample(s, np.array([len(s)], dtype=np.int64), VOXEL)[0] for s in scans]
+    return mo.calibrate_limits([[p] for p in pre], NUM_STAGES, VOXEL, RADIUS)
 
 
 def workload_config(pairs, limits, streams=1):
@@ -231,7 +218,7 @@ def run_b200(args):
     net = net.to(dev)
 
     scans = make_scans(args.pairs, rank)
-    limits = gdata.calibrate_neighbors_stack_mode(scans[:2], NUM_STAGES, VOXEL, RADIUS, pre_voxel=VOXEL, device=dev)
+    limits = gdata.calibrate_neighbors_scans(scans[:2], NUM_STAGES, VOXEL, RADIUS, pre_voxel=VOXEL, device=dev)
     host_pts = torch.from_numpy(np.concatenate(scans, 0)).pin_memory()
     host_len = torch.tensor([len(s) for s in scans], dtype=torch.int64).pin_memory()
     dev_pts, dev_len = host_pts.to(dev), host_len.to(dev)
@@ -432,7 +419,7 @@ def run_db(args):
     net = net.to(dev)
     from lcrnet_b200 import pipeline
     pool = make_scans(32, rank)
-    limits = gdata.calibrate_neighbors_stack_mode(pool[:2], NUM_STAGES, VOXEL, RADIUS, pre_voxel=VOXEL, device=dev)
+    limits = gdata.calibrate_neighbors_scans(pool[:2], NUM_STAGES, VOXEL, RADIUS, pre_voxel=VOXEL, device=dev)
     pts = torch.from_numpy(np.concatenate(pool, 0)).to(dev)
     lens_list = [len(s) for s in pool]
     n_local, batch = args.db_scans, len(pool)
@@ -500,7 +487,7 @@ def run_pairs(args):
     dev = torch.device('cuda', int(os.environ.get('LOCAL_RANK', '0')))
     torch.cuda.set_device(dev)
     scans = make_scans(args.pairs)
-    limits = gdata.calibrate_neighbors_stack_mode(scans[:2], NUM_STAGES, VOXEL, RADIUS, pre_voxel=VOXEL, device=dev)
+    limits = gdata.calibrate_neighbors_scans(scans[:2], NUM_STAGES, VOXEL, RADIUS, pre_voxel=VOXEL, device=dev)
     net = lcrnet.create_model(lcrnet.default_cfg(limits)).eval()
     net.load_state_dict(checkpoint.random_state_dict('lcrnet', 7351), strict=True)
     net = net.to(dev)

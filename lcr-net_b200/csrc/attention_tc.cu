@@ -350,10 +350,11 @@ extern "C" int lcr_attention_tc(const float* q, int ld_q, const float* k, int ld
                   (((uintptr_t)q | (uintptr_t)k | (uintptr_t)v | (uintptr_t)out) & 15) == 0,
               "attention_tc: rows must be 16-byte aligned (TMA bulk copies)");
   if (max_q_rows == 0) return LCR_OK;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static LcrOncePerDevice attr_done;
+  const int attr_done_dev = attr_done.need();
+  if (attr_done_dev != -1) {
     LCR_CUDA_TRY(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    attr_done = true;
+    attr_done.done(attr_done_dev);
   }
   LcrProfScope prof("attention_tc", flops_hint, 0.0, stream);
   dim3 grid((unsigned)((max_q_rows + QT - 1) / QT), (unsigned)(n_problems * heads));

@@ -49,6 +49,21 @@ struct LcrProfScope {
   ~LcrProfScope();
 };
 
+// Opt-in dynamic shared memory is a PER-DEVICE function attribute: set it once per (kernel, device).
+// Usage: static LcrOncePerDevice once; int d = once.need(); if (d != -1) { cudaFuncSetAttribute(...); once.done(d); }
+struct LcrOncePerDevice {
+  unsigned long long mask[2] = {0ull, 0ull};  // 128 devices; racing threads at worst set the attribute twice
+  // current device id if the attribute still has to be set on it, -1 if already done; -2: unknown device (always set)
+  int need() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 128) return -2;
+    return ((__atomic_load_n(&mask[dev >> 6], __ATOMIC_ACQUIRE) >> (dev & 63)) & 1ull) ? -1 : dev;
+  }
+  void done(int dev) {
+    if (dev >= 0 && dev < 128) __atomic_fetch_or(&mask[dev >> 6], 1ull << (dev & 63), __ATOMIC_RELEASE);
+  }
+};
+
 static inline size_t lcr_align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
 // Bump allocator over a caller-provided workspace.

@@ -750,11 +750,12 @@ int launch_tc_ws(const float* A, int lda, const float* W, const float* W_lo, int
                  int K, const float* rowscale, const float* bias, int relu, const GnFuse& gnf, cudaStream_t stream) {
   constexpr size_t smem = (size_t)STAGES * (2 * BM * BK * 4 + 2 * BN * BK * 4) + kWsEpilogueWarps * 32 * 33 * 4 + 1024;
   static_assert(smem <= 227 * 1024, "shared memory budget");
-  static bool attr_done = false;
-  if (!attr_done) {
+  static LcrOncePerDevice attr_done;
+  const int attr_done_dev = attr_done.need();
+  if (attr_done_dev != -1) {
     LCR_CUDA_TRY(cudaFuncSetAttribute(gemm_tf32x3_ws_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)smem));
-    attr_done = true;
+    attr_done.done(attr_done_dev);
   }
   const long tiles = (long)((M + BM - 1) / BM) * ((N + BN - 1) / BN);
   const unsigned grid = (unsigned)(tiles < LCR_SM_COUNT ? tiles : LCR_SM_COUNT);
@@ -768,11 +769,12 @@ int launch_tc_small(const float* A, int lda, const float* W, const float* W_lo, 
                     int K, const float* rowscale, const float* bias, int relu, const GnFuse& gnf, cudaStream_t stream) {
   constexpr size_t stage = 2 * BM * BK * 4 + 2 * BN * BK * 4;
   constexpr size_t smem = (stage > 8 * 32 * 33 * 4 ? stage : 8 * 32 * 33 * 4) + 1024;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static LcrOncePerDevice attr_done;
+  const int attr_done_dev = attr_done.need();
+  if (attr_done_dev != -1) {
     LCR_CUDA_TRY(cudaFuncSetAttribute(gemm_tf32x3_small_kernel<BN, PS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)smem));
-    attr_done = true;
+    attr_done.done(attr_done_dev);
   }
   dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
   gemm_tf32x3_small_kernel<BN, PS><<<grid, kThreads, smem, stream>>>(A, lda, W, W_lo, ldw, C, ldc, M, N, K, rowscale,
@@ -784,11 +786,12 @@ template <int BN, int STAGES, bool PS, int MINB = 1>
 int launch_tc(const float* A, int lda, const float* W, const float* W_lo, int ldw, float* C, int ldc, int M, int N, int K,
               const float* rowscale, const float* bias, int relu, const GnFuse& gnf, cudaStream_t stream) {
   constexpr size_t smem = (size_t)STAGES * (2 * BM * BK * 4 + 2 * BN * BK * 4) + 1024;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static LcrOncePerDevice attr_done;
+  const int attr_done_dev = attr_done.need();
+  if (attr_done_dev != -1) {
     LCR_CUDA_TRY(cudaFuncSetAttribute(gemm_tf32x3_kernel<BN, STAGES, PS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)smem));
-    attr_done = true;
+    attr_done.done(attr_done_dev);
   }
   dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
   gemm_tf32x3_kernel<BN, STAGES, PS, MINB><<<grid, kThreads, smem, stream>>>(A, lda, W, W_lo, ldw, C, ldc, M, N, K, rowscale,

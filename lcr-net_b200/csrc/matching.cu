@@ -708,22 +708,26 @@ __device__ void kabsch_rotation(const double H[3][3], double R[3][3]) {
       U[i][j] = sv[o] > 1e-30 ? A[i][o] / sv[o] : 0.0;
     }
   }
-  // complete degenerate columns of U to an orthonormal basis
+  // Complete degenerate columns of U (singular value ~ 0) from the matching V column, orthogonalised
+  // against the columns already fixed, so that V U^T tends to the identity on the null space: H = 0 (no
+  // correspondences / all-zero weights) gives R = I like torch.svd of a zero matrix (U = V = I, procrustes.py:53).
   auto norm3 = [](double* x) { return sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]); };
-  if (sv[ord[0]] <= 1e-30) { U[0][0] = 1; U[1][0] = 0; U[2][0] = 0; }
-  if (sv[ord[1]] <= 1e-30) {
-    double e[3] = {0, 0, 0};
-    int m = fabs(U[0][0]) < fabs(U[1][0]) ? (fabs(U[0][0]) < fabs(U[2][0]) ? 0 : 2) : (fabs(U[1][0]) < fabs(U[2][0]) ? 1 : 2);
-    e[m] = 1.0;
-    const double dp = e[0] * U[0][0] + e[1] * U[1][0] + e[2] * U[2][0];
-    double w[3] = {e[0] - dp * U[0][0], e[1] - dp * U[1][0], e[2] - dp * U[2][0]};
-    const double nw = norm3(w);
-    for (int i = 0; i < 3; i++) U[i][1] = w[i] / nw;
-  }
-  if (sv[ord[2]] <= 1e-30 * fmax(sv[ord[0]], 1.0) || sv[ord[2]] <= 1e-30) {
-    U[0][2] = U[1][0] * U[2][1] - U[2][0] * U[1][1];
-    U[1][2] = U[2][0] * U[0][1] - U[0][0] * U[2][1];
-    U[2][2] = U[0][0] * U[1][1] - U[1][0] * U[0][1];
+  const double tiny = 1e-30;
+  for (int j = 0; j < 3; j++) {
+    if (sv[ord[j]] > tiny) continue;
+    double best[3] = {0, 0, 0};
+    double best_n = 0.0;
+    for (int cand = 0; cand < 4 && best_n < 1e-6; cand++) {
+      double w[3];
+      for (int i = 0; i < 3; i++) w[i] = cand == 0 ? Vs[i][j] : (i == cand - 1 ? 1.0 : 0.0);
+      for (int c = 0; c < j; c++) {
+        const double dp = w[0] * U[0][c] + w[1] * U[1][c] + w[2] * U[2][c];
+        for (int i = 0; i < 3; i++) w[i] -= dp * U[i][c];
+      }
+      const double n = norm3(w);
+      if (n > best_n) { best_n = n; for (int i = 0; i < 3; i++) best[i] = w[i]; }
+    }
+    for (int i = 0; i < 3; i++) U[i][j] = best[i] / best_n;
   }
   // M = V U^T, d = sign(det M)
   double M[3][3];
@@ -930,7 +934,7 @@ extern "C" int lcr_sinkhorn(const float* scores, int batch, int rows, int cols, 
   const size_t vec = sizeof(float) * 3 * (size_t)(rows + 1 + cols + 1);
   const size_t mat = sizeof(float) * (size_t)(rows + 1) * (cols + 1);
   LCR_REQUIRE(vec <= 96 * 1024, "sinkhorn: problem too large");
-  LcrProfScope prof("sinkhorn", 4.0 * batch * (double)(rows + 1) * (cols + 1) * iters,
+  LcrProfScope prof(rows == PK && cols == PK ? "sinkhorn_point" : "sinkhorn_node", 4.0 * batch * (double)(rows + 1) * (cols + 1) * iters,
                     4.0 * batch * ((double)rows * cols + (double)(rows + 1) * (cols + 1)), stream);
   if (vec + mat <= 200 * 1024) {
     LCR_CUDA_TRY(cudaFuncSetAttribute(sinkhorn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,

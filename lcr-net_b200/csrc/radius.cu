@@ -447,11 +447,12 @@ extern "C" int lcr_radius_neighbors(const float* q_points, int64_t nq_total, con
         q_points, nq_total, w.q_off, batch, w.geom, inv_cell, r2, w.tkeys, w.tstart, w.tcount, w.tcap - 1, w.sorted,
         width, ns_total, (int64_t*)out_idx, out_counts, out_max_count, w.spill_list, w.spill_n);
     if (out_idx) {
-      static bool attr_set64 = false;
-      if (!attr_set64) {
+      static LcrOncePerDevice attr_set64;
+      const int attr_set64_dev = attr_set64.need();
+      if (attr_set64_dev != -1) {
         LCR_CUDA_TRY(cudaFuncSetAttribute(spill_kernel<int64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)spill_smem));
-        attr_set64 = true;
+        attr_set64.done(attr_set64_dev);
       }
       spill_kernel<int64_t><<<LCR_SM_COUNT, kSpillThreads, spill_smem, stream>>>(
           q_points, w.q_off, batch, w.geom, inv_cell, r2, w.tkeys, w.tstart, w.tcount, w.tcap - 1, w.sorted, width,
@@ -462,11 +463,12 @@ extern "C" int lcr_radius_neighbors(const float* q_points, int64_t nq_total, con
         q_points, nq_total, w.q_off, batch, w.geom, inv_cell, r2, w.tkeys, w.tstart, w.tcount, w.tcap - 1, w.sorted,
         width, ns_total, (int32_t*)out_idx, out_counts, out_max_count, w.spill_list, w.spill_n);
     if (out_idx) {
-      static bool attr_set32 = false;
-      if (!attr_set32) {
+      static LcrOncePerDevice attr_set32;
+      const int attr_set32_dev = attr_set32.need();
+      if (attr_set32_dev != -1) {
         LCR_CUDA_TRY(cudaFuncSetAttribute(spill_kernel<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)spill_smem));
-        attr_set32 = true;
+        attr_set32.done(attr_set32_dev);
       }
       spill_kernel<int32_t><<<LCR_SM_COUNT, kSpillThreads, spill_smem, stream>>>(
           q_points, w.q_off, batch, w.geom, inv_cell, r2, w.tkeys, w.tstart, w.tcount, w.tcap - 1, w.sorted, width,

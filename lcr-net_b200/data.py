@@ -88,20 +88,118 @@ def device_collate(points, lengths, num_stages, voxel_size, search_radius, neigh
     return d
 
 
-def calibrate_neighbors_stack_mode(scans, num_stages, voxel_size, search_radius, keep_ratio=0.8,
-                                   sample_threshold=2000, pre_voxel=None, device='cuda'):
-    """data.py:408-433: histogram of neighbourhood sizes per level (table limit 'hist_n' = the
-    number of points in a ball of the search radius at unit voxel density), keep the
-    ``keep_ratio`` quantile.  Runs the counting pass of the radius kernel only."""
+def _merge_samples(data_dicts):
+    """data.py:96-105 / :377-385: values with the same key gathered into lists, numpy -> torch."""
+    collated = {}
+    for data_dict in data_dicts:
+        for key, value in data_dict.items():
+            if isinstance(value, np.ndarray):
+                value = torch.from_numpy(value)
+            collated.setdefault(key, []).append(value)
+    return collated
+
+
+def _finish_collate(collated, feats, points_list, batch_size, num_stages, voxel_size, search_radius, neighbor_limits,
+                    precompute_data, device, stack_size):
+    lengths = torch.LongTensor([p.shape[0] for p in points_list])
+    points = torch.cat([torch.as_tensor(p, dtype=torch.float32) for p in points_list], dim=0)
+    if batch_size == 1:
+        for key, value in collated.items():           # remove wrapping brackets if batch_size is 1
+            collated[key] = value[0]
+    collated['features'] = feats
+    if precompute_data:
+        from . import _lib
+        _lib.require_cuda()
+        dev = torch.device(device)
+        d = precompute_data_stack_mode(points.contiguous().to(dev, non_blocking=True), lengths.to(dev), num_stages,
+                                       voxel_size, search_radius, neighbor_limits)
+        collated.update(d)
+        collated['features'] = feats.to(dev)
+        if stack_size is not None:
+            collated['stack_size'] = stack_size
+    else:
+        collated['points'] = points
+        collated['lengths'] = lengths
+    collated['batch_size'] = batch_size
+    return collated
+
+
+def registration_collate_fn_stack_mode(data_dicts, num_stages, voxel_size, search_radius, neighbor_limits,
+                                       precompute_data=True, device='cuda'):
+    """data.py:77-127, same arguments, same dict: points ordered [ref_1..ref_B, src_1..src_B], ``features`` the
+    concatenated ref/src features, the pyramid keys of precompute_data_stack_mode (int64 tables, as the reference
+    returns them), ``batch_size``; every other key passed through (unwrapped when batch_size == 1).  The pyramid is
+    built on ``device`` -- this collate runs in the main process (DataLoader ``num_workers=0``); worker processes
+    may still stack raw points with ``precompute_data=False`` (data.py:119-124)."""
+    batch_size = len(data_dicts)
+    collated = _merge_samples(data_dicts)
+    feats = torch.cat(collated.pop('ref_feats') + collated.pop('src_feats'), dim=0)
+    points_list = collated.pop('ref_points') + collated.pop('src_points')
+    # the model treats the whole collated sample as ONE stack (reference GroupNorm semantics): stack_size None
+    return _finish_collate(collated, feats, points_list, batch_size, num_stages, voxel_size, search_radius,
+                           neighbor_limits, precompute_data, device, None)
+
+
+def test_loop_detection_collate_fn_stack_mode_online(data_dicts, num_stages, voxel_size, search_radius,
+                                                     neighbor_limits, precompute_data=True, device='cuda'):
+    """data.py:350-406, same arguments, same dict (``features`` = the first sample's ``anc_feats``, like the
+    reference)."""
+    batch_size = len(data_dicts)
+    collated = _merge_samples(data_dicts)
+    feats = collated.pop('anc_feats')
+    points_list = collated.pop('anc_points')
+    return _finish_collate(collated, feats[0], points_list, batch_size, num_stages, voxel_size, search_radius,
+                           neighbor_limits, precompute_data, device, None)
+
+
+test_loop_detection_collate_fn_stack_mode_online.__test__ = False      # a collate function, not a pytest test
+
+
+def calibrate_neighbors_stack_mode(dataset, collate_fn, num_stages, voxel_size, search_radius, keep_ratio=0.8,
+                                   sample_threshold=2000):
+    """data.py:408-433, same arguments: histogram of neighbourhood sizes per level over the samples of
+    ``dataset`` (collated ONE SAMPLE at a time with a table limit of 'hist_n' = the number of points in a ball of
+    the search radius at unit voxel density; a sample may hold several clouds, e.g. a registration pair), stop
+    once every level has seen more than ``sample_threshold`` points, keep the ``keep_ratio`` quantile.  A row with
+    hist_n or more neighbours falls off the histogram exactly like in the reference (``bincount(...)[:hist_n]``)."""
     hist_n = int(np.ceil(4 / 3 * np.pi * (search_radius / voxel_size + 1) ** 3))
     hists = np.zeros((num_stages, hist_n), dtype=np.int64)
     max_limits = [hist_n] * num_stages
-    for scan in scans:
-        d = scans_collate_fn_stack_mode([scan], num_stages, voxel_size, search_radius, max_limits,
-                                        pre_voxel=pre_voxel, int32=True, upsampling=False, device=device)
+    for i in range(len(dataset)):
+        d = collate_fn([dataset[i]], num_stages, voxel_size, search_radius, max_limits, precompute_data=True)
         counts = [(nb < nb.shape[0]).sum(1).cpu().numpy() for nb in d['neighbors']]
         hists += np.stack([np.bincount(c, minlength=hist_n)[:hist_n] for c in counts])
         if np.min(np.sum(hists, axis=1)) > sample_threshold:
             break
     cum = np.cumsum(hists.T, axis=0)
     return [int(x) for x in np.sum(cum < (keep_ratio * cum[hist_n - 1, :]), axis=0)]
+
+
+def calibrate_neighbors_scans(scans, num_stages, voxel_size, search_radius, keep_ratio=0.8, sample_threshold=2000,
+                              pre_voxel=None, device='cuda', scans_per_sample=1):
+    """calibrate_neighbors_stack_mode for a plain list of raw scans: ``scans_per_sample`` consecutive scans form
+    one sample (2 = the reference's registration samples, a stacked pair), optional 0.3 m ``pre_voxel``."""
+    samples = [scans[i:i + scans_per_sample] for i in range(0, len(scans), scans_per_sample)]
+
+    def collate_fn(sample, num_stages, voxel_size, search_radius, limits, precompute_data=True):
+        return scans_collate_fn_stack_mode(sample[0], num_stages, voxel_size, search_radius, limits,
+                                           pre_voxel=pre_voxel, int32=True, upsampling=False, device=device)
+    return calibrate_neighbors_stack_mode(samples, collate_fn, num_stages, voxel_size, search_radius, keep_ratio,
+                                          sample_threshold)
+
+
+def build_dataloader_stack_mode(dataset, collate_fn, num_stages, voxel_size, search_radius, neighbor_limits,
+                                batch_size=1, num_workers=0, shuffle=False, drop_last=False, distributed=False,
+                                precompute_data=True, pin_memory=False):
+    """data.py:436-468 (+ utils/utils/torch.py:53-80).  ``num_workers`` must be 0 when ``precompute_data`` is set:
+    the pyramid is built by CUDA kernels in the main process (threading row)."""
+    from functools import partial
+    if precompute_data and num_workers != 0:
+        raise RuntimeError('the B200 collate builds the pyramid on the GPU in the main process: use num_workers=0 '
+                           '(or precompute_data=False in the workers)')
+    sampler = torch.utils.data.DistributedSampler(dataset) if distributed else None
+    return torch.utils.data.DataLoader(
+        dataset, batch_size=batch_size, num_workers=num_workers, shuffle=False if distributed else shuffle,
+        sampler=sampler, drop_last=drop_last, pin_memory=pin_memory,
+        collate_fn=partial(collate_fn, num_stages=num_stages, voxel_size=voxel_size, search_radius=search_radius,
+                           neighbor_limits=neighbor_limits, precompute_data=precompute_data))

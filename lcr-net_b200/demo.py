@@ -23,8 +23,8 @@ def load_scan(path):
 
 def run_pair(pos, anc, state_dict=None, pre_voxel=None, device='cuda'):
     """pos = reference scan, anc = source scan (estimated_transform maps anc -> pos)."""
-    limits = gdata.calibrate_neighbors_stack_mode([pos, anc], NUM_STAGES, VOXEL, RADIUS, pre_voxel=pre_voxel,
-                                                  device=device)
+    limits = gdata.calibrate_neighbors_scans([pos, anc], NUM_STAGES, VOXEL, RADIUS, pre_voxel=pre_voxel,
+                                             device=device, scans_per_sample=2)
     net = lcrnet.create_model(lcrnet.default_cfg(limits)).eval()
     sd = state_dict if state_dict is not None else checkpoint.random_state_dict('lcrnet', 7351)
     sd = {k[7:] if k.startswith('module.') else k: v for k, v in sd.items()}      # base_tester.py:115-119

@@ -35,6 +35,31 @@ def load_weights(path):
     return _strip_module(torch.load(path, map_location='cpu', weights_only=True)['model'])
 
 
+# parameters the inference forward never reads (LCRNet.py:60: only the training loss uses it)
+_UNUSED_AT_INFERENCE = ('proj_node_overlap_score.',)
+
+
+def _load_checked(net, state_dict, kind):
+    """``load_state_dict`` as base_tester.py:111-122 does it (strict=False, 'module.' stripped), but a checkpoint
+    that leaves parameters of the inference path uninitialised is an ERROR here: this package zero-initialises
+    its parameter holders, so a mismatched checkpoint would silently produce descriptors / poses from zero
+    weights.  ``state_dict=None`` selects seeded random weights (smoke runs) with a loud warning."""
+    import warnings
+    if state_dict is None:
+        warnings.warn('lcrnet_b200.infer: no checkpoint given -- running with SEEDED RANDOM weights '
+                      '(checkpoint.random_state_dict(%r, 7351)); outputs are not meaningful' % kind, stacklevel=3)
+        state_dict = checkpoint.random_state_dict(kind, 7351)
+    sd = _strip_module(state_dict)
+    own = net.state_dict()
+    res = net.load_state_dict({k: v for k, v in sd.items() if k in own}, strict=False)
+    missing = [k for k in res.missing_keys if not k.startswith(_UNUSED_AT_INFERENCE)
+               and not k.endswith('num_batches_tracked')]
+    if missing:
+        raise RuntimeError('checkpoint does not cover %d tensor(s) of the %s model (first: %s): refusing to run '
+                           'with uninitialised weights' % (len(missing), kind, ', '.join(missing[:5])))
+    return net
+
+
 def _scan_list(scans):
     """list of arrays / file names, or a directory of .bin / .npy files in frame order."""
     if isinstance(scans, str):
@@ -68,12 +93,10 @@ def generate_descriptors(scans, out_dir, seq, state_dict=None, batch_scans=32, p
     if pre_voxel is None:
         pre_voxel = VOXEL if scans and _needs_prevoxel(scans[0]) else 0
     net = model.create_model(model.default_cfg()).eval()
-    sd = state_dict if state_dict is not None else checkpoint.random_state_dict('global_descriptor', 7351)
-    net.load_state_dict({k: v for k, v in _strip_module(sd).items() if k in net.state_dict()}, strict=False)
-    net = net.to(device)
+    net = _load_checked(net, state_dict, 'global_descriptor').to(device)
     limits = neighbor_limits
     if limits is None:
-        limits = gdata.calibrate_neighbors_stack_mode([_load(s) for s in scans[:4]], NUM_STAGES, VOXEL, RADIUS,
+        limits = gdata.calibrate_neighbors_scans([_load(s) for s in scans[:4]], NUM_STAGES, VOXEL, RADIUS,
                                                       pre_voxel=pre_voxel or None, device=device)
     pipe = pipeline.DescriptorPipeline(net, limits, NUM_STAGES, VOXEL, RADIUS, pre_voxel=pre_voxel or None,
                                        n_streams=2, device=device)
@@ -113,12 +136,10 @@ def register_pairs(pairs, out_dir, seq_id, state_dict=None, pre_voxel=None, devi
     first = [_load(pairs[0][2]), _load(pairs[0][3])]
     if pre_voxel is None:
         pre_voxel = VOXEL if _needs_prevoxel(pairs[0][2]) else 0
-    limits = gdata.calibrate_neighbors_stack_mode(first, NUM_STAGES, VOXEL, RADIUS, pre_voxel=pre_voxel or None,
+    limits = gdata.calibrate_neighbors_scans(first, NUM_STAGES, VOXEL, RADIUS, pre_voxel=pre_voxel or None,
                                                   device=device)
     net = lcrnet.create_model(lcrnet.default_cfg(limits)).eval()
-    sd = state_dict if state_dict is not None else checkpoint.random_state_dict('lcrnet', 7351)
-    net.load_state_dict(_strip_module(sd), strict=False)
-    net = net.to(device)
+    net = _load_checked(net, state_dict, 'lcrnet').to(device)
     out = []
     for pos_idx, anc_idx, pos, anc in pairs:
         d = gdata.scans_collate_fn_stack_mode([_load(pos), _load(anc)], NUM_STAGES, VOXEL, RADIUS, limits,

@@ -30,7 +30,8 @@ class LinearT(nn.Linear):
     def packed(self):
         w = self.weight
         key = (w.data_ptr(), w._version, self.bias.data_ptr() if self.bias is not None else 0)
-        if self._cache is None or self._cache[0] != key:
+
+        def build():
             cout, cin = w.shape
             pi, po = (cin + 3) // 4 * 4, (cout + 3) // 4 * 4
             wt = torch.zeros((pi, po), dtype=torch.float32, device=w.device)
@@ -38,14 +39,25 @@ class LinearT(nn.Linear):
             b = torch.zeros(po, dtype=torch.float32, device=w.device)
             if self.bias is not None:
                 b[:cout] = self.bias.detach()
-            self._cache = (key, wt, b)
-        return self._cache[1], self._cache[2]
+            return wt, b
+        return ops.derived(self, '_cache', key, build)
+
+    def _tc(self):
+        return self.in_features % 32 == 0 and self.out_features % 4 == 0 and ops.use_tensor_cores()
 
     def run(self, x, relu=False):
-        if self.in_features % 32 == 0 and self.out_features % 4 == 0 and ops.use_tensor_cores():
+        if self._tc():
             return P.linear_tc(x, self.weight, self.bias, relu=relu)
         wt, b = self.packed()
         return P.linear_ex(x, wt, b, relu=relu)
+
+    def prepare_b200(self):
+        if not self.weight.is_cuda:
+            return
+        if self._tc():
+            ops.tf32_split(self.weight)
+        else:
+            self.packed()
 
 
 def _fused(linears):
@@ -69,9 +81,16 @@ class _MHA(nn.Module):
 
     def fused(self):
         key = tuple((l.weight.data_ptr(), l.weight._version) for l in (self.proj_q, self.proj_k, self.proj_v))
-        if self._qkv is None or self._qkv[0] != key:
-            self._qkv = (key, _fused([self.proj_q, self.proj_k, self.proj_v]), _fused([self.proj_k, self.proj_v]))
-        return self._qkv[1], self._qkv[2]
+        return ops.derived(self, '_qkv', key, lambda: (_fused([self.proj_q, self.proj_k, self.proj_v]),
+                                                       _fused([self.proj_k, self.proj_v])))
+
+    def prepare_b200(self):
+        if not self.proj_q.weight.is_cuda:
+            return
+        (w_qkv, _), (w_kv, _) = self.fused()
+        if ops.use_tensor_cores():
+            ops.tf32_split(w_qkv)
+            ops.tf32_split(w_kv)
 
 
 class _AttentionLayer(nn.Module):
@@ -410,7 +429,8 @@ class LCRNet(nn.Module):
                 'pos_node_corr_knn_points': pad3(s['pos_pf'])[s['pos_knn'].long()[ci.long()]],
                 'anc_node_corr_knn_points': pad3(s['anc_pf'])[s['anc_knn'].long()[cj.long()]],
                 'pos_node_corr_knn_masks': s['pkm'], 'anc_node_corr_knn_masks': s['akm'],
-                '_node_ot': node_ot, '_point_ot': ot}
+                '_node_ot': node_ot, '_point_ot': ot, '_corr_patch': corr['pair'][:n], '_corr_i': corr['i'][:n],
+                '_corr_j': corr['j'][:n]}
 
 
 def _pad4(w):

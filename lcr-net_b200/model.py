@@ -38,7 +38,8 @@ class KPConv(nn.Module):
         self._kp_host = None
 
     def kernel_points_host(self):
-        """CPU copy of the kernel points (kernel arguments of the sparse gather; cached)."""
+        """CPU copy of the kernel points (kernel arguments of the fast gather; cached; the device->host copy
+        is synchronous, so the value is complete when this returns)."""
         kp = self.kernel_points
         key = (kp.data_ptr(), kp._version)
         if self._kp_host is None or self._kp_host[0] != key:
@@ -46,12 +47,15 @@ class KPConv(nn.Module):
         return self._kp_host[1]
 
     def weights_nk(self):
-        """[c_out, 15 * c_in] copy of the weights for the tensor-core contraction (cached)."""
+        """[c_out, 15 * c_in] copy of the weights for the tensor-core contraction (cached, stream-safe)."""
         w = self.weights
-        key = (w.data_ptr(), w._version)
-        if self._w_nk is None or self._w_nk[0] != key:
-            self._w_nk = (key, w.detach().reshape(-1, w.shape[2]).t().contiguous())
-        return self._w_nk[1]
+        return ops.derived(self, '_w_nk', (w.data_ptr(), w._version),
+                           lambda: w.detach().reshape(-1, w.shape[2]).t().contiguous())
+
+    def prepare_b200(self):
+        self.kernel_points_host()
+        if self.in_channels > 1 and self.weights.is_cuda and ops.use_tensor_cores():
+            ops.tf32_split(self.weights_nk())
 
     def forward(self, s_feats, q_points, s_points, neighbor_indices, s_flags=None, gn=None):
         """``gn`` = (stacks, eps, groups) of the GroupNorm that follows: returns (out, stats), the statistics
@@ -93,10 +97,13 @@ class UnaryBlock(nn.Module):
 
     def weight_t(self):
         w = self.mlp.weight
-        key = (w.data_ptr(), w._version)
-        if self._wt is None or self._wt[0] != key:
-            self._wt = (key, w.detach().t().contiguous())
-        return self._wt[1]
+        return ops.derived(self, '_wt', (w.data_ptr(), w._version), lambda: w.detach().t().contiguous())
+
+    def prepare_b200(self):
+        self.weight_t()
+        w = self.mlp.weight
+        if w.is_cuda and w.shape[1] % 32 == 0 and w.shape[0] % 4 == 0 and ops.use_tensor_cores():
+            ops.tf32_split(w)
 
     def linear(self, x):
         return ops.linear(x, self.weight_t(), self.mlp.bias, self.mlp.weight)
@@ -244,11 +251,12 @@ class NetVLADLoupe2(nn.Module):
         return torch.cat([bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var]).contiguous()
 
     def _bn_params(self):
-        key = tuple((b.weight.data_ptr(), b.weight._version, b.running_mean._version)
-                    for b in (self.bn1, self.bn2, self.context_gating.bn1))
-        if self._packed is None or self._packed[0] != key:
-            self._packed = (key, tuple(self._pack(b) for b in (self.bn1, self.bn2, self.context_gating.bn1)))
-        return self._packed[1]
+        bns = (self.bn1, self.bn2, self.context_gating.bn1)
+        key = tuple((b.weight.data_ptr(), b.weight._version, b.running_mean._version) for b in bns)
+        return ops.derived(self, '_packed', key, lambda: tuple(self._pack(b) for b in bns))
+
+    def prepare_b200(self):
+        self._bn_params()
 
     def forward(self, feats, scan_off, n_scans):
         """feats [rows, 1024] (un-normalised encoder output), scan_off int64 [n_scans+1] on device.

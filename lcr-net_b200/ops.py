@@ -34,13 +34,48 @@ def _f32c(t):
     return t
 
 
+class Derived:
+    """A tensor (or tuple of tensors) derived from model weights by kernels queued on the stream that was
+    current when it was built.  The pipelines run chunks on several CUDA streams from several host threads
+    and share these cached values: ``get()`` makes the consuming stream wait for the producing kernels
+    (a recorded event), so a second stream can never read halves that are still only queued."""
+
+    __slots__ = ('key', 'value', 'stream', 'event')
+
+    def __init__(self, key, value):
+        self.key, self.value = key, value
+        if torch.cuda.is_available():
+            self.stream = torch.cuda.current_stream()
+            self.event = torch.cuda.Event()
+            self.event.record(self.stream)
+        else:
+            self.stream = self.event = None
+
+    def get(self):
+        if self.event is not None:
+            cur = torch.cuda.current_stream()
+            if cur != self.stream:
+                cur.wait_event(self.event)
+        return self.value
+
+
+def derived(owner, slot, key, build):
+    """Cached ``build()`` on ``owner.<slot>``, rebuilt when ``key`` changes (weights reloaded / updated in place)."""
+    ent = getattr(owner, slot, None)
+    if ent is None or ent.key != key:
+        ent = Derived(key, build())
+        setattr(owner, slot, ent)
+    return ent.get()
+
+
 _SPLIT_CACHE = {}
 
 
 def tf32_split(weight):
     """(hi, lo) tf32 halves of a weight tensor for the 3xTF32 GEMM (lcr_tf32_split), cached per
     (storage, version): the cache entry keeps ``weight`` alive, so its address cannot be reused by
-    another tensor while the entry exists; an in-place update bumps the version and re-splits."""
+    another tensor while the entry exists; an in-place update bumps the version and re-splits.
+    The entry carries the event of its split kernel (see Derived): safe to share between streams."""
     key = (weight.data_ptr(), weight._version, tuple(weight.shape), tuple(weight.stride()))
     ent = _SPLIT_CACHE.get(key)
     if ent is None:
@@ -52,9 +87,23 @@ def tf32_split(weight):
         halves = torch.empty((2,) + tuple(wc.shape), dtype=torch.float32, device=w.device)
         _lib.check(_lib.lib().lcr_tf32_split(_lib.ptr(wc), wc.numel(), _lib.ptr(halves[0]), _lib.ptr(halves[1]),
                                              _lib.stream_ptr(w.device)))
-        ent = (weight, halves[0], halves[1])
+        ent = Derived(key, (weight, halves[0], halves[1]))
         _SPLIT_CACHE[key] = ent
-    return ent[1], ent[2]
+    v = ent.get()
+    return v[1], v[2]
+
+
+def prepare(net, sync=True):
+    """Builds every derived weight (transposes, packed BatchNorm parameters, fused QKV weights, tf32 halves)
+    of ``net`` once, on the current stream, then synchronises: called by the multi-stream pipelines before
+    the first chunk is queued so no stream ever builds -- or half-builds -- a cache entry another one reads."""
+    for m in net.modules():
+        fn = getattr(m, 'prepare_b200', None)
+        if fn is not None:
+            fn()
+    if sync and torch.cuda.is_available():
+        torch.cuda.current_stream().synchronize()
+    return net
 
 
 def _host_ptr(t):

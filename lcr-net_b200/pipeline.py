@@ -14,6 +14,21 @@ from concurrent.futures import ThreadPoolExecutor
 import torch
 
 from . import data as gdata
+from . import ops
+
+
+def _record_stream(obj, stream):
+    """Marks every tensor reachable from ``obj`` as in use on ``stream`` (torch's caching allocator then keeps
+    the block away from the side stream that allocated it until the consumer's queued work has run)."""
+    if torch.is_tensor(obj):
+        if obj.is_cuda:
+            obj.record_stream(stream)
+    elif isinstance(obj, dict):
+        for v in obj.values():
+            _record_stream(v, stream)
+    elif isinstance(obj, (list, tuple)):
+        for v in obj:
+            _record_stream(v, stream)
 
 
 class DescriptorPipeline:
@@ -31,6 +46,10 @@ class DescriptorPipeline:
         self.n_streams = max(1, int(n_streams))
         self.streams = [torch.cuda.Stream(self.device) for _ in range(self.n_streams)]
         self.pool = ThreadPoolExecutor(self.n_streams) if self.n_streams > 1 else None
+        # every derived weight is built once, here, and the device is synchronised: the chunks then only READ the
+        # caches (the entries also carry events, ops.Derived, should a weight be updated in place later)
+        with torch.cuda.device(self.device):
+            ops.prepare(net)
 
     def _chunk(self, points, lens, lo, hi, row_lo, row_hi, out, stream, ready):
         torch.cuda.set_device(self.device)
@@ -92,6 +111,8 @@ class PairPipeline:
         self.n_streams = max(1, int(n_streams))
         self.streams = [torch.cuda.Stream(self.device) for _ in range(self.n_streams)]
         self.pool = ThreadPoolExecutor(self.n_streams) if self.n_streams > 1 else None
+        with torch.cuda.device(self.device):
+            ops.prepare(net)
 
     def _chunk(self, points, lens, lo, hi, row_lo, row_hi, stream, ready):
         torch.cuda.set_device(self.device)
@@ -133,6 +154,7 @@ class PairPipeline:
         outs = []
         for o, e in res:
             main.wait_event(e)
+            _record_stream(o, main)       # allocated on a side stream, consumed by the caller on ``main``
             outs += o
         return outs
 

@@ -256,10 +256,10 @@ def fine_correspondences(log_scores, ref_masks, src_masks):
     return corr, s[:, :-1, :-1] * corr.float()
 
 
-def local_global_registration(ref_knn_points, src_knn_points, score_mat, corr_mat, radius=0.45, min_corr=3, steps=5):
-    """local_global_registration.py:140-202."""
-    b, i, j = torch.nonzero(corr_mat, as_tuple=True)
-    ref_c, src_c, sc = ref_knn_points[b, i], src_knn_points[b, j], score_mat[b, i, j]
+def lgr_from_lists(ref_c, src_c, sc, b, radius=0.45, min_corr=3, steps=5):
+    """local_global_registration.py:140-202 on flat correspondence lists; ``b`` = patch index of every
+    correspondence (non-decreasing): one weighted-Procrustes hypothesis per patch with >= min_corr entries, the
+    hypothesis with most inliers over ALL correspondences seeds ``steps`` rounds of inlier re-weighting."""
     bounds = [0] + (torch.nonzero(b[1:] != b[:-1])[:, 0] + 1).tolist() + [b.shape[0]]
     chunks = [(x, y) for x, y in zip(bounds[:-1], bounds[1:]) if y - x >= min_corr]
     if chunks:
@@ -279,7 +279,14 @@ def local_global_registration(ref_knn_points, src_knn_points, score_mat, corr_ma
     for _ in range(steps - 1):
         cur = sc * (torch.linalg.norm(ref_c - apply_transform(src_c, T), dim=1) < radius).float()
         T = weighted_procrustes(src_c, ref_c, cur)
-    return ref_c, src_c, sc, T
+    return T
+
+
+def local_global_registration(ref_knn_points, src_knn_points, score_mat, corr_mat, radius=0.45, min_corr=3, steps=5):
+    """local_global_registration.py:140-202."""
+    b, i, j = torch.nonzero(corr_mat, as_tuple=True)
+    ref_c, src_c, sc = ref_knn_points[b, i], src_knn_points[b, j], score_mat[b, i, j]
+    return ref_c, src_c, sc, lgr_from_lists(ref_c, src_c, sc, b, radius, min_corr, steps)
 
 
 # --------------------------------------------------------------------------- composition

@@ -271,3 +271,33 @@ def test_multistream_pipeline_matches_single_stream(net):
         assert np.abs(many.cpu().numpy() - one).max() <= 1e-6
     pipe.close()
     assert np.allclose(np.linalg.norm(one, axis=1), 1.0, atol=1e-5)
+
+
+def test_multistream_pipeline_cold_caches():
+    """ADVICE r1 (ops.py:40): derived weights (tf32 halves, transposes, packed BN) are shared between the
+    pipeline's streams.  A FRESH network enters the 3-stream pipeline first (nothing primed by a single-stream
+    pass), then its weights are replaced in place while the pipeline exists (every cache entry goes stale and is
+    rebuilt from whichever side stream touches it first, protected by the entry's event); both results must equal
+    the single-stream pass computed afterwards."""
+    from lcrnet_b200 import model, pipeline
+    scans = [np.ascontiguousarray(synth.make_scan(i // 2, 7351 + i)[::8]) for i in range(6)]
+    pts = torch.from_numpy(np.concatenate(scans, 0)).pin_memory()
+    lens = [len(s) for s in scans]
+    lim = [30, 30, 30, 30]
+    fresh = model.create_model(model.default_cfg()).eval()
+    fresh.load_state_dict(checkpoint.random_state_dict('global_descriptor', 11), strict=True)
+    fresh = fresh.cuda()
+    pipe = pipeline.DescriptorPipeline(fresh, lim, n_streams=3)
+    cold = pipe(pts, lens).cpu().numpy()                      # first use of this network at all
+    fresh.load_state_dict({k: v.cuda() for k, v in checkpoint.random_state_dict('global_descriptor', 12).items()},
+                          strict=True)                        # in-place copy: versions bump, caches stale
+    stale = pipe(pts, lens).cpu().numpy()                     # rebuilt on the fly from the side streams
+    pipe.close()
+    one = pipeline.DescriptorPipeline(fresh, lim, n_streams=1)
+    ref12 = one(pts, lens).cpu().numpy()
+    fresh.load_state_dict({k: v.cuda() for k, v in checkpoint.random_state_dict('global_descriptor', 11).items()},
+                          strict=True)
+    ref11 = one(pts, lens).cpu().numpy()
+    assert np.abs(cold - ref11).max() <= 1e-6
+    assert np.abs(stale - ref12).max() <= 1e-6
+    assert np.abs(ref11 - ref12).max() > 1e-3                 # the two weight sets really differ

@@ -115,18 +115,30 @@ def test_partition_vs_oracle(oracle_run):
     assert bool((dk[:, 1:] >= dk[:, :-1] - 1e-5).all())
 
 
-@pytest.mark.parametrize('b,m,n', [(1, 324, 312), (5, 128, 128), (3, 40, 57)])
-def test_sinkhorn_vs_oracle(b, m, n):
+@pytest.mark.parametrize('b,m,n,scale', [(1, 324, 312, 2.0), (5, 128, 128, 2.0), (3, 40, 57, 2.0),
+                                         (4, 128, 128, 8.0), (2, 370, 362, 8.0), (4, 128, 128, 25.0)])
+def test_sinkhorn_vs_oracle(b, m, n, scale):
+    """100 Sinkhorn iterations (learnable_sinkhorn.py:13-66) vs the oracle at 1e-4 absolute on the log scores
+    (SURVEY D.10 hook: 1e-5 relative to scores of magnitude ~10).  The kernel switches to linear-domain updates
+    after 4 log-domain iterations (matching.cu); ``scale`` 8 and 25 are the worst cases for that switch: score
+    ranges of +-30 .. +-100 make the absorbed plan K = exp(S + u + v) span the whole fp32 exponent range and
+    under-flow its small entries, 10 % of the rows / columns are masked."""
     from lcrnet_b200 import pair_ops as P
-    g = torch.Generator().manual_seed(m)
-    s = torch.randn(b, m, n, generator=g) * 2
+    g = torch.Generator().manual_seed(m + int(scale))
+    s = torch.randn(b, m, n, generator=g) * scale
     rm, cm = torch.rand(b, m, generator=g) > 0.1, torch.rand(b, n, generator=g) > 0.1
     alpha = torch.tensor(0.7)
     ref = po.sinkhorn(s, rm, cm, alpha)
+    ref64 = po.sinkhorn(s.double(), rm, cm, alpha.double())
     got = P.sinkhorn(c(s), rm.cuda(), cm.cuda(), alpha.cuda()).cpu()
     valid = ref > -1e11
     assert torch.equal(valid, got > -1e11)
-    assert float(((got - ref).abs() * valid).max()) < 1e-3
+    err = float(((got - ref).abs() * valid).max())
+    err64 = float(((got.double() - ref64).abs() * valid).max())
+    ora64 = float(((ref.double() - ref64).abs() * valid).max())
+    print('sinkhorn [%d x %d x %d, scale %g]: max abs error vs oracle %.2e, vs fp64 %.2e (oracle vs fp64 %.2e)' % (
+        b, m, n, scale, err, err64, ora64))
+    assert err < 1e-4 * max(1.0, scale / 2.0)
     # size-independent property: valid rows of exp(out) carry unit mass
     mass = torch.exp(got)[:, :m, :].sum(2)
     assert float((mass[rm] - 1).abs().max()) < 1e-3
