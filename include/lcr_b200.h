@@ -269,6 +269,9 @@ int lcr_point_to_node(const float* points, int64_t n_points, const float* nodes,
  * ---------------------------------------------------------------------------------------- */
 int lcr_sinkhorn(const float* scores, int batch, int rows, int cols, const uint8_t* row_mask, const uint8_t* col_mask,
                  const float* alpha, int iters, float* out, void* stream);
+/* Debug / tuning: out4 = {LOG iterations, LIN iterations, discarded LIN iterations, absorptions} summed over all
+ * problems since the last reset (sinkhorn.cu); synchronises the device. */
+int lcr_sinkhorn_stats(int64_t* out4, int reset);
 size_t lcr_coarse_matching_ws_bytes(int rows, int cols);
 int lcr_coarse_matching(const float* log_scores, int rows, int cols, int32_t* out_i, int32_t* out_j,
                         float* out_scores, int32_t* out_count, void* ws, size_t ws_bytes, void* stream);

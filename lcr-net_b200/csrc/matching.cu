@@ -135,267 +135,6 @@ node_topk_kernel(const unsigned long long* __restrict__ keys, const uint32_t* __
   }
 }
 
-// ================================================================== Sinkhorn
-// One CTA per problem.  S = padded score matrix [(M+1) x (N+1)] lives in `out` (global, L2
-// resident) or, when it fits, in shared memory; u, v, log_mu, log_nu in shared memory.
-struct SinkhornArgs {
-  const float* scores;       // [B, M, N]
-  const uint8_t* row_mask;   // [B, M] (1 = valid) or NULL
-  const uint8_t* col_mask;   // [B, N] or NULL
-  const float* alpha;        // device scalar
-  float* out;                // [B, M+1, N+1]
-  int M, N, iters;
-};
-
-// exp(x) on the SFU with a compensated argument: ex2.approx(x * log2e) loses |x| * 2^-24 in the
-// product; the FMA residual restores it, leaving the ~2 ulp of ex2.approx itself (the same order
-// as expf) at a quarter of the instructions.  Sinkhorn evaluates 2 * 129^2 * 100 of these per patch pair.
-__device__ __forceinline__ float sk_exp(float x) {
-  const float kL2E = 1.4426950408889634f, kL2E_lo = 1.925963033500011e-8f;
-  const float y = x * kL2E;
-  const float e = fmaf(x, kL2E_lo, fmaf(x, kL2E, -y));
-  float r;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(y));
-  return fmaf(r, e * 0.6931471805599453f, r);
-}
-
-template <bool kSmem>
-__global__ void __launch_bounds__(kSmem ? 512 : 1024) sinkhorn_kernel(SinkhornArgs a) {
-  extern __shared__ float sm[];
-  const int R = a.M + 1, C = a.N + 1;
-  float* u = sm;
-  float* v = u + R;
-  float* log_mu = v + C;
-  float* log_nu = log_mu + R;
-  float* u0 = log_nu + C;     // potentials saved at the switch to the linear domain
-  float* v0 = u0 + R;
-  float* S = kSmem ? v0 + C : a.out + (size_t)blockIdx.x * R * C;
-  __shared__ float s_norm;
-  __shared__ int s_cnt[2];
-  const int b = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
-  const int lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
-  const float inf = 1e12f;
-  const float alpha = *a.alpha;
-  const uint8_t* rm = a.row_mask ? a.row_mask + (size_t)b * a.M : nullptr;
-  const uint8_t* cm = a.col_mask ? a.col_mask + (size_t)b * a.N : nullptr;
-  if (tid < 2) s_cnt[tid] = 0;
-  __syncthreads();
-  int c0 = 0, c1 = 0;
-  for (int i = tid; i < a.M; i += nt) c0 += rm ? rm[i] : 1;
-  for (int j = tid; j < a.N; j += nt) c1 += cm ? cm[j] : 1;
-  c0 = lcr_warp_sum(c0);
-  c1 = lcr_warp_sum(c1);
-  if (lane == 0) {
-    atomicAdd(&s_cnt[0], c0);
-    atomicAdd(&s_cnt[1], c1);
-  }
-  __syncthreads();
-  const float nvr = (float)s_cnt[0], nvc = (float)s_cnt[1];
-  if (tid == 0) s_norm = -logf(nvr + nvc);
-  __syncthreads();
-  const float norm = s_norm;
-  for (int i = tid; i < R; i += nt) {
-    const bool masked = i < a.M && rm && !rm[i];
-    log_mu[i] = masked ? -inf : (i < a.M ? norm : logf(nvc) + norm);
-    u[i] = 0.f;
-  }
-  for (int j = tid; j < C; j += nt) {
-    const bool masked = j < a.N && cm && !cm[j];
-    log_nu[j] = masked ? -inf : (j < a.N ? norm : logf(nvr) + norm);
-    v[j] = 0.f;
-  }
-  const float* src = a.scores + (size_t)b * a.M * a.N;
-  for (int e = tid; e < R * C; e += nt) {
-    const int i = e / C, j = e % C;
-    float val = (i < a.M && j < a.N) ? src[(size_t)i * a.N + j] : alpha;
-    const bool masked = (i < a.M && rm && !rm[i]) || (j < a.N && cm && !cm[j]);
-    S[e] = masked ? -inf : val;
-  }
-  __syncthreads();
-  // The first kLogIters iterations run in the log domain exactly as written in the reference;
-  // the potentials are then absorbed, K = exp(S + u + v) (the current transport plan, entries
-  // <= ~1, masked entries exactly 0) replaces S (shared memory, or L2 for the node-level
-  // problem) and the remaining iterations are the same Sinkhorn updates in the linear domain,
-  //     a_i = mu_i / sum_j K_ij b_j ,  b_j = nu_j / sum_i K_ij a_i     (u += log a, v += log b),
-  // one FMA per matrix element instead of one exp.  a, b stay O(1), so there is no range problem.
-  constexpr int kLogIters = 4;
-  const int log_iters = min(a.iters, kLogIters);
-  for (int it = 0; it < log_iters; it++) {
-    if (kSmem) {
-      // matrix in shared memory: one THREAD per row / per column (no shuffle reductions; with the
-      // odd row length 129 both the row walk and the column walk are bank-conflict free)
-      for (int i = tid; i < R; i += nt) {
-        const float* row = S + (size_t)i * C;
-        float mx = -INFINITY;
-#pragma unroll 4
-        for (int j = 0; j < C; j++) mx = fmaxf(mx, row[j] + v[j]);
-        float sum = 0.f;
-#pragma unroll 4
-        for (int j = 0; j < C; j++) sum += sk_exp(row[j] + v[j] - mx);
-        u[i] = log_mu[i] - (mx + logf(sum));
-      }
-      __syncthreads();
-      for (int j = tid; j < C; j += nt) {
-        float mx = -INFINITY;
-#pragma unroll 4
-        for (int i = 0; i < R; i++) mx = fmaxf(mx, S[(size_t)i * C + j] + u[i]);
-        float sum = 0.f;
-#pragma unroll 4
-        for (int i = 0; i < R; i++) sum += sk_exp(S[(size_t)i * C + j] + u[i] - mx);
-        v[j] = log_nu[j] - (mx + logf(sum));
-      }
-      __syncthreads();
-      continue;
-    }
-    // u = log_mu - logsumexp_j(S + v)
-    for (int i = warp; i < R; i += nw) {
-      const float* row = S + (size_t)i * C;
-      float mx = -INFINITY;
-      for (int j = lane; j < C; j += 32) mx = fmaxf(mx, row[j] + v[j]);
-      mx = lcr_warp_max(mx);
-      float sum = 0.f;
-      for (int j = lane; j < C; j += 32) sum += sk_exp(row[j] + v[j] - mx);
-      sum = lcr_warp_sum(sum);
-      if (lane == 0) u[i] = log_mu[i] - (mx + logf(sum));
-    }
-    __syncthreads();
-    // v = log_nu - logsumexp_i(S + u)
-    if (kSmem) {
-      for (int j = warp; j < C; j += nw) {
-        float mx = -INFINITY;
-        for (int i = lane; i < R; i += 32) mx = fmaxf(mx, S[(size_t)i * C + j] + u[i]);
-        mx = lcr_warp_max(mx);
-        float sum = 0.f;
-        for (int i = lane; i < R; i += 32) sum += sk_exp(S[(size_t)i * C + j] + u[i] - mx);
-        sum = lcr_warp_sum(sum);
-        if (lane == 0) v[j] = log_nu[j] - (mx + logf(sum));
-      }
-    } else {
-      // matrix in L2: warp w owns a slab of rows, lanes stride the columns (coalesced row
-      // segments, independent columns -> ILP); per-slab (max, sum-exp) partials are combined
-      // per column through shared memory
-      float* part_m = v0 + C;
-      float* part_s = part_m + (size_t)nw * C;
-      const int rs = (R + nw - 1) / nw, r0 = warp * rs, r1 = min(r0 + rs, R);
-      for (int j = lane; j < C; j += 32) {
-        float mx = -INFINITY;
-        for (int i = r0; i < r1; i++) mx = fmaxf(mx, S[(size_t)i * C + j] + u[i]);
-        float sum = 0.f;
-        for (int i = r0; i < r1; i++) sum += sk_exp(S[(size_t)i * C + j] + u[i] - mx);
-        part_m[(size_t)warp * C + j] = mx;
-        part_s[(size_t)warp * C + j] = sum;
-      }
-      __syncthreads();
-      for (int j = tid; j < C; j += nt) {
-        float mx = -INFINITY;
-        for (int w = 0; w < nw; w++) mx = fmaxf(mx, part_m[(size_t)w * C + j]);
-        float sum = 0.f;
-        for (int w = 0; w < nw; w++) {
-          const float pm = part_m[(size_t)w * C + j];
-          if (pm > -INFINITY) sum += part_s[(size_t)w * C + j] * sk_exp(pm - mx);
-        }
-        v[j] = log_nu[j] - (mx + logf(sum));
-      }
-    }
-    __syncthreads();
-  }
-  if (a.iters > log_iters) {
-    // absorb: K = exp(S + u + v); mu, nu to the linear domain (masked rows / columns carry no mass)
-    for (int e = tid; e < R * C; e += nt) {
-      const int i = e / C, j = e % C;
-      S[e] = sk_exp(S[e] + u[i] + v[j]);
-    }
-    __syncthreads();
-    float* mu = log_mu;   // reused in place
-    float* nu = log_nu;
-    for (int i = tid; i < R; i += nt) {
-      mu[i] = log_mu[i] > -1e11f ? expf(log_mu[i]) : 0.f;
-      u0[i] = u[i];
-      u[i] = 1.f;         // a
-    }
-    for (int j = tid; j < C; j += nt) {
-      nu[j] = log_nu[j] > -1e11f ? expf(log_nu[j]) : 0.f;
-      v0[j] = v[j];
-      v[j] = 1.f;         // b
-    }
-    __syncthreads();
-    float* part = v0 + C + (kSmem ? 0 : 0);   // (global variant) per-warp column partials, after the vectors
-    for (int it = log_iters; it < a.iters; it++) {
-      if (kSmem) {
-        for (int i = tid; i < R; i += nt) {       // one thread per row
-          const float* row = S + (size_t)i * C;
-          float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-          int j = 0;
-          for (; j + 4 <= C; j += 4) {
-            s0 = fmaf(row[j], v[j], s0);
-            s1 = fmaf(row[j + 1], v[j + 1], s1);
-            s2 = fmaf(row[j + 2], v[j + 2], s2);
-            s3 = fmaf(row[j + 3], v[j + 3], s3);
-          }
-          for (; j < C; j++) s0 = fmaf(row[j], v[j], s0);
-          const float sum = (s0 + s1) + (s2 + s3);
-          u[i] = sum > 0.f ? mu[i] / sum : 0.f;
-        }
-        __syncthreads();
-        for (int j = tid; j < C; j += nt) {       // one thread per column
-          float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-          int i = 0;
-          for (; i + 4 <= R; i += 4) {
-            s0 = fmaf(S[(size_t)i * C + j], u[i], s0);
-            s1 = fmaf(S[(size_t)(i + 1) * C + j], u[i + 1], s1);
-            s2 = fmaf(S[(size_t)(i + 2) * C + j], u[i + 2], s2);
-            s3 = fmaf(S[(size_t)(i + 3) * C + j], u[i + 3], s3);
-          }
-          for (; i < R; i++) s0 = fmaf(S[(size_t)i * C + j], u[i], s0);
-          const float sum = (s0 + s1) + (s2 + s3);
-          v[j] = sum > 0.f ? nu[j] / sum : 0.f;
-        }
-        __syncthreads();
-      } else {
-        for (int i = warp; i < R; i += nw) {      // warp per row, coalesced
-          const float* row = S + (size_t)i * C;
-          float sum = 0.f;
-          for (int j = lane; j < C; j += 32) sum = fmaf(row[j], v[j], sum);
-          sum = lcr_warp_sum(sum);
-          if (lane == 0) u[i] = sum > 0.f ? mu[i] / sum : 0.f;
-        }
-        __syncthreads();
-        const int rs = (R + nw - 1) / nw, r0 = warp * rs, r1 = min(r0 + rs, R);
-        for (int j = lane; j < C; j += 32) {      // warp per row slab, lanes over columns
-          float sum = 0.f;
-          for (int i = r0; i < r1; i++) sum = fmaf(S[(size_t)i * C + j], u[i], sum);
-          part[(size_t)warp * C + j] = sum;
-        }
-        __syncthreads();
-        for (int j = tid; j < C; j += nt) {
-          float sum = 0.f;
-          for (int w = 0; w < nw; w++) sum += part[(size_t)w * C + j];
-          v[j] = sum > 0.f ? nu[j] / sum : 0.f;
-        }
-        __syncthreads();
-      }
-    }
-    // back to log potentials (masked rows / columns: the value is irrelevant, their entries stay -1e12)
-    for (int i = tid; i < R; i += nt) u[i] = u0[i] + (u[i] > 0.f ? logf(u[i]) : 0.f);
-    for (int j = tid; j < C; j += nt) v[j] = v0[j] + (v[j] > 0.f ? logf(v[j]) : 0.f);
-    __syncthreads();
-    // S was overwritten by K: rebuild the padded log scores from the input for the output
-    float* dst = a.out + (size_t)b * R * C;
-    for (int e = tid; e < R * C; e += nt) {
-      const int i = e / C, j = e % C;
-      const float val = (i < a.M && j < a.N) ? src[(size_t)i * a.N + j] : alpha;
-      const bool masked = (i < a.M && rm && !rm[i]) || (j < a.N && cm && !cm[j]);
-      dst[e] = (masked ? -inf : val) + u[i] + v[j] - norm;
-    }
-    return;
-  }
-  float* dst = a.out + (size_t)b * R * C;
-  for (int e = tid; e < R * C; e += nt) {
-    const int i = e / C, j = e % C;
-    dst[e] = S[e] + u[i] + v[j] - norm;
-  }
-}
-
 // ================================================================== coarse correspondences
 // log_scores [(M+1) x (N+1)]: (i,j) kept iff it is the column-argmax and beats the dustbin row, or
 // the row-argmax and beats the dustbin column (exp domain, strict >); listed row-major.
@@ -921,35 +660,6 @@ extern "C" int lcr_point_to_node(const float* points, int64_t n_points, const fl
   node_scatter_kernel<<<(N + 255) / 256, 256, 0, stream>>>(owner, d2, N, start, cursor, keys);
   node_topk_kernel<<<M, 256, 0, stream>>>(keys, start, N, k, idx_is64, knn_idx, knn_mask, out_status ? out_status : err);
   LCR_LAUNCHED(4);
-  LCR_CUDA_CHECK_LAUNCH();
-  return LCR_OK;
-}
-
-extern "C" int lcr_sinkhorn(const float* scores, int batch, int rows, int cols, const uint8_t* row_mask,
-                            const uint8_t* col_mask, const float* alpha, int iters, float* out, void* stream_) {
-  cudaStream_t stream = (cudaStream_t)stream_;
-  LCR_REQUIRE(batch >= 0 && rows >= 1 && cols >= 1 && iters >= 0, "sinkhorn: sizes");
-  if (batch == 0) return LCR_OK;
-  SinkhornArgs a{scores, row_mask, col_mask, alpha, out, rows, cols, iters};
-  const size_t vec = sizeof(float) * 3 * (size_t)(rows + 1 + cols + 1);
-  const size_t mat = sizeof(float) * (size_t)(rows + 1) * (cols + 1);
-  LCR_REQUIRE(vec <= 96 * 1024, "sinkhorn: problem too large");
-  LcrProfScope prof(rows == PK && cols == PK ? "sinkhorn_point" : "sinkhorn_node", 4.0 * batch * (double)(rows + 1) * (cols + 1) * iters,
-                    4.0 * batch * ((double)rows * cols + (double)(rows + 1) * (cols + 1)), stream);
-  if (vec + mat <= 200 * 1024) {
-    LCR_CUDA_TRY(cudaFuncSetAttribute(sinkhorn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)(vec + mat)));
-    int nt = ((rows > cols ? rows : cols) + 1 + 31) / 32 * 32;
-    nt = nt > 512 ? 512 : nt;
-    sinkhorn_kernel<true><<<batch, nt, vec + mat, stream>>>(a);
-  } else {
-    const size_t part = sizeof(float) * 2 * 32 * (size_t)(cols + 1);  // per-warp column partials (32 warps)
-    LCR_REQUIRE(vec + part <= 200 * 1024, "sinkhorn: problem too large");
-    LCR_CUDA_TRY(cudaFuncSetAttribute(sinkhorn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)(vec + part)));
-    sinkhorn_kernel<false><<<batch, 1024, vec + part, stream>>>(a);
-  }
-  LCR_LAUNCHED(1);
   LCR_CUDA_CHECK_LAUNCH();
   return LCR_OK;
 }

@@ -318,8 +318,8 @@ def lcrnet_forward(sd, data, limits, stages=False):
     pkm, akm = pos_km[ci], anc_km[cj]
     pkp, akp = pad(pos_pf)[pk], pad(anc_pf)[ak]
     pkf, akf = pad(pos_ff)[pk], pad(anc_ff)[ak]
-    ms = torch.einsum('bnd,bmd->bnm', pkf, akf) / feats_f.shape[1] ** 0.5
-    ms = sinkhorn(ms, pkm, akm, sd['optimal_transport.alpha'])
+    ms_raw = torch.einsum('bnd,bmd->bnm', pkf, akf) / feats_f.shape[1] ** 0.5
+    ms = sinkhorn(ms_raw, pkm, akm, sd['optimal_transport.alpha'])
     corr_mat, score_mat = fine_correspondences(ms, pkm, akm)
     ref_c, src_c, sc, T = local_global_registration(pkp, akp, score_mat, corr_mat)
     out.update({'estimated_transform': T, 'pos_corr_points': ref_c, 'anc_corr_points': src_c, 'corr_scores': sc,
@@ -330,5 +330,5 @@ def lcrnet_forward(sd, data, limits, stages=False):
     if stages:
         out['_stages'] = {'feats_c': fc, 'enhanced': enhanced, 'vote': vd, 'node_ot': node_ot, 'feats_f': feats_f,
                           'pos_knn': pos_knn, 'anc_knn': anc_knn, 'pos_node_masks': pos_nm, 'anc_node_masks': anc_nm,
-                          'point_ot': ms, 'corr_mat': corr_mat}
+                          'point_ot': ms, 'corr_mat': corr_mat, 'node_scores': node_scores[0], 'point_scores': ms_raw}
     return out

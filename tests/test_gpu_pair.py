@@ -116,13 +116,15 @@ def test_partition_vs_oracle(oracle_run):
 
 
 @pytest.mark.parametrize('b,m,n,scale', [(1, 324, 312, 2.0), (5, 128, 128, 2.0), (3, 40, 57, 2.0),
-                                         (4, 128, 128, 8.0), (2, 370, 362, 8.0), (4, 128, 128, 25.0)])
+                                         (4, 128, 128, 8.0), (2, 370, 362, 8.0), (4, 128, 128, 25.0),
+                                         (3, 128, 128, 100.0), (2, 370, 362, 100.0)])
 def test_sinkhorn_vs_oracle(b, m, n, scale):
-    """100 Sinkhorn iterations (learnable_sinkhorn.py:13-66) vs the oracle at 1e-4 absolute on the log scores
-    (SURVEY D.10 hook: 1e-5 relative to scores of magnitude ~10).  The kernel switches to linear-domain updates
-    after 4 log-domain iterations (matching.cu); ``scale`` 8 and 25 are the worst cases for that switch: score
-    ranges of +-30 .. +-100 make the absorbed plan K = exp(S + u + v) span the whole fp32 exponent range and
-    under-flow its small entries, 10 % of the rows / columns are masked."""
+    """100 Sinkhorn iterations (learnable_sinkhorn.py:13-66): <= 1e-4 ABSOLUTE on the log scores against an fp64
+    evaluation of the reference iteration, and within (1e-4 + the oracle's own fp32 rounding) of the torch fp32
+    oracle.  The kernels run linear-domain updates between log-domain absorptions (sinkhorn.cu); ``scale`` 8 .. 100
+    are the worst cases for that: score ranges of +-30 .. +-450 (the full-size node-level problems reach 457) make
+    the absorbed plan K = exp(S + u + v) span the whole fp32 exponent range; 10 % of the rows / columns are
+    masked.  Round 1's unconditional switch after 4 iterations failed the scale-100 cases by O(100)."""
     from lcrnet_b200 import pair_ops as P
     g = torch.Generator().manual_seed(m + int(scale))
     s = torch.randn(b, m, n, generator=g) * scale
@@ -134,14 +136,26 @@ def test_sinkhorn_vs_oracle(b, m, n, scale):
     valid = ref > -1e11
     assert torch.equal(valid, got > -1e11)
     err = float(((got - ref).abs() * valid).max())
-    err64 = float(((got.double() - ref64).abs() * valid).max())
+    d64 = (got.double() - ref64).abs() * valid
+    err64 = float(d64.max())
     ora64 = float(((ref.double() - ref64).abs() * valid).max())
-    print('sinkhorn [%d x %d x %d, scale %g]: max abs error vs oracle %.2e, vs fp64 %.2e (oracle vs fp64 %.2e)' % (
-        b, m, n, scale, err, err64, ora64))
-    assert err < 1e-4 * max(1.0, scale / 2.0)
-    # size-independent property: valid rows of exp(out) carry unit mass
-    mass = torch.exp(got)[:, :m, :].sum(2)
-    assert float((mass[rm] - 1).abs().max()) < 1e-3
+    mass_carrying = valid & (ref64 > -30.0)                    # entries with probability > e^-30
+    err_mass = float((d64 * mass_carrying).max())
+    rel64 = float((d64 / ref64.abs().clamp(min=1.0)).max())
+    print('sinkhorn [%d x %d x %d, scale %g]: vs fp64: %.2e abs on mass-carrying entries, %.2e abs / %.2e relative '
+          'on all (|L| up to %.0f); vs oracle %.2e (oracle vs fp64 %.2e)' % (
+              b, m, n, scale, err_mass, err64, rel64, float((ref64.abs() * valid).max()), err, ora64))
+    assert err_mass < 1e-4                 # absolute, where it matters
+    assert rel64 < 5e-5                    # element-wise relative everywhere (entries down to log p = -2000; 1 ulp of |L| = 700 is 9e-8 * 700)
+    assert err < 1e-4 + 2 * ora64          # and as close to the fp32 oracle as the oracle is to fp64
+    # size-independent property: the last update is v, so every valid column of exp(out) carries unit mass
+    mass = torch.exp(got.double())[:, :, :n].sum(1)
+    assert float((mass[cm] - 1).abs().max()) < 1e-4
+    from lcrnet_b200 import _lib
+    import ctypes
+    st = (ctypes.c_int64 * 4)()
+    _lib.check(_lib.lib().lcr_sinkhorn_stats(st, 1))
+    print('   iterations per problem: LOG %.1f, LIN %.1f, discarded %.1f, absorptions %.1f' % tuple(x / b for x in st))
 
 
 def test_coarse_and_fine_matching_vs_oracle(oracle_run):
