@@ -1,23 +1,31 @@
 #!/usr/bin/env python
-"""bench.py -- scan-pairs/sec of the LCR-Net descriptor hot path on B200.
+"""bench.py -- scan-pairs/sec of the LCR-Net hot path on B200: ONE JSON line that carries every
+BASELINE.json configuration.
 
-Workload (BASELINE.json configs[1], "single-scan encoder+global-descriptor forward, 64k
-synthetic pts"): every step processes a batch of P = 32 scan pairs (2P synthetic 65 536-point
-KITTI-shaped scans) through raw points -> 0.3 m voxel pre-pass -> 3-level voxel pyramid ->
-7 radius-neighbour tables -> 11-block KPConv encoder -> NetVLAD descriptor, one descriptor per
-scan, plus the squared-L2 descriptor distance of every pair (the loop-detection score).
+Headline (BASELINE.json configs[1], "single-scan encoder+global-descriptor forward, 64k synthetic pts", the
+configuration the tier contract names for N = 1): every step processes a batch of P = 32 scan pairs (2P synthetic
+65 536-point KITTI-shaped scans) through raw points -> 0.3 m voxel pre-pass -> 3-level voxel pyramid -> 7
+radius-neighbour tables -> 11-block KPConv encoder -> NetVLAD descriptor, one descriptor per scan, plus the
+squared-L2 descriptor distance of every pair (the loop-detection score).
 
-  value : pairs/s with the raw scans already resident in HBM (CUDA events, L2 flushed
-          between timed steps, max over ranks).
-  e2e   : the same through the public API from pinned HOST buffers (H2D of the raw scans and
-          D2H of descriptors + distances inside the timed region).
+  value : pairs/s with the raw scans already resident in HBM (CUDA events, L2 flushed between timed steps, max
+          over ranks).
+  e2e   : the same through the public API from pinned HOST buffers (H2D of the raw scans and D2H of
+          descriptors + distances inside the timed region).
   roofline / cpu_baseline : see DESIGN.md "Measurement".
 
-Launch: `python bench.py --gpus 1` or
-`python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N` (weak scaling: every
-rank runs its own P pairs, no data-path collective: independent units).
-`--impl reference` times the CPU path (reference C++ operators from oracle/_ref when shipped +
-the torch-CPU oracle port of the model) on the host cores.
+In the same line, under ``workloads`` (each with its own value / e2e / ms_per_step / gpu_launches / roofline):
+  pairs : configs[2], full registration (SURVEY 8d "raw points in -> descriptors + pose out"): LCRNet forward of
+          32 pairs per step (encoder, 3D-RoFormer, vote, Sinkhorn matching, LGR) -> pairs/s.
+  db    : configs[3] at N = 1, configs[4]-shaped at N > 1: every rank builds the descriptors of its contiguous
+          shard of 4000 scans, ONE NCCL all-gather assembles the database, every rank answers its own queries
+          with the brute-force L2 top-25 kernel -> scans/s, all_gather_ms, topk_ms.
+and under ``parity`` the in-run errors against the CPU oracle on one sample (descriptor relative L2, pose).
+
+Launch: `python bench.py --gpus 1` or `python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N`
+(weak scaling: every rank runs its own batch; the only data-path collective is the db workload's all-gather).
+`--workload descriptor|pairs|db` runs one of them alone (ncu captures).  `--impl reference` times the CPU path
+(reference C++ operators from oracle/_ref when shipped + the torch-CPU oracle port of the model) on the host cores.
 """
 import argparse
 import json
@@ -48,10 +56,12 @@ def parse():
     ap.add_argument('--ncu', action='store_true', help='one warm-up step + one step only (for ncu captures)')
     ap.add_argument('--streams', type=int, default=2,
                     help='descriptor workload: chunks of the batch in flight on separate CUDA streams (pipeline.py)')
-    ap.add_argument('--workload', default='descriptor', choices=['descriptor', 'db', 'pairs'],
-                    help='descriptor: the headline line (configs[1]); db: descriptor-database build + all-gather + '
-                         'top-25 (configs[3]/[4]); pairs: full registration of scan pairs (configs[2])')
+    ap.add_argument('--workload', default='all', choices=['all', 'descriptor', 'db', 'pairs'],
+                    help='all: the headline (configs[1]) with the pairs and db workloads as sub-records; or one of '
+                         'them alone: descriptor (configs[1]); db: descriptor-database build + all-gather + top-25 '
+                         '(configs[3]/[4]); pairs: full registration of scan pairs (configs[2])')
     ap.add_argument('--db-scans', type=int, default=4000, help='db workload: scans per GPU')
+    ap.add_argument('--no-parity', action='store_true', help='skip the in-run oracle comparison (about 20 s of CPU)')
     return ap.parse_args()
 
 
@@ -109,13 +119,15 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- CPU path
-def cpu_pair_pipeline(scans, sd, limits, use_ref_ops):
-    """The reference's CPU path on the same scans: collate (C++ operators) + torch-CPU model."""
+def cpu_pair_pipeline(scans, sd, limits, use_ref_ops, split=None):
+    """The reference's CPU path on the same scans: collate (C++ operators) + torch-CPU model.
+    ``split``: optional dict accumulating the seconds spent in 'collate' and 'model'."""
     import torch
     from oracle import model_oracle as mo
     from oracle import native as on
     descs = []
     for s in scans:
+        t0 = time.perf_counter()
         lens = np.array([len(s)], dtype=np.int64)
         if use_ref_ops:
             p0, l0 = on.ref_grid_subsample(s, lens, VOXEL)
@@ -137,8 +149,12 @@ def cpu_pair_pipeline(scans, sd, limits, use_ref_ops):
         else:
             p0, l0 = on.grid_subsample(s, lens, VOXEL)
             data = mo.precompute_pyramid(p0, l0, NUM_STAGES, VOXEL, RADIUS, limits)
+        t1 = time.perf_counter()
         with torch.no_grad():
             descs.append(mo.global_descriptor(sd, data))
+        if split is not None:
+            split['collate'] = split.get('collate', 0.0) + t1 - t0
+            split['model'] = split.get('model', 0.0) + time.perf_counter() - t1
     d = torch.cat(descs)
     return d, ((d[0::2] - d[1::2]) ** 2).sum(1)
 
@@ -152,15 +168,36 @@ def time_cpu(scans, sd, limits, steps=1, warmup=0):
     use_ref = on.ref_lib() is not None
     for _ in range(warmup):
         cpu_pair_pipeline(scans, sd, limits, use_ref)
+    split = {}
     t0 = time.perf_counter()
     for _ in range(steps):
-        cpu_pair_pipeline(scans, sd, limits, use_ref)
+        cpu_pair_pipeline(scans, sd, limits, use_ref, split)
     dt = (time.perf_counter() - t0) / steps
     n_pairs = len(scans) // 2
     kind_ops = 'reference C++ operators (oracle/_ref)' if use_ref else 'C oracle operators'
     return {'value': n_pairs / dt, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+            'collate_s_per_pair': split['collate'] / steps / n_pairs, 'model_s_per_pair': split['model'] / steps / n_pairs,
+            '_model_s_per_pair': split['model'] / steps / n_pairs,
             'sample': '%d pair(s) = %d scans of 65536 pts per step; collate single-threaded (%s), model = torch-CPU '
                       'oracle port with %d threads; %.2f s per step' % (n_pairs, len(scans), kind_ops, cores, dt)}, dt
+
+
+def add_collate_workers(base, scans, limits):
+    """8-process collate figure (mirrors ``num_workers=8``, config_reg.py:55) and the throughput of the
+    reference as deployed: 8 collate workers overlapped with the model process, bounded by the slower of the two."""
+    t_model = float(base.pop('_model_s_per_pair'))
+    try:
+        from oracle import collate_worker
+        col = collate_worker.collate_rate(scans, limits, processes=8)
+        base['collate_8_processes'] = col
+        if 'scans_per_s' in col:
+            base['pipelined_8_workers_pairs_per_s'] = 1.0 / max(2.0 / col['scans_per_s'], t_model)
+            base['note'] = ('value = the measured serial run (collate, then model: what one process does); '
+                            'pipelined_8_workers_pairs_per_s = min(8-process collate rate / 2, model rate), both rates '
+                            'measured in this run')
+    except Exception as e:                                      # the baseline is a reported number, never fatal
+        base['collate_8_processes'] = {'error': repr(e)}
+    return base
 
 
 def run_reference(args):
@@ -172,6 +209,7 @@ def run_reference(args):
     scans = make_scans(args.cpu_pairs)
     limits = calibrated_limits_cpu(scans[:2])
     base, dt = time_cpu(scans, sd, limits, steps=max(1, args.steps), warmup=min(args.warmup, 1))
+    add_collate_workers(base, make_scans(8)[:16], limits)
     line = {'impl': 'reference', 'metric': METRIC, 'value': base['value'], 'unit': UNIT, 'n_gpus': args.gpus,
             'steps': args.steps, 'warmup': min(args.warmup, 1), 'ms_per_step': dt * 1e3, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
@@ -199,59 +237,42 @@ def workload_config(pairs, limits, streams=1):
 
 
 # ----------------------------------------------------------------------------- GPU path
-def run_b200(args):
-    import torch
-    import torch.distributed as dist
-    from lcrnet_b200 import _lib, checkpoint, model
-    from lcrnet_b200 import data as gdata
-    world = int(os.environ.get('WORLD_SIZE', '1'))
-    rank = int(os.environ.get('RANK', '0'))
-    local = int(os.environ.get('LOCAL_RANK', '0'))
-    torch.cuda.set_device(local)
-    dev = torch.device('cuda', local)
-    if world > 1:
-        dist.init_process_group('nccl', device_id=dev)
-    L = _lib.lib()
-    net = model.create_model(model.default_cfg()).eval()
-    sd = checkpoint.random_state_dict('global_descriptor', 7351)
-    net.load_state_dict(sd, strict=True)
-    net = net.to(dev)
+class Ctx:
+    """Process / device context of one rank (one process per GPU)."""
 
-    scans = make_scans(args.pairs, rank)
-    limits = gdata.calibrate_neighbors_scans(scans[:2], NUM_STAGES, VOXEL, RADIUS, pre_voxel=VOXEL, device=dev)
-    host_pts = torch.from_numpy(np.concatenate(scans, 0)).pin_memory()
-    host_len = torch.tensor([len(s) for s in scans], dtype=torch.int64).pin_memory()
-    dev_pts, dev_len = host_pts.to(dev), host_len.to(dev)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    out_desc = torch.empty((2 * args.pairs, 256), dtype=torch.float32).pin_memory()
-    out_dist = torch.empty(args.pairs, dtype=torch.float32).pin_memory()
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.world = int(os.environ.get('WORLD_SIZE', '1'))
+        self.rank = int(os.environ.get('RANK', '0'))
+        self.local = int(os.environ.get('LOCAL_RANK', '0'))
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device('cuda', self.local)
+        if self.world > 1:
+            dist.init_process_group('nccl', device_id=self.dev)
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=self.dev)     # > 126 MB L2
+        from lcrnet_b200 import _lib
+        self.L = _lib.lib()
 
-    from lcrnet_b200 import pipeline
-    lens_list = host_len.tolist()
-    pipe1 = pipeline.DescriptorPipeline(net, limits, NUM_STAGES, VOXEL, RADIUS, pre_voxel=VOXEL, n_streams=1)
-    pipe = pipe1 if args.streams <= 1 or args.ncu else pipeline.DescriptorPipeline(
-        net, limits, NUM_STAGES, VOXEL, RADIUS, pre_voxel=VOXEL, n_streams=args.streams)
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
 
-    def step(points, lengths, p=None):
-        desc = (p or pipe)(points, lens_list)
-        diff = desc[0::2] - desc[1::2]
-        return desc, (diff * diff).sum(1)
+    def max_over_ranks(self, *vals):
+        if self.world == 1:
+            return list(vals)
+        t = self.torch.tensor(list(vals), dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return t.tolist()
 
-    def step_e2e():
-        desc, dd = step(host_pts, None)           # every chunk copies its own slice of the pinned host buffer
-        out_desc.copy_(desc, non_blocking=True)
-        out_dist.copy_(dd, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn, steps):
+    def timed(self, fn, steps):
+        """CUDA events around every step on the launching stream, L2 flushed before each."""
+        torch = self.torch
         evs = []
         for _ in range(steps):
-            flush.fill_(1)
+            self.flush.fill_(1)
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
             fn()
@@ -260,126 +281,115 @@ def run_b200(args):
         torch.cuda.synchronize()
         return [a.elapsed_time(b) for a, b in evs]
 
-    if args.ncu:
-        step(dev_pts, dev_len)
-        torch.cuda.synchronize()
-        step(dev_pts, dev_len)
-        torch.cuda.synchronize()
-        return
-    for _ in range(max(args.warmup, 3)):
-        step(dev_pts, dev_len)
-        step_e2e()
-    barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
-    if sampler:
-        sampler.start()
-    n0 = L.lcr_launch_count()
-    barrier()
-    ms = timed(lambda: step(dev_pts, dev_len), args.steps)
-    barrier()
-    launches = (L.lcr_launch_count() - n0) // args.steps
-    ms_e2e = timed(step_e2e, args.steps)
-    barrier()
-    clocks = sampler.stop() if sampler else None
-
-    total, total_e2e = sum(ms), sum(ms_e2e)
-    if world > 1:
-        t = torch.tensor([total, total_e2e], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total, total_e2e = t.tolist()
-    pairs_all = args.pairs * world * args.steps
-    value = pairs_all / (total * 1e-3)
-    e2e_value = pairs_all / (total_e2e * 1e-3)
-
-    # parity spot check of the benchmarked configuration is in tests/; here only sanity
-    desc, dd = step(dev_pts, dev_len)
-    assert torch.isfinite(desc).all() and abs(float(desc.norm(dim=1).mean()) - 1.0) < 1e-4
-
-    # per-kernel event timing needs the launches serialised: the single-stream pipeline
-    roof = dominant_kernel_roofline(lambda a, b: step(a, b, pipe1), dev_pts, dev_len, flush) if rank == 0 else None
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-    line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
-            'warmup': max(args.warmup, 3), 'ms_per_step': total / args.steps, 'higher_is_better': True,
-            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': workload_config(args.pairs, limits, args.streams),
-            'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(host_pts.numel() * 4 + host_len.numel() * 8),
-                    'd2h_bytes_per_step': int(out_desc.numel() * 4 + out_dist.numel() * 4),
-                    'ms_per_step': total_e2e / args.steps},
-            'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roof}
-    if world == 1 and not args.no_cpu_baseline:
-        cpu_scans = scans[:2 * args.cpu_pairs]
-        base, _ = time_cpu(cpu_scans, sd, limits)
-        line['cpu_baseline'] = base
-    print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    def close(self):
+        if self.world > 1:
+            self.dist.destroy_process_group()
 
 
-def dominant_kernel_roofline(step, pts, lens, flush):
-    """Roofline entry for the dominant kernel of the step (the fp32 tile GEMM, gemm.cu, which
-    carries the KPConv contraction and the unary layers): algorithmic FLOPs of all its launches in
-    one step / their summed device time, measured live with CUDA events around every launch via
-    the library's own per-kernel timing hook.  See DESIGN.md "Measurement"."""
-    import torch
-    from lcrnet_b200 import _lib
-    peaks = {}
+def peaks():
     try:
-        peaks = json.load(open(os.path.join(REPO, 'MEASURED_PEAKS.json')))
+        return json.load(open(os.path.join(REPO, 'MEASURED_PEAKS.json'))), 'measured (MEASURED_PEAKS.json)'
     except Exception:
-        pass
-    L = _lib.lib()
-    if not hasattr(L, 'lcr_profile_begin'):
-        return None
-    L.lcr_profile_begin()
-    flush.fill_(1)
-    step(pts, lens)
-    torch.cuda.synchronize()
+        return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0}, 'fallback (B200_PROFILING.md)'
+
+
+def measure_tf32_peak(ctx):
+    """Dense TF32 tensor throughput measured like MEASURED_PEAKS.json's bf16 figure: cuBLAS (torch.matmul with
+    TF32 enabled) on 8192^3, best of 10 (burst) and back to back for ~2 s (sustained).  Used ONLY as the roofline
+    denominator of the tcgen05 kind::tf32 kernels; no library GEMM is on the hot path."""
+    torch = ctx.torch
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        n = 8192
+        a = torch.randn(n, n, device=ctx.dev)
+        b = torch.randn(n, n, device=ctx.dev)
+        for _ in range(3):
+            a @ b
+        torch.cuda.synchronize()
+        best = 1e9
+        for _ in range(10):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            a @ b
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        reps = max(8, int(2000.0 / best))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            a @ b
+        e1.record()
+        torch.cuda.synchronize()
+        fl = 2.0 * n ** 3
+        return {'tf32_tflops': fl / (best * 1e-3) / 1e12, 'tf32_tflops_sustained': fl * reps / (e0.elapsed_time(e1) * 1e-3) / 1e12,
+                'how': 'torch.matmul fp32 inputs with allow_tf32 (cuBLAS) 8192^3: best of 10 (burst), %d back to back '
+                       '(sustained)' % reps}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def kernel_profile(ctx, step):
+    """One extra step with the library's per-kernel-group event scopes on (single stream, serialised launches)."""
     import ctypes
+    L = ctx.L
+    L.lcr_profile_begin()
+    ctx.flush.fill_(1)
+    step()
+    ctx.torch.cuda.synchronize()
     n = L.lcr_profile_end()
-    rows = []
+    agg = {}
     for i in range(n):
         name = ctypes.create_string_buffer(64)
         ms, flops, bytes_ = ctypes.c_double(), ctypes.c_double(), ctypes.c_double()
         L.lcr_profile_get(i, name, 64, ctypes.byref(ms), ctypes.byref(flops), ctypes.byref(bytes_))
-        rows.append((name.value.decode(), ms.value, flops.value, bytes_.value))
-    agg = {}
-    for name, ms, fl, by in rows:
-        a = agg.setdefault(name, [0.0, 0.0, 0.0, 0])
-        a[0] += ms
-        a[1] += fl
-        a[2] += by
+        a = agg.setdefault(name.value.decode(), [0.0, 0.0, 0.0, 0])
+        a[0] += ms.value
+        a[1] += flops.value
+        a[2] += bytes_.value
         a[3] += 1
+    return agg
+
+
+def roofline_from_profile(agg, tf32=None):
+    """Roofline entry of the dominant kernel group of a step: algorithmic flops / bytes of all its launches in one
+    step over their summed event-timed duration (DESIGN.md "Measurement")."""
     if not agg:
         return None
-    leaf = {k: v for k, v in agg.items() if not k.endswith('_total')}
+    pk, src = peaks()
     nested = ('radius_query', 'netvlad_hidden')          # already inside a *_total group
+    leaf = {k: v for k, v in agg.items() if not k.endswith('_total')}
     total_ms = sum(v[0] for k, v in agg.items() if k not in nested)
-    top = max(leaf.items(), key=lambda kv: kv[1][0])
-    name, (ms, fl, by, cnt) = top
-    hbm_peak = peaks.get('hbm_gbs', 6650.0)
-    tens_peak = peaks.get('bf16_tflops', 1590.0)
-    src = 'measured (MEASURED_PEAKS.json)' if peaks else 'fallback (B200_PROFILING.md)'
+    name, (ms, fl, by, cnt) = max(leaf.items(), key=lambda kv: kv[1][0])
     groups = {k: {'ms': round(v[0], 4), 'launches': v[3], 'share': round(v[0] / total_ms, 4),
                   'gflops': round(v[1] / 1e9, 3), 'mbytes': round(v[2] / 1e6, 3)} for k, v in agg.items()}
     traffic, traffic_src = ncu_traffic(name, cnt)
+    common = {'kernel': name, 'traffic': traffic, 'traffic_source': traffic_src, 'peak_source': src,
+              'launches_per_step': cnt, 'ms_per_step': ms, 'share_of_step': ms / total_ms, 'kernel_groups': groups}
     if fl > 0 and name.startswith('gemm'):
         ach = fl / (ms * 1e-3) / 1e12
-        note = ('achieved = fp32-equivalent algorithmic flops (2MNK) of all launches of the group in one step / their '
-                'summed event-timed duration; peak = dense bf16 tensor peak.  The tcgen05 kernel issues 3 TF32 MMAs per '
-                'fp32 product (3xTF32 split, DESIGN.md 5) and TF32 runs at half the bf16 rate, so the tensor pipe sees '
-                '6x this fraction' if name == 'gemm_tf32x3' else
-                'fp32 SIMT GEMM; fraction is against the dense bf16 tensor peak')
-        return {'kernel': name, 'bound': 'tensor', 'achieved': ach, 'peak': tens_peak, 'unit': 'TFLOP/s',
-                'frac': ach / tens_peak, 'traffic': traffic, 'traffic_source': traffic_src, 'peak_source': src,
-                'note': note, 'tf32_mma_tflops': 3 * ach if name == 'gemm_tf32x3' else None,
-                'launches_per_step': cnt, 'ms_per_step': ms, 'share_of_step': ms / total_ms, 'kernel_groups': groups}
+        out = dict(common, bound='tensor', achieved=ach, peak=pk['bf16_tflops'], unit='TFLOP/s', frac=ach / pk['bf16_tflops'],
+                   note='achieved = fp32-equivalent algorithmic flops (2MNK) of all launches of the group in one step / '
+                        'their summed event-timed duration; peak = measured dense bf16 tensor peak.  The tcgen05 kernel '
+                        'issues 3 kind::tf32 MMAs per fp32 product (3xTF32 split, DESIGN.md 5): tf32_mma_tflops = 3 x '
+                        'achieved is the rate the tensor pipe actually sustains, frac_of_tf32_peak compares it with the '
+                        'TF32 peak measured in this run')
+        if name == 'gemm_tf32x3':
+            out['tf32_mma_tflops'] = 3 * ach
+            if tf32:
+                out['tf32_peak_tflops'] = tf32['tf32_tflops']
+                out['tf32_peak_tflops_sustained'] = tf32['tf32_tflops_sustained']
+                out['tf32_peak_how'] = tf32['how']
+                out['frac_of_tf32_peak'] = 3 * ach / tf32['tf32_tflops']
+        return out
+    if fl > 0 and by <= 0:
+        ach = fl / (ms * 1e-3) / 1e12
+        fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12           # FFMA issue: 148 SMs x 128 lanes x 2 flop x 1.965 GHz
+        return dict(common, bound='fp32-issue', achieved=ach, peak=fp32_peak, unit='TFLOP/s', frac=ach / fp32_peak,
+                    note='latency / issue-bound SIMT kernel: algorithmic multiply-adds over the FFMA issue peak')
     ach = by / (ms * 1e-3) / 1e9
-    return {'kernel': name, 'bound': 'hbm', 'achieved': ach, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': ach / hbm_peak,
-            'traffic': traffic, 'traffic_source': traffic_src, 'peak_source': src, 'launches_per_step': cnt,
-            'ms_per_step': ms, 'share_of_step': ms / total_ms, 'kernel_groups': groups}
+    return dict(common, bound='hbm', achieved=ach, peak=pk['hbm_gbs'], unit='GB/s', frac=ach / pk['hbm_gbs'])
 
 
 def ncu_traffic(group, launches):
@@ -397,142 +407,342 @@ def ncu_traffic(group, launches):
     return None, None
 
 
-def run_db(args):
-    """configs[3]/[4]: every rank builds the descriptors of its contiguous shard of `db_scans`
-    scans (a pool of 64 distinct synthetic scans cycled with a small per-batch offset: descriptor cost
-    does not depend on the content; batches of 64 scans through the 2-stream DescriptorPipeline), ONE
-    all-gather assembles the database, then each rank answers its own shard's queries with the
-    brute-force L2 top-25 kernel.  One step = the whole build + search."""
-    import torch
-    import torch.distributed as dist
-    from lcrnet_b200 import _lib, checkpoint, model, retrieval
-    from lcrnet_b200 import data as gdata
-    world = int(os.environ.get('WORLD_SIZE', '1'))
-    rank = int(os.environ.get('RANK', '0'))
-    local = int(os.environ.get('LOCAL_RANK', '0'))
-    torch.cuda.set_device(local)
-    dev = torch.device('cuda', local)
-    if world > 1:
-        dist.init_process_group('nccl', device_id=dev)
+class Inputs:
+    """The synthetic scans of this rank: pinned host copy and HBM-resident copy."""
+
+    def __init__(self, ctx, n_pairs):
+        torch = ctx.torch
+        from lcrnet_b200 import data as gdata
+        self.scans = make_scans(n_pairs, ctx.rank)
+        # the reference calibrates on collated SAMPLES (data.py:408-433): a registration sample is a stacked pair
+        self.limits = gdata.calibrate_neighbors_scans(self.scans[:2], NUM_STAGES, VOXEL, RADIUS, pre_voxel=VOXEL,
+                                                      device=ctx.dev, scans_per_sample=2)
+        self.host_pts = torch.from_numpy(np.concatenate(self.scans, 0)).pin_memory()
+        self.lens = [len(s) for s in self.scans]
+        self.dev_pts = self.host_pts.to(ctx.dev)
+        self.h2d_bytes = int(self.host_pts.numel() * 4 + len(self.lens) * 8)
+
+
+def bench_descriptor(ctx, args, inp):
+    """configs[1]: the headline record."""
+    torch = ctx.torch
+    from lcrnet_b200 import checkpoint, model, pipeline
     net = model.create_model(model.default_cfg()).eval()
-    net.load_state_dict(checkpoint.random_state_dict('global_descriptor', 7351), strict=True)
-    net = net.to(dev)
-    from lcrnet_b200 import pipeline
-    pool = make_scans(32, rank)
-    limits = gdata.calibrate_neighbors_scans(pool[:2], NUM_STAGES, VOXEL, RADIUS, pre_voxel=VOXEL, device=dev)
-    pts = torch.from_numpy(np.concatenate(pool, 0)).to(dev)
-    lens_list = [len(s) for s in pool]
-    n_local, batch = args.db_scans, len(pool)
-    jitter = torch.linspace(0.0, 0.05, steps=(n_local + batch - 1) // batch, device=dev)
-    pipe = pipeline.DescriptorPipeline(net, limits, NUM_STAGES, VOXEL, RADIUS, pre_voxel=VOXEL, n_streams=args.streams)
+    sd = checkpoint.random_state_dict('global_descriptor', 7351)
+    net.load_state_dict(sd, strict=True)
+    net = net.to(ctx.dev)
+    n_scans = len(inp.lens)
+    out_desc = torch.empty((n_scans, 256), dtype=torch.float32).pin_memory()
+    out_dist = torch.empty(n_scans // 2, dtype=torch.float32).pin_memory()
+    mk = lambda n: pipeline.DescriptorPipeline(net, inp.limits, NUM_STAGES, VOXEL, RADIUS, pre_voxel=VOXEL, n_streams=n)
+    pipe1 = mk(1)
+    pipe = pipe1 if args.streams <= 1 or args.ncu else mk(args.streams)
 
-    def step():
+    def step(points, p=None):
+        desc = (p or pipe)(points, inp.lens)
+        diff = desc[0::2] - desc[1::2]
+        return desc, (diff * diff).sum(1)
+
+    def step_e2e():
+        desc, dd = step(inp.host_pts)            # every chunk copies its own slice of the pinned host buffer
+        out_desc.copy_(desc, non_blocking=True)
+        out_dist.copy_(dd, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    if args.ncu:
+        for _ in range(2):
+            step(inp.dev_pts)
+            torch.cuda.synchronize()
+        return None
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
+        step(inp.dev_pts)
+        step_e2e()
+    ctx.barrier()
+    sampler = ClockSampler(ctx.local) if ctx.rank == 0 else None
+    if sampler:
+        sampler.start()
+    n0 = ctx.L.lcr_launch_count()
+    ctx.barrier()
+    ms = ctx.timed(lambda: step(inp.dev_pts), args.steps)
+    ctx.barrier()
+    launches = (ctx.L.lcr_launch_count() - n0) // args.steps
+    ms_e2e = ctx.timed(step_e2e, args.steps)
+    ctx.barrier()
+    clocks = sampler.stop() if sampler else None
+    total, total_e2e = ctx.max_over_ranks(sum(ms), sum(ms_e2e))
+    pairs_all = (n_scans // 2) * ctx.world * args.steps
+    desc, _ = step(inp.dev_pts)
+    assert torch.isfinite(desc).all() and abs(float(desc.norm(dim=1).mean()) - 1.0) < 1e-4
+    prof = kernel_profile(ctx, lambda: step(inp.dev_pts, pipe1)) if ctx.rank == 0 else None
+    return {'metric': METRIC, 'value': pairs_all / (total * 1e-3), 'unit': UNIT, 'n_gpus': ctx.world, 'steps': args.steps,
+            'warmup': warm, 'ms_per_step': total / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': workload_config(n_scans // 2, inp.limits, args.streams),
+            'e2e': {'value': pairs_all / (total_e2e * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': inp.h2d_bytes,
+                    'd2h_bytes_per_step': int(out_desc.numel() * 4 + out_dist.numel() * 4),
+                    'ms_per_step': total_e2e / args.steps},
+            'gpu_launches': int(launches), 'clocks': clocks, '_profile': prof, '_sd': sd, '_desc0': desc[:2].cpu()}
+
+
+def bench_pairs(ctx, args, inp):
+    """configs[2]: full registration (LCRNet forward: encoder, 3D-RoFormer, vote, matching, LGR + both descriptors) of
+    a batch of scan pairs per step -- SURVEY 8(d)'s "raw points in -> descriptors + pose out"."""
+    torch = ctx.torch
+    from lcrnet_b200 import checkpoint, lcrnet, pipeline
+    sd = checkpoint.random_state_dict('lcrnet', 7351)
+    net = lcrnet.create_model(lcrnet.default_cfg(inp.limits)).eval()
+    net.load_state_dict(sd, strict=True)
+    net = net.to(ctx.dev)
+    n_pairs = len(inp.lens) // 2
+    mk = lambda n: pipeline.PairPipeline(net, inp.limits, NUM_STAGES, VOXEL, RADIUS, pre_voxel=VOXEL, n_streams=n)
+    pipe1 = mk(1)
+    pipe = pipe1 if args.streams <= 1 or args.ncu else mk(args.streams)
+    out_T = torch.empty((n_pairs, 4, 4), dtype=torch.float32).pin_memory()
+    out_desc = torch.empty((2 * n_pairs, 256), dtype=torch.float32).pin_memory()
+    last = {}
+
+    def step(points, p=None):
+        outs = (p or pipe)(points, inp.lens)
+        T = torch.stack([o['estimated_transform'] for o in outs])
+        d = torch.cat([torch.cat([o['pos_feature_global'], o['anc_feature_global']]) for o in outs])
+        last['outs'] = outs
+        return T, d
+
+    def step_e2e():
+        T, d = step(inp.host_pts)
+        out_T.copy_(T, non_blocking=True)
+        out_desc.copy_(d, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    if args.ncu:
+        for _ in range(2):
+            step(inp.dev_pts)
+            torch.cuda.synchronize()
+        return None
+    steps = max(2, min(args.steps, 5))
+    warm = 3
+    for _ in range(warm):
+        step(inp.dev_pts)
+    step_e2e()
+    ctx.barrier()
+    n0 = ctx.L.lcr_launch_count()
+    ms = ctx.timed(lambda: step(inp.dev_pts), steps)
+    ctx.barrier()
+    launches = (ctx.L.lcr_launch_count() - n0) // steps
+    ms_e2e = ctx.timed(step_e2e, steps)
+    ctx.barrier()
+    total, total_e2e = ctx.max_over_ranks(sum(ms), sum(ms_e2e))
+    pairs_all = n_pairs * ctx.world * steps
+    T, d = step(inp.dev_pts)
+    n_corr = [int(o['corr_scores'].shape[0]) for o in last['outs']]
+    prof = kernel_profile(ctx, lambda: step(inp.dev_pts, pipe1)) if ctx.rank == 0 else None
+    rec = {'metric': 'registration_pairs_per_sec_64k', 'value': pairs_all / (total * 1e-3), 'unit': 'pairs/s',
+           'steps': steps, 'warmup': warm, 'ms_per_step': total / steps,
+           'config': {'workload': 'configs[2]: scan-pair registration (LCRNet full forward: descriptors + pose), batch '
+                                  '%d pairs of 65536-point scans per step per GPU' % n_pairs,
+                      'neighbor_limits': inp.limits, 'streams': args.streams, 'cache': 'L2 flushed between timed steps',
+                      'weights': 'seeded random: correspondences are not meaningful, the work is'},
+           'e2e': {'value': pairs_all / (total_e2e * 1e-3), 'unit': 'pairs/s', 'h2d_bytes_per_step': inp.h2d_bytes,
+                   'd2h_bytes_per_step': int(out_T.numel() * 4 + out_desc.numel() * 4), 'ms_per_step': total_e2e / steps},
+           'gpu_launches': int(launches), 'mean_correspondences': float(np.mean(n_corr)),
+           'finite': bool(torch.isfinite(T).all()), '_profile': prof, '_sd': sd,
+           '_pair0': {k: (last['outs'][0][k].cpu() if torch.is_tensor(last['outs'][0][k]) else last['outs'][0][k])
+                      for k in ('estimated_transform', 'pos_feature_global', 'anc_feature_global',
+                                'pos_node_corr_indices', 'anc_node_corr_indices')}}
+    return rec
+
+
+def bench_db(ctx, args, inp, desc_net):
+    """configs[3] (N = 1) / configs[4]-shaped (N > 1): every rank builds the descriptors of its contiguous shard of
+    `db_scans` scans (the rank's pool of distinct synthetic scans cycled with a small per-batch offset: descriptor
+    cost does not depend on the content; batches through the multi-stream DescriptorPipeline), ONE all-gather
+    assembles the database, then each rank answers its own shard's queries with the brute-force L2 top-25 kernel.
+    One step = the whole build + gather + search."""
+    torch = ctx.torch
+    from lcrnet_b200 import pipeline, retrieval
+    n_local, batch = args.db_scans, len(inp.lens)
+    n_batches = (n_local + batch - 1) // batch
+    jitter = torch.linspace(0.0, 0.05, steps=n_batches, device=ctx.dev)
+    pipe = pipeline.DescriptorPipeline(desc_net, inp.limits, NUM_STAGES, VOXEL, RADIUS, pre_voxel=VOXEL,
+                                       n_streams=1 if args.ncu else args.streams)
+    out_idx = torch.empty((n_local, 25), dtype=torch.int64).pin_memory()
+    out_d2 = torch.empty((n_local, 25), dtype=torch.float32).pin_memory()
+
+    def step(host=False):
         out = []
-        for b in range((n_local + batch - 1) // batch):
-            out.append(pipe(pts + jitter[b], lens_list))
+        for b in range(n_batches):
+            out.append(pipe(inp.host_pts if host else inp.dev_pts + jitter[b], inp.lens))
         local_db = torch.cat(out)[:n_local].contiguous()
-        ev = torch.cuda.Event(enable_timing=True)
-        ev.record()
+        e0 = torch.cuda.Event(enable_timing=True)
+        e0.record()
         db = retrieval.all_gather_descriptors(local_db)
-        ev2 = torch.cuda.Event(enable_timing=True)
-        ev2.record()
+        e1 = torch.cuda.Event(enable_timing=True)
+        e1.record()
         d2, idx = retrieval.search(local_db, db, k=25)
-        return db, idx, (ev, ev2)
+        e2 = torch.cuda.Event(enable_timing=True)
+        e2.record()
+        if host:
+            out_idx.copy_(idx, non_blocking=True)
+            out_d2.copy_(d2, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        return db, idx, (e0, e1, e2)
 
+    steps = max(1, min(args.steps, 2))
+    warm = 1
     step()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
+    ctx.barrier()
+    n0 = ctx.L.lcr_launch_count()
     times, gather_ms, search_ms = [], [], []
-    for _ in range(args.steps):
+    for _ in range(steps):
+        ctx.flush.fill_(1)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        db, idx, (g0, g1) = step()
+        db, idx, (e0, e1, e2) = step()
         b.record()
         torch.cuda.synchronize()
         times.append(a.elapsed_time(b))
-        gather_ms.append(g0.elapsed_time(g1))
-        search_ms.append(g1.elapsed_time(b))
-    # every query's nearest database row is itself (distance 0): index check across the gather
-    start, _ = retrieval.shard_range(n_local * world, rank, world)
-    ok = bool((idx[:, 0].cpu() == torch.arange(start, start + n_local)).float().mean() > 0.99)
-    total = sum(times)
-    if world > 1:
-        t = torch.tensor([total], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total = float(t)
-    if rank == 0:
-        n_all = n_local * world * args.steps
-        print(json.dumps({'metric': 'db_build_scans_per_sec', 'value': n_all / (total * 1e-3), 'unit': 'scans/s',
-                          'n_gpus': world, 'steps': args.steps, 'warmup': 1, 'ms_per_step': total / args.steps,
-                          'higher_is_better': True, 'scaling': 'weak', 'dtype': 'f32', 'data': 'synthetic',
-                          'config': {'workload': 'configs[%d]: %d-scan descriptor DB build sharded %d x B200, one '
-                                                 'all-gather, brute-force L2 top-25' % (3 if world == 1 else 4,
-                                                                                          n_local * world, world),
-                                     'scans_per_gpu': n_local, 'db_rows': n_local * world, 'k': 25},
-                          'all_gather_ms': float(np.mean(gather_ms)), 'topk_ms': float(np.mean(search_ms)),
-                          'all_gather_bytes': int(n_local * world * 256 * 4),
-                          'queries_per_sec': n_local * world / (float(np.mean(search_ms)) * 1e-3),
-                          'self_match_ok': ok}))
-    if world > 1:
-        dist.destroy_process_group()
-
-
-def run_pairs(args):
-    """configs[2]: full registration (LCRNet: encoder, 3D-RoFormer, vote, matching, LGR) of a batch of
-    scan pairs per step; pairs/s."""
-    import torch
-    from lcrnet_b200 import checkpoint, lcrnet
-    from lcrnet_b200 import data as gdata
-    dev = torch.device('cuda', int(os.environ.get('LOCAL_RANK', '0')))
-    torch.cuda.set_device(dev)
-    scans = make_scans(args.pairs)
-    limits = gdata.calibrate_neighbors_scans(scans[:2], NUM_STAGES, VOXEL, RADIUS, pre_voxel=VOXEL, device=dev)
-    net = lcrnet.create_model(lcrnet.default_cfg(limits)).eval()
-    net.load_state_dict(checkpoint.random_state_dict('lcrnet', 7351), strict=True)
-    net = net.to(dev)
-    pts = torch.from_numpy(np.concatenate(scans, 0)).to(dev)
-    lens = torch.tensor([len(s) for s in scans], dtype=torch.int64, device=dev)
-
-    from lcrnet_b200 import pipeline
-    lens_list = [len(s) for s in scans]
-    pipe = pipeline.PairPipeline(net, limits, NUM_STAGES, VOXEL, RADIUS, pre_voxel=VOXEL, n_streams=args.streams)
-    pipe1 = pipeline.PairPipeline(net, limits, NUM_STAGES, VOXEL, RADIUS, pre_voxel=VOXEL, n_streams=1)
-
-    def step(p=None):
-        return (p or pipe)(pts, lens_list)
-
-    for _ in range(max(1, min(args.warmup, 2))):
-        out = step()
+        gather_ms.append(e0.elapsed_time(e1))
+        search_ms.append(e1.elapsed_time(e2))
+    launches = (ctx.L.lcr_launch_count() - n0) // steps
+    ctx.barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    step(host=True)
+    b.record()
     torch.cuda.synchronize()
-    times = []
-    for _ in range(args.steps):
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        out = step()
-        b.record()
-        torch.cuda.synchronize()
-        times.append(a.elapsed_time(b))
-    roof = dominant_kernel_roofline(lambda p, l: step(pipe1), pts, lens, torch.empty(1 << 20, dtype=torch.uint8, device=dev))
-    T = torch.stack([o['estimated_transform'] for o in out])
-    n_corr = [int(o['corr_scores'].shape[0]) for o in out]
-    print(json.dumps({'metric': 'registration_pairs_per_sec', 'value': args.pairs * args.steps / (sum(times) * 1e-3),
-                      'unit': 'pairs/s', 'n_gpus': 1, 'steps': args.steps, 'ms_per_step': sum(times) / args.steps,
-                      'higher_is_better': True, 'dtype': 'f32', 'data': 'synthetic',
-                      'config': {'workload': 'configs[2]: scan-pair registration (LCRNet full forward), batch %d pairs'
-                                             % args.pairs, 'neighbor_limits': limits,
-                                 'weights': 'seeded random: correspondences are not meaningful', 'streams': args.streams},
-                      'mean_correspondences': float(np.mean(n_corr)), 'finite': bool(torch.isfinite(T).all()),
-                      'kernel_groups': roof['kernel_groups'] if roof else None}))
+    t_e2e = a.elapsed_time(b)
+    ctx.barrier()
+    # every query's nearest database row is itself (distance 0) at its GLOBAL index: checks the gather order
+    start, _ = retrieval.shard_range(n_local * ctx.world, ctx.rank, ctx.world)
+    ok = bool((idx[:, 0].cpu() == torch.arange(start, start + n_local)).float().mean() > 0.99)
+    other_rows_filled = bool(db.abs().sum(1).min() > 0)
+    total, t_e2e, g_ms, s_ms = ctx.max_over_ranks(sum(times), t_e2e, float(np.mean(gather_ms)), float(np.mean(search_ms)))
+    n_all = n_local * ctx.world
+    return {'metric': 'db_build_scans_per_sec', 'value': n_all * steps / (total * 1e-3), 'unit': 'scans/s', 'steps': steps,
+            'warmup': warm, 'ms_per_step': total / steps,
+            'config': {'workload': 'configs[%d]: %d-scan descriptor DB build sharded over %d x B200 (%d scans per GPU), one '
+                                   'NCCL all-gather, brute-force L2 top-25 of every rank\'s own queries'
+                                   % (3 if ctx.world == 1 else 4, n_all, ctx.world, n_local),
+                       'scans_per_gpu': n_local, 'db_rows': n_all, 'k': 25, 'batch_scans': batch, 'streams': args.streams},
+            'e2e': {'value': n_all / (t_e2e * 1e-3), 'unit': 'scans/s', 'h2d_bytes_per_step': inp.h2d_bytes * n_batches,
+                    'd2h_bytes_per_step': int(out_idx.numel() * 8 + out_d2.numel() * 4), 'ms_per_step': t_e2e, 'steps': 1},
+            'gpu_launches': int(launches), 'all_gather_ms': g_ms, 'topk_ms': s_ms,
+            'all_gather_bytes': int(n_all * 256 * 4), 'nccl_world_size': ctx.world,
+            'queries_per_sec': n_all / (s_ms * 1e-3), 'self_match_ok': ok, 'gathered_rows_nonzero': other_rows_filled}
+
+
+def parity_in_run(inp, desc_rec, pairs_rec):
+    """desc / pose errors of THIS run's outputs for the first pair against the CPU oracle ("plus
+    descriptor relative L2 error and pose error vs the oracle").  Also returns the CPU time of the oracle's
+    registration forward, the cpu baseline of the pairs workload."""
+    import torch
+    from oracle import model_oracle as mo
+    from oracle import native as on
+    from oracle import pair_oracle as po
+    ref, src = inp.scans[0], inp.scans[1]
+    out = {}
+    t0 = time.perf_counter()
+    p0, l0 = on.grid_subsample(np.concatenate([ref, src]), np.array([len(ref), len(src)], dtype=np.int64), VOXEL)
+    data = mo.precompute_pyramid(p0, l0, NUM_STAGES, VOXEL, RADIUS, inp.limits)
+    t_collate = time.perf_counter() - t0
+    if desc_rec is not None:
+        want = []
+        for s in (ref, src):
+            q0, m0 = on.grid_subsample(s, np.array([len(s)], dtype=np.int64), VOXEL)
+            with torch.no_grad():
+                want.append(mo.global_descriptor(desc_rec['_sd'], mo.precompute_pyramid(q0, m0, NUM_STAGES, VOXEL, RADIUS,
+                                                                                         inp.limits)))
+        want = torch.cat(want)
+        got = desc_rec['_desc0']
+        out['desc_rel_l2_err'] = float(((got - want).norm(dim=1) / want.norm(dim=1)).max())
+    if pairs_rec is not None:
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            o = po.lcrnet_forward(pairs_rec['_sd'], data, inp.limits)
+        t_fwd = time.perf_counter() - t0
+        g = pairs_rec['_pair0']
+        T, Tr = g['estimated_transform'], o['estimated_transform']
+        out['pose_err'] = float((T - Tr).abs().max()) / max(1.0, float(Tr.abs().max()))
+        out['pair_desc_rel_l2_err'] = max(float((g[k] - o[k]).norm() / o[k].norm())
+                                          for k in ('pos_feature_global', 'anc_feature_global'))
+        a = set(zip(g['pos_node_corr_indices'].tolist(), g['anc_node_corr_indices'].tolist()))
+        b = set(zip(o['pos_node_corr_indices'].tolist(), o['anc_node_corr_indices'].tolist()))
+        out['node_correspondence_jaccard'] = len(a & b) / max(1, len(a | b))
+        out['sample'] = 'pair 0 of the benchmarked batch (2 x 65536 points) vs oracle/pair_oracle.py + model_oracle.py'
+        out['_cpu_pairs'] = {'value': 1.0 / (t_collate + t_fwd), 'unit': 'pairs/s', 'cores': os.cpu_count() or 1,
+                             'kind': 'port', 'sample': '1 pair: collate %.2f s (C oracle operators, 1 thread) + torch-CPU '
+                             'registration forward %.2f s (%d threads)' % (t_collate, t_fwd, torch.get_num_threads())}
+    return out
+
+
+def strip_private(rec):
+    return None if rec is None else {k: v for k, v in rec.items() if not k.startswith('_')}
+
+
+def run_b200(args):
+    ctx = Ctx()
+    inp = Inputs(ctx, args.pairs)
+    which = args.workload
+    desc = pairs = db = None
+    desc_net = None
+    if which in ('all', 'descriptor', 'db'):
+        if which == 'db':
+            from lcrnet_b200 import checkpoint, model
+            desc_net = model.create_model(model.default_cfg()).eval()
+            desc_net.load_state_dict(checkpoint.random_state_dict('global_descriptor', 7351), strict=True)
+            desc_net = desc_net.to(ctx.dev)
+        else:
+            desc = bench_descriptor(ctx, args, inp)
+    if which in ('all', 'pairs'):
+        pairs = bench_pairs(ctx, args, inp)
+    if which in ('all', 'db'):
+        if desc_net is None:
+            from lcrnet_b200 import checkpoint, model
+            desc_net = model.create_model(model.default_cfg()).eval()
+            desc_net.load_state_dict(checkpoint.random_state_dict('global_descriptor', 7351), strict=True)
+            desc_net = desc_net.to(ctx.dev)
+        db = bench_db(ctx, args, inp, desc_net)
+    if args.ncu:
+        ctx.close()
+        return
+    tf32 = measure_tf32_peak(ctx) if ctx.rank == 0 else None
+    ctx.barrier()
+    ctx.close()
+    if ctx.rank != 0:
+        return
+    for rec in (desc, pairs):
+        if rec is not None:
+            rec['roofline'] = roofline_from_profile(rec.get('_profile'), tf32)
+    parity = None
+    if ctx.world == 1 and not args.no_parity and (desc or pairs):
+        parity = parity_in_run(inp, desc, pairs)
+        if pairs is not None and '_cpu_pairs' in parity:
+            pairs['cpu_baseline'] = parity.pop('_cpu_pairs')
+    if ctx.world == 1 and not args.no_cpu_baseline and desc is not None:
+        base, _ = time_cpu(inp.scans[:2 * args.cpu_pairs], desc['_sd'], inp.limits)
+        add_collate_workers(base, inp.scans[:16], inp.limits)
+        desc['cpu_baseline'] = base
+    if which == 'all':
+        line = strip_private(desc)
+        line['workloads'] = {'pairs': strip_private(pairs), 'db': strip_private(db)}
+    else:
+        line = strip_private(desc or pairs or db)
+        line.setdefault('n_gpus', ctx.world)
+        line.setdefault('higher_is_better', True)
+        line.setdefault('scaling', 'weak')
+        line.setdefault('dtype', 'f32')
+        line.setdefault('data', 'synthetic')
+    if parity is not None:
+        line['parity'] = parity
+    if tf32 is not None:
+        line['tf32_peak'] = tf32
+    print(json.dumps(line))
 
 
 if __name__ == '__main__':
     a = parse()
     if a.impl == 'reference':
         run_reference(a)
-    elif a.workload == 'db':
-        run_db(a)
-    elif a.workload == 'pairs':
-        run_pairs(a)
     else:
         run_b200(a)

@@ -303,6 +303,42 @@ int lcr_local_global_registration(const float* ref, const float* src, const floa
                                   int n_pairs, int64_t capacity, float radius, int min_corr, int steps, float* out_T,
                                   void* ws, size_t ws_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Batched forms of a10 / a12 / a13 and the node score product of LCRNet.py:196-199: every pair of a
+ * chunk in ONE set of launches.  Clouds are stacked (ref_0, src_0, ref_1, src_1, ...); `pts_off` /
+ * `node_off` are int64 device arrays of row offsets per cloud (n_clouds + 1 entries).
+ *   lcr_point_to_node_batched  pointcloud_partition.py:61-107 per cloud: owner = GLOBAL node row;
+ *       knn_global int32 [M, k] = global point rows (pad = n_points), knn_local int64 [M, k] = rows
+ *       local to the node's cloud (pad = points of that cloud: the reference's table; may be NULL)
+ *   lcr_node_scores            out[p, i, j] = <f[ref node i], f[src node j]> / sqrt(C) padded with
+ *       zeros to [n_pairs, m_max, n_max], plus the padded node masks (rows / columns of the Sinkhorn)
+ *   lcr_coarse_matching_batched  superpoint_matching.py:129-160 on [n_pairs, rows+1, cols+1] log
+ *       scores; outputs [n_pairs, rows + cols], counts [n_pairs]
+ *   lcr_gather_coarse          compacts them into one patch list (global + local node indices,
+ *       patch -> pair) given patch_off int32 [n_pairs + 1] (exclusive scan of the counts)
+ *   lcr_lgr_batched            local_global_registration.py:140-202 for all scan pairs: patches t own
+ *       correspondences [pair_off[t], pair_off[t+1]), scan pair s owns patches [patch_off[s],
+ *       patch_off[s+1]); out_T [n_scan_pairs, 4, 4]
+ * ---------------------------------------------------------------------------------------- */
+int lcr_point_to_node_batched(const float* points, int64_t n_points, const int64_t* pts_off, const float* nodes,
+                              int64_t n_nodes, const int64_t* node_off, int n_clouds, int64_t max_cloud_points,
+                              int64_t max_cloud_nodes, int k, int32_t* point_to_node, uint8_t* node_mask,
+                              int32_t* knn_global, int64_t* knn_local, uint8_t* knn_mask, int32_t* out_status, void* ws,
+                              size_t ws_bytes, void* stream);
+int lcr_node_scores(const float* feats, int channels, const int64_t* node_off, const uint8_t* node_mask, int n_pairs,
+                    int m_max, int n_max, float* out, uint8_t* row_mask, uint8_t* col_mask, void* stream);
+int lcr_coarse_matching_batched(const float* log_scores, int n_pairs, int rows, int cols, int32_t* out_i, int32_t* out_j,
+                                float* out_scores, int32_t* out_count, void* ws, size_t ws_bytes, void* stream);
+int lcr_gather_coarse(const int32_t* out_i, const int32_t* out_j, const float* out_scores, int capacity,
+                      const int32_t* patch_off, const int64_t* node_off, int n_pairs, int32_t* ci_global,
+                      int32_t* cj_global, int32_t* ci_local, int32_t* cj_local, float* scores, int32_t* patch_pair,
+                      void* stream);
+size_t lcr_lgr_batched_ws_bytes(int n_patches, int n_scan_pairs, int64_t capacity);
+int lcr_lgr_batched(const float* ref, const float* src, const float* scores, const int32_t* c_pair,
+                    const int32_t* pair_off, int n_patches, const int32_t* patch_pair, const int32_t* patch_off,
+                    int n_scan_pairs, int64_t capacity, float radius, int min_corr, int steps, float* out_T, void* ws,
+                    size_t ws_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

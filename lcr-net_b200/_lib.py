@@ -76,6 +76,14 @@ SIGNATURES = {
     'lcr_lgr_ws_bytes': (c_sz, [c_i32, c_i64]),
     'lcr_local_global_registration': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i64, c_f32, c_i32, c_i32, c_vp, c_vp,
                                               c_sz, c_vp]),
+    'lcr_point_to_node_batched': (c_i32, [c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_i32, c_i64, c_i64, c_i32, c_vp, c_vp, c_vp,
+                                          c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    'lcr_node_scores': (c_i32, [c_vp, c_i32, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp]),
+    'lcr_coarse_matching_batched': (c_i32, [c_vp, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    'lcr_gather_coarse': (c_i32, [c_vp, c_vp, c_vp, c_i32, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    'lcr_lgr_batched_ws_bytes': (c_sz, [c_i32, c_i32, c_i64]),
+    'lcr_lgr_batched': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_vp, c_i32, c_i64, c_f32, c_i32, c_i32, c_vp,
+                                c_vp, c_sz, c_vp]),
     'lcr_l2_topk': (c_i32, [c_vp, c_i64, c_vp, c_i64, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp]),
 }
 

@@ -144,6 +144,17 @@ coarse_match_kernel(const float* __restrict__ ls, int M, int N, int32_t* __restr
                     int32_t* __restrict__ row_best, int32_t* __restrict__ col_best, int32_t* __restrict__ row_cnt) {
   const int R = M + 1, C = N + 1;
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+  {  // one CTA per problem of a batch (capacity M + N outputs per problem)
+    const size_t b = blockIdx.x;
+    ls += b * R * C;
+    out_i += b * (M + N);
+    out_j += b * (M + N);
+    out_s += b * (M + N);
+    out_n += b;
+    row_best += b * R;
+    row_cnt += b * R;
+    col_best += b * C;
+  }
   // exp() is monotone, so arg-maxima are taken on exp(ls) exactly like the reference (ties: first)
   for (int i = warp; i < R; i += nw) {
     float best = -INFINITY;
@@ -566,10 +577,12 @@ __device__ __forceinline__ bool is_inlier(const float* T, const float* src, cons
 }
 
 // inlier count of every local transform over ALL correspondences; one CTA per segment
+// (batched: hypothesis s belongs to scan pair seg_pair[s], whose correspondences are [corr_off[sp], corr_off[sp+1]))
 __global__ void __launch_bounds__(256)
 inlier_count_kernel(const float* __restrict__ T, const int32_t* __restrict__ valid, const float* __restrict__ src,
                     const float* __restrict__ ref, const int32_t* __restrict__ n_total, float radius,
-                    int32_t* __restrict__ counts) {
+                    int32_t* __restrict__ counts, const int32_t* __restrict__ seg_pair,
+                    const int32_t* __restrict__ corr_off) {
   __shared__ int s_c[8];
   const int s = blockIdx.x;
   if (!valid[s]) {
@@ -578,8 +591,9 @@ inlier_count_kernel(const float* __restrict__ T, const int32_t* __restrict__ val
   }
   const float* Ts = T + (size_t)s * 16;
   int c = 0;
-  const int n = *n_total;
-  for (int t = threadIdx.x; t < n; t += 256) c += is_inlier(Ts, src, ref, t, radius);
+  const int sp = seg_pair ? seg_pair[s] : 0;
+  const int t_lo = corr_off ? corr_off[sp] : 0, n = corr_off ? corr_off[sp + 1] : *n_total;
+  for (int t = t_lo + threadIdx.x; t < n; t += 256) c += is_inlier(Ts, src, ref, t, radius);
   c = lcr_warp_sum(c);
   if ((threadIdx.x & 31) == 0) s_c[threadIdx.x >> 5] = c;
   __syncthreads();
@@ -591,11 +605,16 @@ inlier_count_kernel(const float* __restrict__ T, const int32_t* __restrict__ val
 }
 
 // best = first argmax of counts (>= 0); copies T[best] to T_cur, or flags "no local transform"
+// (batched: CTA b picks among the hypotheses [seg_off[b], seg_off[b+1]) of scan pair b)
 __global__ void pick_best_kernel(const int32_t* __restrict__ counts, int S, const float* __restrict__ T,
-                                 float* __restrict__ T_cur, int32_t* __restrict__ have_local) {
+                                 float* __restrict__ T_cur, int32_t* __restrict__ have_local,
+                                 const int32_t* __restrict__ seg_off) {
   __shared__ int s_best[32], s_idx[32];
   int best = -1, bi = 0x7fffffff;
-  for (int s = threadIdx.x; s < S; s += blockDim.x)
+  const int s_lo = seg_off ? seg_off[blockIdx.x] : 0, s_hi = seg_off ? seg_off[blockIdx.x + 1] : S;
+  T_cur += (size_t)blockIdx.x * 16;
+  have_local += blockIdx.x;
+  for (int s = s_lo + threadIdx.x; s < s_hi; s += blockDim.x)
     if (counts[s] > best) { best = counts[s]; bi = s; }
   for (int o = 16; o > 0; o >>= 1) {
     const int ob = __shfl_xor_sync(0xffffffffu, best, o), oi = __shfl_xor_sync(0xffffffffu, bi, o);
@@ -613,14 +632,182 @@ __global__ void pick_best_kernel(const int32_t* __restrict__ counts, int S, cons
 }
 
 // w_cur[t] = score[t] * inlier(T), T = (*select != 0) ? T_a : T_b   (select == NULL -> T_a)
+// (batched: correspondence t belongs to scan pair seg_pair[c_pair[t]]; T_a, T_b, select are indexed by scan pair)
 __global__ void reweight_kernel(const float* __restrict__ T_a, const float* __restrict__ T_b,
                                 const int32_t* __restrict__ select, const float* __restrict__ src,
                                 const float* __restrict__ ref, const float* __restrict__ score,
-                                const int32_t* __restrict__ n_total, float radius, float* __restrict__ w_cur) {
+                                const int32_t* __restrict__ n_total, float radius, float* __restrict__ w_cur,
+                                const int32_t* __restrict__ c_pair, const int32_t* __restrict__ seg_pair) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= *n_total) return;
-  const float* T = (!select || *select != 0) ? T_a : T_b;
+  const int sp = (c_pair && seg_pair) ? seg_pair[c_pair[t]] : 0;
+  const float* T = (!select || select[sp] != 0) ? T_a + (size_t)sp * 16 : T_b + (size_t)sp * 16;
   w_cur[t] = is_inlier(T, src, ref, t, radius) ? score[t] : 0.f;
+}
+
+
+// ================================================================== batched variants (all pairs of a chunk per launch)
+// owner of every point among the nodes of ITS cloud: grid (ceil(max cloud points / 256), clouds); owner indices
+// are GLOBAL node rows
+__global__ void __launch_bounds__(256)
+owner_batched_kernel(const float* __restrict__ pts, const int64_t* __restrict__ pts_off,
+                     const float* __restrict__ nodes, const int64_t* __restrict__ node_off,
+                     int32_t* __restrict__ owner, float* __restrict__ owner_d2, uint32_t* __restrict__ node_count) {
+  extern __shared__ float4 s_nodes[];  // x, y, z, |n|^2
+  const int b = blockIdx.y;
+  const int n0 = (int)pts_off[b], n1 = (int)pts_off[b + 1], m0 = (int)node_off[b], M = (int)node_off[b + 1] - m0;
+  if ((int)(blockIdx.x * blockDim.x) >= n1 - n0) return;
+  for (int i = threadIdx.x; i < M; i += blockDim.x) {
+    const float x = nodes[3 * (size_t)(m0 + i)], y = nodes[3 * (size_t)(m0 + i) + 1], z = nodes[3 * (size_t)(m0 + i) + 2];
+    s_nodes[i] = make_float4(x, y, z, x * x + y * y + z * z);
+  }
+  __syncthreads();
+  const int j = n0 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n1 || M <= 0) return;
+  const float px = pts[3 * (size_t)j], py = pts[3 * (size_t)j + 1], pz = pts[3 * (size_t)j + 2];
+  const float p2 = px * px + py * py + pz * pz;
+  float best = INFINITY;
+  int bi = 0;
+  for (int i = 0; i < M; i++) {
+    const float4 n = s_nodes[i];
+    const float xy = n.x * px + n.y * py + n.z * pz;
+    const float d = fmaxf(n.w - 2.f * xy + p2, 1e-12f);
+    if (d < best) {
+      best = d;
+      bi = i;
+    }
+  }
+  owner[j] = m0 + bi;
+  owner_d2[j] = best;
+  atomicAdd(&node_count[m0 + bi], 1u);
+}
+
+// one CTA per node (global row): sort its owned points by (d2, index), emit the first K as GLOBAL point rows (int32,
+// pad = n_total) and as rows LOCAL to the node's cloud (int64, pad = points of that cloud: the reference's table)
+__global__ void __launch_bounds__(256)
+node_topk_batched_kernel(const unsigned long long* __restrict__ keys, const uint32_t* __restrict__ node_start,
+                         int n_total, int K, const int64_t* __restrict__ pts_off, const int64_t* __restrict__ node_off,
+                         int n_clouds, int32_t* __restrict__ knn_global, int64_t* __restrict__ knn_local,
+                         uint8_t* __restrict__ knn_mask, int* __restrict__ err) {
+  __shared__ unsigned long long s[kNodeCap];
+  const int node = blockIdx.x;
+  const uint32_t st = node_start[node];
+  int cnt = (int)(node_start[node + 1] - st);
+  if (cnt > kNodeCap) {
+    if (threadIdx.x == 0) *err = LCR_ERR_OVERFLOW;
+    cnt = kNodeCap;
+  }
+  const int b = lcr_find_segment(node_off, n_clouds, (int64_t)node);
+  const int64_t p0 = pts_off[b], np = pts_off[b + 1] - p0;
+  int n = 32;
+  while (n < cnt) n <<= 1;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s[i] = i < cnt ? keys[st + i] : kEmptyKey;
+  __syncthreads();
+  for (int k = 2; k <= n; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const unsigned long long a = s[i], c = s[ixj];
+          if ((a > c) == ((i & k) == 0)) {
+            s[i] = c;
+            s[ixj] = a;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  for (int t = threadIdx.x; t < K; t += blockDim.x) {
+    const bool ok = t < cnt;
+    const int64_t g = ok ? (int64_t)(unsigned)(s[t] & 0xFFFFFFFFull) : (int64_t)n_total;
+    knn_global[(size_t)node * K + t] = (int32_t)g;
+    if (knn_local) knn_local[(size_t)node * K + t] = ok ? g - p0 : np;
+    knn_mask[(size_t)node * K + t] = ok;
+  }
+}
+
+// node score matrices of all pairs: out[p, i, j] = <f[node_off[2p] + i], f[node_off[2p+1] + j]> / sqrt(C), zero
+// outside the pair's m x n block (LCRNet.py:196-199), plus the padded row / column masks for the Sinkhorn
+constexpr int NS_T = 64, NS_K = 16;
+__global__ void __launch_bounds__(256)
+node_scores_kernel(const float* __restrict__ f, int C, const int64_t* __restrict__ node_off,
+                   const uint8_t* __restrict__ node_mask, int m_max, int n_max, float inv_div,
+                   float* __restrict__ out, uint8_t* __restrict__ row_mask, uint8_t* __restrict__ col_mask) {
+  __shared__ float sa[NS_K][NS_T + 4], sb[NS_K][NS_T + 4];
+  const int p = blockIdx.z, i0 = blockIdx.y * NS_T, j0 = blockIdx.x * NS_T, tid = threadIdx.x;
+  const int a0 = (int)node_off[2 * p], m = (int)node_off[2 * p + 1] - a0;
+  const int b0 = (int)node_off[2 * p + 1], n = (int)node_off[2 * p + 2] - b0;
+  if (blockIdx.x == 0)
+    for (int i = i0 + tid; i < min(i0 + NS_T, m_max); i += 256) row_mask[(size_t)p * m_max + i] = i < m ? node_mask[a0 + i] : 0;
+  if (blockIdx.y == 0)
+    for (int j = j0 + tid; j < min(j0 + NS_T, n_max); j += 256) col_mask[(size_t)p * n_max + j] = j < n ? node_mask[b0 + j] : 0;
+  const int tx = tid & 15, ty = tid >> 4;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) acc[i][j] = 0.f;
+  if (i0 < m && j0 < n) {
+    for (int c0 = 0; c0 < C; c0 += NS_K) {
+      for (int e = tid; e < NS_T * (NS_K / 4); e += 256) {
+        const int r = e / (NS_K / 4), c4 = e % (NS_K / 4);
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 va = i0 + r < m ? *reinterpret_cast<const float4*>(f + (size_t)(a0 + i0 + r) * C + c0 + 4 * c4) : z;
+        const float4 vb = j0 + r < n ? *reinterpret_cast<const float4*>(f + (size_t)(b0 + j0 + r) * C + c0 + 4 * c4) : z;
+        sa[4 * c4][r] = va.x; sa[4 * c4 + 1][r] = va.y; sa[4 * c4 + 2][r] = va.z; sa[4 * c4 + 3][r] = va.w;
+        sb[4 * c4][r] = vb.x; sb[4 * c4 + 1][r] = vb.y; sb[4 * c4 + 2][r] = vb.z; sb[4 * c4 + 3][r] = vb.w;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int c = 0; c < NS_K; c++) {
+        const float4 a4 = *reinterpret_cast<const float4*>(&sa[c][4 * ty]);
+        const float4 b4 = *reinterpret_cast<const float4*>(&sb[c][4 * tx]);
+        const float a[4] = {a4.x, a4.y, a4.z, a4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+          for (int j = 0; j < 4; j++) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+      }
+      __syncthreads();
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const int r = i0 + 4 * ty + i;
+    if (r >= m_max) continue;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int cidx = j0 + 4 * tx + j;
+      if (cidx < n_max) out[((size_t)p * m_max + r) * n_max + cidx] = (r < m && cidx < n) ? acc[i][j] * inv_div : 0.f;
+    }
+  }
+}
+
+// node correspondences of all pairs, compacted to one list of GLOBAL node rows: patch t in [patch_off[p],
+// patch_off[p+1]) is correspondence t - patch_off[p] of pair p
+__global__ void gather_coarse_kernel(const int32_t* __restrict__ out_i, const int32_t* __restrict__ out_j,
+                                     const float* __restrict__ out_s, int cap, const int32_t* __restrict__ patch_off,
+                                     const int64_t* __restrict__ node_off, int32_t* __restrict__ ci_g,
+                                     int32_t* __restrict__ cj_g, int32_t* __restrict__ ci_l, int32_t* __restrict__ cj_l,
+                                     float* __restrict__ cs, int32_t* __restrict__ patch_pair) {
+  const int p = blockIdx.x, t0 = patch_off[p], cnt = patch_off[p + 1] - t0;
+  const int a0 = (int)node_off[2 * p], b0 = (int)node_off[2 * p + 1];
+  for (int t = threadIdx.x; t < cnt; t += blockDim.x) {
+    const int i = out_i[(size_t)p * cap + t], j = out_j[(size_t)p * cap + t];
+    ci_g[t0 + t] = a0 + i;
+    cj_g[t0 + t] = b0 + j;
+    ci_l[t0 + t] = i;
+    cj_l[t0 + t] = j;
+    cs[t0 + t] = out_s[(size_t)p * cap + t];
+    patch_pair[t0 + t] = p;
+  }
+}
+
+// corr_off[s] = pair_off[patch_off[s]]: first correspondence of scan pair s
+__global__ void corr_offsets_kernel(const int32_t* __restrict__ pair_off, const int32_t* __restrict__ patch_off, int S,
+                                    int32_t* __restrict__ corr_off) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s <= S) corr_off[s] = pair_off[patch_off[s]];
 }
 
 }  // namespace
@@ -763,8 +950,8 @@ extern "C" int lcr_local_global_registration(const float* ref, const float* src,
   int launches = 0;
   if (n_pairs > 0) {
     procrustes_kernel<<<n_pairs, 256, 0, stream>>>(src, ref, scores, pair_off, n_corr, min_corr, T_local, valid);
-    inlier_count_kernel<<<n_pairs, 256, 0, stream>>>(T_local, valid, src, ref, n_corr, radius, counts);
-    pick_best_kernel<<<1, 1024, 0, stream>>>(counts, n_pairs, T_local, out_T, have_local);
+    inlier_count_kernel<<<n_pairs, 256, 0, stream>>>(T_local, valid, src, ref, n_corr, radius, counts, nullptr, nullptr);
+    pick_best_kernel<<<1, 1024, 0, stream>>>(counts, n_pairs, T_local, out_T, have_local, nullptr);
     launches += 3;
   }
   // degenerate branch (no patch with >= min_corr correspondences): start from all correspondences
@@ -772,13 +959,163 @@ extern "C" int lcr_local_global_registration(const float* ref, const float* src,
   float* T_deg = T_local + (size_t)n_pairs * 16;
   procrustes_kernel<<<1, 256, 0, stream>>>(src, ref, scores, nullptr, n_corr, 0, T_deg, nullptr);
   // w = score * inlier(have_local ? T_best : T_deg)
-  reweight_kernel<<<gridC, 256, 0, stream>>>(out_T, T_deg, have_local, src, ref, scores, n_corr, radius, w_cur);
+  reweight_kernel<<<gridC, 256, 0, stream>>>(out_T, T_deg, have_local, src, ref, scores, n_corr, radius, w_cur, nullptr,
+                                             nullptr);
   launches += 2;
   for (int it = 0; it < steps; it++) {
     procrustes_kernel<<<1, 256, 0, stream>>>(src, ref, w_cur, nullptr, n_corr, 0, out_T, nullptr);
     launches++;
     if (it + 1 < steps) {
-      reweight_kernel<<<gridC, 256, 0, stream>>>(out_T, nullptr, nullptr, src, ref, scores, n_corr, radius, w_cur);
+      reweight_kernel<<<gridC, 256, 0, stream>>>(out_T, nullptr, nullptr, src, ref, scores, n_corr, radius, w_cur,
+                                                 nullptr, nullptr);
+      launches++;
+    }
+  }
+  LCR_LAUNCHED(launches);
+  LCR_CUDA_CHECK_LAUNCH();
+  return LCR_OK;
+}
+
+// ================================================================== batched C ABI (all pairs of a chunk per call)
+extern "C" int lcr_point_to_node_batched(const float* points, int64_t n_points, const int64_t* pts_off,
+                                         const float* nodes, int64_t n_nodes, const int64_t* node_off, int n_clouds,
+                                         int64_t max_cloud_points, int64_t max_cloud_nodes, int k,
+                                         int32_t* point_to_node, uint8_t* node_mask, int32_t* knn_global,
+                                         int64_t* knn_local, uint8_t* knn_mask, int32_t* out_status, void* ws,
+                                         size_t ws_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  LCR_REQUIRE(n_points >= 1 && n_nodes >= 1 && n_points < (1ll << 31) && n_nodes < (1ll << 31) && n_clouds >= 1,
+              "point_to_node_batched: sizes");
+  LCR_REQUIRE(max_cloud_nodes >= 1 && max_cloud_nodes <= 12000, "point_to_node_batched: at most 12000 nodes per cloud");
+  LCR_REQUIRE(k >= 1 && k <= kNodeCap, "point_to_node_batched: k");
+  LCR_REQUIRE(points && pts_off && nodes && node_off && node_mask && knn_global && knn_mask, "point_to_node_batched: null");
+  LCR_REQUIRE(ws && ws_bytes >= lcr_point_to_node_ws_bytes(n_points, n_nodes), "point_to_node_batched: workspace too small");
+  const int N = (int)n_points, M = (int)n_nodes;
+  LcrArena a(ws, ws_bytes);
+  float* d2 = a.take<float>(N);
+  int32_t* owner_tmp = a.take<int32_t>(N);
+  unsigned long long* keys = a.take<unsigned long long>(N);
+  uint32_t* count = a.take<uint32_t>(M + 1);
+  uint32_t* start = a.take<uint32_t>(M + 1);
+  uint32_t* cursor = a.take<uint32_t>(M + 1);
+  int* err = (int*)a.take<int>(1);
+  int32_t* owner = point_to_node ? point_to_node : owner_tmp;
+  LcrProfScope prof("point_to_node", 8.0 * N * (double)max_cloud_nodes, 12.0 * (N + M) + 4.0 * N + 13.0 * M * k, stream);
+  LCR_CUDA_TRY(cudaMemsetAsync(count, 0, sizeof(uint32_t) * (M + 1), stream));
+  LCR_CUDA_TRY(cudaMemsetAsync(cursor, 0, sizeof(uint32_t) * (M + 1), stream));
+  if (out_status) LCR_CUDA_TRY(cudaMemsetAsync(out_status, 0, sizeof(int32_t), stream));
+  const size_t smem = sizeof(float4) * (size_t)max_cloud_nodes;
+  if (smem > 48 * 1024)
+    LCR_CUDA_TRY(cudaFuncSetAttribute(owner_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((unsigned)((max_cloud_points + 255) / 256), (unsigned)n_clouds);
+  owner_batched_kernel<<<grid, 256, smem, stream>>>(points, pts_off, nodes, node_off, owner, d2, count);
+  node_scan_kernel<<<1, 1024, 0, stream>>>(count, M, start, node_mask);
+  node_scatter_kernel<<<(N + 255) / 256, 256, 0, stream>>>(owner, d2, N, start, cursor, keys);
+  node_topk_batched_kernel<<<M, 256, 0, stream>>>(keys, start, N, k, pts_off, node_off, n_clouds, knn_global, knn_local,
+                                                  knn_mask, out_status ? out_status : err);
+  LCR_LAUNCHED(4);
+  LCR_CUDA_CHECK_LAUNCH();
+  return LCR_OK;
+}
+
+extern "C" int lcr_node_scores(const float* feats, int channels, const int64_t* node_off, const uint8_t* node_mask,
+                               int n_pairs, int m_max, int n_max, float* out, uint8_t* row_mask, uint8_t* col_mask,
+                               void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  LCR_REQUIRE(n_pairs >= 1 && m_max >= 1 && n_max >= 1 && channels % NS_K == 0, "node_scores: sizes");
+  LCR_REQUIRE(feats && node_off && node_mask && out && row_mask && col_mask, "node_scores: null");
+  LcrProfScope prof("node_scores", 2.0 * n_pairs * (double)m_max * n_max * channels,
+                    4.0 * n_pairs * ((double)(m_max + n_max) * channels + (double)m_max * n_max), stream);
+  dim3 grid((unsigned)((n_max + NS_T - 1) / NS_T), (unsigned)((m_max + NS_T - 1) / NS_T), (unsigned)n_pairs);
+  node_scores_kernel<<<grid, 256, 0, stream>>>(feats, channels, node_off, node_mask, m_max, n_max,
+                                               1.f / sqrtf((float)channels), out, row_mask, col_mask);
+  LCR_LAUNCHED(1);
+  LCR_CUDA_CHECK_LAUNCH();
+  return LCR_OK;
+}
+
+extern "C" int lcr_coarse_matching_batched(const float* log_scores, int n_pairs, int rows, int cols, int32_t* out_i,
+                                           int32_t* out_j, float* out_scores, int32_t* out_count, void* ws,
+                                           size_t ws_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  LCR_REQUIRE(n_pairs >= 1 && rows >= 1 && cols >= 1, "coarse_matching_batched: sizes");
+  const size_t per = (size_t)(rows + 1) * 2 + (size_t)(cols + 1);
+  LCR_REQUIRE(ws && ws_bytes >= sizeof(int32_t) * per * n_pairs + 1024, "coarse_matching_batched: workspace too small");
+  LcrArena a(ws, ws_bytes);
+  int32_t* row_best = a.take<int32_t>((size_t)(rows + 1) * n_pairs);
+  int32_t* row_cnt = a.take<int32_t>((size_t)(rows + 1) * n_pairs);
+  int32_t* col_best = a.take<int32_t>((size_t)(cols + 1) * n_pairs);
+  LcrProfScope prof("coarse_matching", 0.0, 12.0 * n_pairs * (double)(rows + 1) * (cols + 1), stream);
+  coarse_match_kernel<<<n_pairs, 1024, 0, stream>>>(log_scores, rows, cols, out_i, out_j, out_scores, out_count, row_best,
+                                                    col_best, row_cnt);
+  LCR_LAUNCHED(1);
+  LCR_CUDA_CHECK_LAUNCH();
+  return LCR_OK;
+}
+
+extern "C" int lcr_gather_coarse(const int32_t* out_i, const int32_t* out_j, const float* out_scores, int capacity,
+                                 const int32_t* patch_off, const int64_t* node_off, int n_pairs, int32_t* ci_global,
+                                 int32_t* cj_global, int32_t* ci_local, int32_t* cj_local, float* scores,
+                                 int32_t* patch_pair, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  LCR_REQUIRE(n_pairs >= 1 && capacity >= 1, "gather_coarse: sizes");
+  gather_coarse_kernel<<<n_pairs, 256, 0, stream>>>(out_i, out_j, out_scores, capacity, patch_off, node_off, ci_global,
+                                                    cj_global, ci_local, cj_local, scores, patch_pair);
+  LCR_LAUNCHED(1);
+  LCR_CUDA_CHECK_LAUNCH();
+  return LCR_OK;
+}
+
+extern "C" size_t lcr_lgr_batched_ws_bytes(int n_patches, int n_scan_pairs, int64_t capacity) {
+  return lcr_align_up((size_t)(n_patches + 1) * 16 * 4) + 2 * lcr_align_up((size_t)(n_patches + 1) * 4) +
+         lcr_align_up((size_t)(capacity > 0 ? capacity : 1) * 4) + 2 * lcr_align_up((size_t)(n_scan_pairs + 1) * 4) +
+         lcr_align_up((size_t)(n_scan_pairs + 1) * 16 * 4) + 1024;
+}
+
+// Local-to-global registration (local_global_registration.py:140-202) of MANY scan pairs in one set of launches.
+// ref / src / scores [capacity]: correspondences of all scan pairs, grouped by patch (node correspondence):
+// patch t owns [pair_off[t], pair_off[t+1]); c_pair[c] = patch of correspondence c; scan pair s owns the patches
+// [patch_off[s], patch_off[s+1]) (patch_pair[t] = s).  out_T [n_scan_pairs, 4, 4].
+extern "C" int lcr_lgr_batched(const float* ref, const float* src, const float* scores, const int32_t* c_pair,
+                               const int32_t* pair_off, int n_patches, const int32_t* patch_pair,
+                               const int32_t* patch_off, int n_scan_pairs, int64_t capacity, float radius, int min_corr,
+                               int steps, float* out_T, void* ws, size_t ws_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  LCR_REQUIRE(n_patches >= 0 && n_scan_pairs >= 1 && capacity >= 0 && steps >= 1, "lgr_batched: sizes");
+  LCR_REQUIRE(ws && ws_bytes >= lcr_lgr_batched_ws_bytes(n_patches, n_scan_pairs, capacity), "lgr_batched: workspace too small");
+  LcrArena a(ws, ws_bytes);
+  float* T_local = a.take<float>((size_t)(n_patches + 1) * 16);
+  int32_t* valid = a.take<int32_t>(n_patches + 1);
+  int32_t* counts = a.take<int32_t>(n_patches + 1);
+  float* w_cur = a.take<float>(capacity > 0 ? capacity : 1);
+  int32_t* have_local = a.take<int32_t>(n_scan_pairs + 1);
+  int32_t* corr_off = a.take<int32_t>(n_scan_pairs + 1);
+  float* T_deg = a.take<float>((size_t)(n_scan_pairs + 1) * 16);
+  const int32_t* n_corr = pair_off + n_patches;
+  const unsigned gridC = (unsigned)((capacity + 255) / 256) > 0 ? (unsigned)((capacity + 255) / 256) : 1u;
+  const int S = n_scan_pairs;
+  LcrProfScope prof("lgr", 0.0, 28.0 * capacity * (n_patches / (double)S + 2.0 * steps), stream);
+  LCR_CUDA_TRY(cudaMemsetAsync(have_local, 0, sizeof(int32_t) * (S + 1), stream));
+  int launches = 1;
+  corr_offsets_kernel<<<(S + 256) / 256, 256, 0, stream>>>(pair_off, patch_off, S, corr_off);
+  if (n_patches > 0) {
+    procrustes_kernel<<<n_patches, 256, 0, stream>>>(src, ref, scores, pair_off, n_corr, min_corr, T_local, valid);
+    inlier_count_kernel<<<n_patches, 256, 0, stream>>>(T_local, valid, src, ref, n_corr, radius, counts, patch_pair,
+                                                       corr_off);
+    launches += 2;
+  }
+  pick_best_kernel<<<S, 1024, 0, stream>>>(counts, n_patches, T_local, out_T, have_local, patch_off);
+  // degenerate branch per scan pair (no patch with >= min_corr correspondences): all its correspondences
+  procrustes_kernel<<<S, 256, 0, stream>>>(src, ref, scores, corr_off, n_corr, 0, T_deg, nullptr);
+  reweight_kernel<<<gridC, 256, 0, stream>>>(out_T, T_deg, have_local, src, ref, scores, n_corr, radius, w_cur, c_pair,
+                                             patch_pair);
+  launches += 3;
+  for (int it = 0; it < steps; it++) {
+    procrustes_kernel<<<S, 256, 0, stream>>>(src, ref, w_cur, corr_off, n_corr, 0, out_T, nullptr);
+    launches++;
+    if (it + 1 < steps) {
+      reweight_kernel<<<gridC, 256, 0, stream>>>(out_T, nullptr, nullptr, src, ref, scores, n_corr, radius, w_cur, c_pair,
+                                                 patch_pair);
       launches++;
     }
   }

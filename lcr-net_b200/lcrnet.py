@@ -6,11 +6,13 @@ Differences from the reference, all in its favour and none visible in the output
 * the three radius searches inside the vote encoder (backbone4.py:149-206) run on the GPU: no
   ``.cpu()`` / ``.cuda()`` round trips;
 * weighted Procrustes uses an on-device 3x3 SVD instead of ``torch.svd(H.cpu())`` (procrustes.py:53);
-* a data_dict may hold several pairs (``stack_size = 2``): encoder, transformer, vote encoder and
-  decoder run batched over all pairs with per-pair GroupNorm statistics; the matching head then
-  runs pair by pair.  With one pair the outputs are the reference's tensors; with several, the
-  per-pair outputs are lists.
+* a data_dict may hold several pairs (``stack_size = 2``): encoder, transformer, vote encoder,
+  decoder AND the matching head (partition, node / point Sinkhorn, correspondences, LGR) run batched
+  over all pairs -- one set of launches per stage, per-pair GroupNorm statistics, two device->host
+  reads of correspondence counts.  With one pair the outputs are the reference's tensors; with
+  several, the per-pair outputs are lists (views of the batch arrays).
 """
+import numpy as np
 import torch
 import torch.nn as nn
 
@@ -220,7 +222,11 @@ class Vote_Encoder(nn.Module):
         keep, counts, kept_idx = P.nms_greedy(shifted, clouds.off, clouds.n, clouds.max_rows, self.NMS_radius)
         counts_host = counts.tolist()                                   # D2H: node counts size everything below
         node_len = counts.to(torch.int64)
-        sel = torch.cat([kept_idx[o:o + c] for o, c in zip(clouds.off.tolist()[:-1], counts_host)]).long()
+        off_host = [0]
+        for n in lengths_c_host:
+            off_host.append(off_host[-1] + int(n))
+        sel_host = np.concatenate([np.arange(o, o + c, dtype=np.int64) for o, c in zip(off_host[:-1], counts_host)])
+        sel = kept_idx[torch.from_numpy(sel_host).to(dev)].long()      # kept points, compacted per cloud
         nms_points = shifted[sel].contiguous()
         lim = self.neighbor_limits
         node_knn = ops.radius_search(nms_points, shifted, node_len, lengths_c, self.NMS_radius, lim[-1], int32=True)
@@ -272,9 +278,9 @@ class LearnableLogOptimalTransport(nn.Module):
 
 # ------------------------------------------------------------------ the model
 class LCRNet(nn.Module):
-    """model_family/LCRNet.py:25-321."""
+    """model_family/LCRNet.py:25-321.  ``with_descriptor=False`` gives LCRNet_Matching (no NetVLAD head)."""
 
-    def __init__(self, cfg):
+    def __init__(self, cfg, with_descriptor=True):
         super().__init__()
         b = cfg.backbone
         self.num_points_in_patch = cfg.model.num_points_in_patch
@@ -287,8 +293,10 @@ class LCRNet(nn.Module):
         self.kpdecoder = KPDecoder(b.output_dim, b.init_dim, b.group_norm)
         self.node_optimal_transport = LearnableLogOptimalTransport(cfg.model.num_sinkhorn_iterations)
         self.optimal_transport = LearnableLogOptimalTransport(cfg.model.num_sinkhorn_iterations)
-        self.netvlad = NetVLADLoupe2(feature_size=1024, cluster_size=64, output_dim=256, gating=True, add_norm=True,
-                                     is_training=False)
+        if with_descriptor:
+            self.netvlad = NetVLADLoupe2(feature_size=1024, cluster_size=64, output_dim=256, gating=True, add_norm=True,
+                                         is_training=False)
+        self.with_descriptor = with_descriptor
         fm = cfg.fine_matching
         assert fm.topk == 1 and not fm.mutual and fm.use_dustbin and not fm.use_global_score and \
             fm.correspondence_limit is None and cfg.coarse_matching.num_correspondences is None, \
@@ -306,7 +314,7 @@ class LCRNet(nn.Module):
         feats = dd['features'].detach()
         dev = feats.device
         stacks, lh = make_stacks(dd, dev)
-        n_f, n_c = lh[0], lh[-1]
+        n_f, n_c = [int(x) for x in lh[0]], [int(x) for x in lh[-1]]
         n_pairs = len(n_c) // 2
         points_f, points_c = dd['points'][0], dd['points'][-1]
         dd = {k: ([ops.as_index32(t) for t in v] if k in ('neighbors', 'subsampling', 'upsampling') else v)
@@ -316,12 +324,15 @@ class LCRNet(nn.Module):
         feats_list = self.encoder(feats, dd, stacks)
         feats_c = feats_list[-1]
         clouds_c = ops.Stacks(n_c, dev)
-        descriptors = self.netvlad(feats_c, clouds_c.off, clouds_c.n)
+        descriptors = self.netvlad(feats_c, clouds_c.off, clouds_c.n) if self.with_descriptor else None
 
         # 2. transformer on the coarsest level: all ref clouds / all src clouds stacked separately
-        off_c = clouds_c.off.tolist()
-        ref_rows = torch.cat([torch.arange(off_c[2 * p], off_c[2 * p + 1], device=dev) for p in range(n_pairs)])
-        src_rows = torch.cat([torch.arange(off_c[2 * p + 1], off_c[2 * p + 2], device=dev) for p in range(n_pairs)])
+        off_c = [0]
+        for n in n_c:
+            off_c.append(off_c[-1] + n)
+        rows = lambda first: torch.from_numpy(np.concatenate(
+            [np.arange(off_c[2 * p + first], off_c[2 * p + first + 1], dtype=np.int64) for p in range(n_pairs)])).to(dev)
+        ref_rows, src_rows = rows(0), rows(1)
         ref_st, src_st = ops.Stacks(n_c[0::2], dev), ops.Stacks(n_c[1::2], dev)
         e0, e1 = self.transformer(points_c[ref_rows].contiguous(), points_c[src_rows].contiguous(),
                                   feats_c[ref_rows].contiguous(), feats_c[src_rows].contiguous(), ref_st.off,
@@ -334,115 +345,92 @@ class LCRNet(nn.Module):
         vd = self.vote_encoder(enhanced, dd, stacks[-1], n_c, 2)
         feats_f = self.kpdecoder(feats_list[:3] + [enhanced], dd, stacks)
 
-        # 4. matching head (LCRNet.py:161-272).  The two Sinkhorn stages are batched over all pairs:
-        #    node level padded to the largest node counts (masked rows/columns are exactly the
-        #    reference's masking), point level over the concatenated patch pairs.
-        off_f = ops.Stacks(n_f, dev).off.tolist()
-        node_off = [0]
-        for c in vd['counts']:
-            node_off.append(node_off[-1] + c)
+        # 4. matching head (LCRNet.py:161-272), every stage ONE set of launches for all pairs of the batch:
+        #    global point / node rows with per-cloud offsets; the node-level Sinkhorn is padded to the largest node
+        #    counts (masked rows / columns are exactly the reference's masking), the point level runs over the
+        #    concatenated patch list; two device->host reads size the outputs (node and point correspondence counts).
         K = self.num_points_in_patch
-        st = []
+        node_cnt = [int(c) for c in vd['counts']]
+        clouds_f, node_st = ops.Stacks(n_f, dev), ops.Stacks(node_cnt, dev)
+        node_mask, knn_g, knn_l, knn_mask, _ = P.point_to_node_batched(points_f, clouds_f, vd['centres'], node_st, K)
+        m_max, n_max = max(node_cnt[0::2] + [1]), max(node_cnt[1::2] + [1])
+        node_scores, row_m, col_m = P.node_scores(vd['feats'], node_st, node_mask, n_pairs, m_max, n_max)
+        node_ot = self.node_optimal_transport(node_scores, row_m, col_m)            # one launch, all pairs
+        oi, oj, os_, cnt = P.coarse_matching_batched(node_ot)
+        patch_off_host = [0]
+        for c in cnt.tolist():                                                       # D2H: node correspondence counts
+            patch_off_host.append(patch_off_host[-1] + int(c))
+        total = patch_off_host[-1]
+        patch_off = torch.tensor(patch_off_host, dtype=torch.int32).to(dev)
+        ci_g, cj_g, ci_l, cj_l, _, patch_pair = P.gather_coarse(oi, oj, os_, patch_off, node_st, total)
+        ms = P.patch_scores(feats_f, knn_g, ci_g, feats_f, knn_g, cj_g)               # LCRNet.py:231-233
+        km_bool = knn_mask.bool()
+        pkm, akm = km_bool[ci_g.long()], km_bool[cj_g.long()]
+        ot = self.optimal_transport(ms, pkm, akm)                                     # one launch, all patch pairs
+        corr = P.fine_correspondences(ot, knn_mask, ci_g, knn_mask, cj_g)
+        ref_c, src_c = P.corr_points(corr, points_f, knn_g, ci_g, points_f, knn_g, cj_g)
+        T = P.lgr_batched(ref_c, src_c, corr['score'], corr['pair'], corr['pair_off'], patch_pair, patch_off, n_pairs,
+                          self.acceptance_radius, self.correspondence_threshold, self.num_refinement_steps)
+        corr_off = corr['pair_off'][patch_off.long()].tolist()                        # D2H: correspondences per pair
+
+        # 5. output dicts: views of the batch arrays (keys: SURVEY Appendix C.4)
+        pts_pad = torch.cat([points_f, torch.zeros_like(points_f[:1])], 0)
+        knn_pts = pts_pad[knn_g.long()]                                               # [M, K, 3], pad row = 0
+        pos_kp, anc_kp = knn_pts[ci_g.long()], knn_pts[cj_g.long()]
+        ci_l64, cj_l64 = ci_l.long(), cj_l.long()
+        cp = corr['pair'][:corr_off[-1]]                                              # valid prefix (capacity arrays)
+        corr_patch_local = cp - patch_off[patch_pair.long()][cp.long()] if total else cp
+        off_f, node_off = clouds_f.off.tolist(), node_st.off.tolist()
+        outs = []
         for p in range(n_pairs):
             a, b = 2 * p, 2 * p + 1
-            s = {'pos_pf': points_f[off_f[a]:off_f[a + 1]].contiguous(), 'anc_pf': points_f[off_f[b]:off_f[b + 1]].contiguous(),
-                 'pos_ff': feats_f[off_f[a]:off_f[a + 1]].contiguous(), 'anc_ff': feats_f[off_f[b]:off_f[b + 1]].contiguous(),
-                 'pos_nodes': vd['centres'][node_off[a]:node_off[a + 1]].contiguous(),
-                 'anc_nodes': vd['centres'][node_off[b]:node_off[b + 1]].contiguous(),
-                 'pos_nf': vd['feats'][node_off[a]:node_off[a + 1]].contiguous(),
-                 'anc_nf': vd['feats'][node_off[b]:node_off[b + 1]].contiguous()}
-            _, s['pos_nm'], s['pos_knn'], s['pos_km'], _ = P.point_to_node_partition(s['pos_pf'], s['pos_nodes'], K)
-            _, s['anc_nm'], s['anc_knn'], s['anc_km'], _ = P.point_to_node_partition(s['anc_pf'], s['anc_nodes'], K)
-            st.append(s)
-        m_max = max(s['pos_nf'].shape[0] for s in st)
-        n_max = max(s['anc_nf'].shape[0] for s in st)
-        node_scores = torch.zeros((n_pairs, m_max, n_max), dtype=torch.float32, device=dev)
-        row_m = torch.zeros((n_pairs, m_max), dtype=torch.bool, device=dev)
-        col_m = torch.zeros((n_pairs, n_max), dtype=torch.bool, device=dev)
-        for p, s in enumerate(st):
-            m, n = s['pos_nf'].shape[0], s['anc_nf'].shape[0]
-            sc = P.linear_ex(s['pos_nf'], _pad4(s['anc_nf'].t()), None)[:, :n]       # LCRNet.py:196-199
-            node_scores[p, :m, :n] = sc / s['pos_nf'].shape[1] ** 0.5
-            row_m[p, :m] = s['pos_nm']
-            col_m[p, :n] = s['anc_nm']
-        node_ot = self.node_optimal_transport(node_scores, row_m, col_m)            # one launch, all pairs
-        pending = [P.coarse_matching(node_ot[p], defer=True) for p in range(n_pairs)]
-        counts = torch.cat([c[3] for c in pending]).tolist()                         # D2H: one read for all pairs
-        ms_all = []
-        for p, s in enumerate(st):
-            oi, oj, os_, _ = pending[p]
-            s['ci'], s['cj'], s['cs'] = oi[:counts[p]], oj[:counts[p]], os_[:counts[p]]
-            ms_all.append(P.patch_scores(s['pos_ff'], s['pos_knn'], s['ci'], s['anc_ff'], s['anc_knn'], s['cj']))
-            s['pkm'], s['akm'] = s['pos_km'][s['ci'].long()], s['anc_km'][s['cj'].long()]
-        ot_all = self.optimal_transport(torch.cat(ms_all), torch.cat([s['pkm'] for s in st]),
-                                        torch.cat([s['akm'] for s in st]))            # one launch, all patch pairs
-        # fine correspondences + LGR of every pair are queued first; the correspondence counts of all pairs come
-        # back in ONE device->host read (a read per pair drained the stream 32 times per batch)
-        launched, o0 = [], 0
-        for p, s in enumerate(st):
-            ot = ot_all[o0:o0 + counts[p]]
-            o0 += counts[p]
-            launched.append((ot,) + self._register_launch(s, ot))
-        n_corr = torch.stack([l[4]['pair_off'][-1] for l in launched]).tolist()
-        outs = []
-        for p, s in enumerate(st):
-            a, b = 2 * p, 2 * p + 1
-            out = self._register_finish(s, launched[p], node_ot[p], n_corr[p])
-            out.update({
+            t0, t1, c0, c1 = patch_off_host[p], patch_off_host[p + 1], corr_off[p], corr_off[p + 1]
+            na, nb_, nc = node_off[a], node_off[b], node_off[b + 1]
+            out = {
                 'ori_pos_points_c': points_c[off_c[a]:off_c[a + 1]], 'ori_anc_points_c': points_c[off_c[b]:off_c[b + 1]],
-                'pos_points_f': s['pos_pf'], 'anc_points_f': s['anc_pf'],
-                'pos_feature_global': descriptors[a:a + 1], 'anc_feature_global': descriptors[b:b + 1],
+                'pos_points_f': points_f[off_f[a]:off_f[a + 1]], 'anc_points_f': points_f[off_f[b]:off_f[b + 1]],
                 'shifted_pos_points_c': vd['shifted'][off_c[a]:off_c[a + 1]],
                 'shifted_anc_points_c': vd['shifted'][off_c[b]:off_c[b + 1]],
-                'length': torch.tensor(vd['counts'][a:b + 1]),
-                'feats_c': vd['feats'][node_off[a]:node_off[b + 1]],
-            })
+                'pos_points_c': vd['centres'][na:nb_], 'anc_points_c': vd['centres'][nb_:nc],
+                'pos_feats_c': vd['feats'][na:nb_], 'anc_feats_c': vd['feats'][nb_:nc],
+                'length': torch.tensor(node_cnt[a:b + 1]), 'feats_c': vd['feats'][na:nc],
+                'anc_node_knn_indices': (knn_l[nb_:nc],), 'anc_node_knn_masks': (km_bool[nb_:nc],),
+                'pos_node_knn_indices': (knn_l[na:nb_],), 'pos_node_knn_masks': (km_bool[na:nb_],),
+                'pos_node_corr_indices': ci_l64[t0:t1], 'anc_node_corr_indices': cj_l64[t0:t1],
+                'pos_feats_f': feats_f[off_f[a]:off_f[a + 1]], 'anc_feats_f': feats_f[off_f[b]:off_f[b + 1]],
+                'pos_node_corr_knn_points': pos_kp[t0:t1], 'anc_node_corr_knn_points': anc_kp[t0:t1],
+                'pos_node_corr_knn_masks': pkm[t0:t1], 'anc_node_corr_knn_masks': akm[t0:t1],
+                'pos_corr_points': ref_c[c0:c1], 'anc_corr_points': src_c[c0:c1], 'corr_scores': corr['score'][c0:c1],
+                'estimated_transform': T[p],
+                '_node_ot': node_ot[p], '_point_ot': ot[t0:t1], '_corr_patch': corr_patch_local[c0:c1],
+                '_corr_i': corr['i'][c0:c1], '_corr_j': corr['j'][c0:c1],
+            }
+            if self.with_descriptor:
+                out['pos_feature_global'] = descriptors[a:a + 1]
+                out['anc_feature_global'] = descriptors[b:b + 1]
             outs.append(out)
         if n_pairs == 1:
             return outs[0]
         merged = {k: [o[k] for o in outs] for k in outs[0]}
-        merged['estimated_transform'] = torch.stack(merged['estimated_transform'])
+        merged['estimated_transform'] = T
         return merged
 
-    def _register_launch(self, s, ot):
-        """Queues fine correspondences + local-to-global registration of one pair (LCRNet.py:251-262); no
-        device->host traffic."""
-        ci, cj = s['ci'], s['cj']
-        corr = P.fine_correspondences(ot, s['pos_km'], ci, s['anc_km'], cj)
-        ref_c, src_c = P.corr_points(corr, s['pos_pf'], s['pos_knn'], ci, s['anc_pf'], s['anc_knn'], cj)
-        T = P.local_global_registration(ref_c, src_c, corr['score'], corr['pair_off'], self.acceptance_radius,
-                                        self.correspondence_threshold, self.num_refinement_steps)
-        return T, ref_c, src_c, corr
 
-    def _register_finish(self, s, launched, node_ot, n):
-        """Output dict of one pair; ``n`` = its number of fine correspondences (host int)."""
-        ot, T, ref_c, src_c, corr = launched
-        ci, cj = s['ci'], s['cj']
-        pad3 = lambda x: torch.cat([x, torch.zeros_like(x[:1])], 0)
-        m, k = s['pos_nf'].shape[0], s['anc_nf'].shape[0]
-        return {'estimated_transform': T, 'pos_corr_points': ref_c[:n], 'anc_corr_points': src_c[:n],
-                'corr_scores': corr['score'][:n], 'pos_node_corr_indices': ci.long(), 'anc_node_corr_indices': cj.long(),
-                'pos_points_c': s['pos_nodes'], 'anc_points_c': s['anc_nodes'], 'pos_feats_c': s['pos_nf'],
-                'anc_feats_c': s['anc_nf'], 'pos_feats_f': s['pos_ff'], 'anc_feats_f': s['anc_ff'],
-                'pos_node_knn_indices': (s['pos_knn'].long(),), 'pos_node_knn_masks': (s['pos_km'],),
-                'anc_node_knn_indices': (s['anc_knn'].long(),), 'anc_node_knn_masks': (s['anc_km'],),
-                'pos_node_corr_knn_points': pad3(s['pos_pf'])[s['pos_knn'].long()[ci.long()]],
-                'anc_node_corr_knn_points': pad3(s['anc_pf'])[s['anc_knn'].long()[cj.long()]],
-                'pos_node_corr_knn_masks': s['pkm'], 'anc_node_corr_knn_masks': s['akm'],
-                '_node_ot': node_ot, '_point_ot': ot, '_corr_patch': corr['pair'][:n], '_corr_i': corr['i'][:n],
-                '_corr_j': corr['j'][:n]}
+class LCRNet_Matching(LCRNet):
+    """model_family/LCRNet_Matching_infer.py:24-292: the registration model without the global-descriptor head
+    (same modules and state_dict minus ``netvlad.*``; output dict without ``pos/anc_feature_global``)."""
 
-
-def _pad4(w):
-    """[c_in, n] -> contiguous with n padded to a multiple of 4 (GEMM operand B)."""
-    cin, n = w.shape
-    out = torch.zeros((cin, (n + 3) // 4 * 4), dtype=torch.float32, device=w.device)
-    out[:, :n] = w
-    return out
+    def __init__(self, cfg):
+        super().__init__(cfg, with_descriptor=False)
 
 
 def create_model(cfg):
     return LCRNet(cfg)
+
+
+def create_matching_model(cfg):
+    """``create_model`` of model_family/LCRNet_Matching_infer.py:290-292."""
+    return LCRNet_Matching(cfg)
 
 
 class _Cfg(dict):

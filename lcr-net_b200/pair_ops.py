@@ -201,3 +201,80 @@ def local_global_registration(ref, src, scores, pair_off, radius=0.45, min_corr=
                                                _lib.ptr(pair_off), p, cap, float(radius), min_corr, steps,
                                                _lib.ptr(T), _lib.ptr(ws), ws.numel(), _s(ref)))
     return T
+
+
+# ------------------------------------------------------------------ batched matching tail (all pairs of a chunk)
+def point_to_node_batched(points, pts_stacks, nodes, node_stacks, point_limit=128, want_local=True):
+    """pointcloud_partition.py:61-107 for every cloud of the batch at once.  ``pts_stacks`` / ``node_stacks``:
+    ops.Stacks over the clouds.  -> (node_mask u8 [M], knn_global i32 [M,K] (global point rows, pad = N),
+    knn_local i64 [M,K] (rows local to the cloud, pad = its size: the reference's table), knn_mask u8 [M,K],
+    status i32 [1])."""
+    n, m = points.shape[0], nodes.shape[0]
+    dev = points.device
+    node_mask = torch.empty(m, dtype=torch.uint8, device=dev)
+    knn_g = torch.empty((m, point_limit), dtype=torch.int32, device=dev)
+    knn_l = torch.empty((m, point_limit), dtype=torch.int64, device=dev) if want_local else None
+    knn_mask = torch.empty((m, point_limit), dtype=torch.uint8, device=dev)
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    L = _L()
+    ws = _lib.workspace.get(L.lcr_point_to_node_ws_bytes(n, m), dev, slot=4)
+    _lib.check(L.lcr_point_to_node_batched(_lib.ptr(_f32c(points)), n, _lib.ptr(pts_stacks.off), _lib.ptr(_f32c(nodes)), m,
+                                           _lib.ptr(node_stacks.off), pts_stacks.n, pts_stacks.max_rows,
+                                           max(node_stacks.max_rows, 1), point_limit, None, _lib.ptr(node_mask),
+                                           _lib.ptr(knn_g), _lib.ptr(knn_l), _lib.ptr(knn_mask), _lib.ptr(status),
+                                           _lib.ptr(ws), ws.numel(), _s(points)))
+    return node_mask, knn_g, knn_l, knn_mask, status
+
+
+def node_scores(feats, node_stacks, node_mask, n_pairs, m_max, n_max):
+    """LCRNet.py:196-199 for all pairs: [P, m_max, n_max] zero-padded scores + padded u8 masks."""
+    dev = feats.device
+    out = torch.empty((n_pairs, m_max, n_max), dtype=torch.float32, device=dev)
+    rm = torch.empty((n_pairs, m_max), dtype=torch.uint8, device=dev)
+    cm = torch.empty((n_pairs, n_max), dtype=torch.uint8, device=dev)
+    _lib.check(_L().lcr_node_scores(_lib.ptr(_f32c(feats)), feats.shape[1], _lib.ptr(node_stacks.off), _lib.ptr(node_mask),
+                                    n_pairs, m_max, n_max, _lib.ptr(out), _lib.ptr(rm), _lib.ptr(cm), _s(feats)))
+    return out, rm, cm
+
+
+def coarse_matching_batched(log_scores):
+    """superpoint_matching.py:129-160 on [P, R+1, C+1] -> capacity arrays [P, R+C] (i, j, score) and counts i32 [P]."""
+    p, r, c = log_scores.shape[0], log_scores.shape[1] - 1, log_scores.shape[2] - 1
+    dev = log_scores.device
+    cap = r + c
+    oi = torch.empty((p, cap), dtype=torch.int32, device=dev)
+    oj = torch.empty((p, cap), dtype=torch.int32, device=dev)
+    os_ = torch.empty((p, cap), dtype=torch.float32, device=dev)
+    cnt = torch.zeros(p, dtype=torch.int32, device=dev)
+    ws_bytes = 4 * p * (2 * (r + 1) + (c + 1)) + 4096
+    ws = _lib.workspace.get(ws_bytes, dev, slot=5)
+    _lib.check(_L().lcr_coarse_matching_batched(_lib.ptr(_f32c(log_scores)), p, r, c, _lib.ptr(oi), _lib.ptr(oj),
+                                                _lib.ptr(os_), _lib.ptr(cnt), _lib.ptr(ws), ws.numel(), _s(log_scores)))
+    return oi, oj, os_, cnt
+
+
+def gather_coarse(oi, oj, os_, patch_off, node_stacks, total):
+    """One patch list for the batch: (ci_global, cj_global, ci_local, cj_local, scores, patch_pair), each [total]."""
+    dev = oi.device
+    p = oi.shape[0]
+    i32 = lambda: torch.empty(max(total, 1), dtype=torch.int32, device=dev)
+    ci_g, cj_g, ci_l, cj_l, pp = i32(), i32(), i32(), i32(), i32()
+    cs = torch.empty(max(total, 1), dtype=torch.float32, device=dev)
+    _lib.check(_L().lcr_gather_coarse(_lib.ptr(oi), _lib.ptr(oj), _lib.ptr(os_), oi.shape[1], _lib.ptr(patch_off),
+                                      _lib.ptr(node_stacks.off), p, _lib.ptr(ci_g), _lib.ptr(cj_g), _lib.ptr(ci_l),
+                                      _lib.ptr(cj_l), _lib.ptr(cs), _lib.ptr(pp), _s(oi)))
+    return ci_g[:total], cj_g[:total], ci_l[:total], cj_l[:total], cs[:total], pp[:total]
+
+
+def lgr_batched(ref, src, scores, c_pair, pair_off, patch_pair, patch_off, n_scan_pairs, radius=0.45, min_corr=3,
+                steps=5):
+    """local_global_registration.py:140-202 for all scan pairs at once -> [S, 4, 4]."""
+    t = pair_off.shape[0] - 1
+    cap = ref.shape[0]
+    T = torch.zeros((n_scan_pairs, 4, 4), dtype=torch.float32, device=ref.device)
+    L = _L()
+    ws = _lib.workspace.get(L.lcr_lgr_batched_ws_bytes(t, n_scan_pairs, cap), ref.device, slot=6)
+    _lib.check(L.lcr_lgr_batched(_lib.ptr(_f32c(ref)), _lib.ptr(_f32c(src)), _lib.ptr(_f32c(scores)), _lib.ptr(c_pair),
+                                 _lib.ptr(pair_off), t, _lib.ptr(patch_pair), _lib.ptr(patch_off), n_scan_pairs, cap,
+                                 float(radius), min_corr, steps, _lib.ptr(T), _lib.ptr(ws), ws.numel(), _s(ref)))
+    return T
