@@ -745,6 +745,264 @@ gemm_tf32x3_ws_kernel(const float* __restrict__ A, int lda, const float* __restr
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Persistent kernel with the A operand in TENSOR MEMORY (tcgen05.mma "TS" form: D += A[tmem] . B[smem]^T).
+// Why: in the kernel above every byte passes through shared memory several times -- per 128 x 32 k-block the
+// tensor core itself reads A and B once per MMA (3 products x 4 k-steps x (4 KB of A + BN x 32 B of B): 96 KB at
+// BN = 128), the cp.async engine writes 48 KB, and the lo-split reads and writes the A block again (32 KB): 176 KB
+// per 768 MMA cycles against a 128 B/clk shared-memory port -- the tensor pipe cannot pass ~55 % (ncu: 48-52 %),
+// and the narrow contractions (BN = 32: 60 KB of A re-reads per 192 MMA cycles) are worse.  Here the producers
+// move each landed raw A block ONCE from shared memory into TMEM (tcgen05.st), already split: hi = the raw word
+// (kind::tf32 truncates it), lo = x - trunc(x); the MMAs read A from TMEM (which has its own read path) and only
+// the W blocks from shared memory: 112 KB per k-block at BN = 128, 52 KB at BN = 32.
+//   TMEM columns: 2 accumulators x BN  +  STAGES x (32 hi + 32 lo) A columns  <= 512.
+//   producer warp pw (physical warp 4 + pw) may touch TMEM lanes 32 (pw % 4) .. + 31: lane = A row 32 (pw % 4) +
+//   lane, columns 16 (pw / 4) .. + 15 of the k-block; its 64 bytes of the row come from four conflict-free
+//   16-byte loads of the swizzled landing buffer.
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+// D[tmem] (+)= A[tmem] . B[smem]^T
+__device__ __forceinline__ void mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u)
+      : "memory");
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(kWsThreads, 1)
+gemm_tf32x3_ts_kernel(const float* __restrict__ A, int lda, const float* __restrict__ W, const float* __restrict__ W_lo,
+                      int ldw, float* __restrict__ C, int ldc, int M, int N, int K, const float* __restrict__ rowscale,
+                      const float* __restrict__ bias, int relu, const GnFuse gnf) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = smem_raw + ((1024u - ((uint32_t)__cvta_generic_to_shared(smem_raw) & 1023u)) & 1023u);
+  constexpr int kATile = BM * BK * 4, kBTile = BN * BK * 4;
+  constexpr int kStageBytes = kATile + 2 * kBTile;          // raw A landing buffer | W hi | W lo
+  constexpr int kProd = kWsProducerWarps * 32;
+  constexpr uint32_t kAccCols = 2 * BN;                     // TMEM: [0, 2 BN) accumulators, then the A stages
+  static_assert(kAccCols + STAGES * 64 <= 512, "TMEM budget");
+  __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], acc_full[2], acc_empty[2];
+  __shared__ uint32_t tmem_base_s;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nk = K / BK;
+  const int tiles_n = (N + BN - 1) / BN;
+  const int tiles = ((M + BM - 1) / BM) * tiles_n;
+  const int my_tiles = ((int)blockIdx.x < tiles) ? (tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const int n_chunks = (nk + kWsChunk - 1) / kWsChunk;     // per tile
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; s++) {
+      mbar_init(&full_bar[s], kWsProducerWarps);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int b = 0; b < 2; b++) {
+      mbar_init(&acc_full[b], 1);
+      mbar_init(&acc_empty[b], kWsEpilogueWarps);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  constexpr int kMmaWarp = kWsEpilogueWarps + kWsProducerWarps;
+  if (warp == kMmaWarp) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
+                 "n"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp >= kWsEpilogueWarps && warp < kMmaWarp) {
+    // ================================================================ producers
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kWsProducerRegs));
+    const int tid = (int)threadIdx.x - kWsEpilogueWarps * 32;   // index among the producer threads
+    const int pw = tid >> 5;                                    // producer warp; physical warp = 4 + pw
+    const int total = my_tiles * nk;                            // blocks this CTA streams, tile-major
+    constexpr int kALoads = BM * 8 / kProd, kBLoads = (BN * 8 + kProd - 1) / kProd;
+    auto issue_block = [&](int g) {
+      if (g < total) {
+        const int t = (int)blockIdx.x + (g / nk) * (int)gridDim.x;
+        const int m0 = (t / tiles_n) * BM, n0 = (t % tiles_n) * BN, k0 = (g % nk) * BK;
+        const int s = g % STAGES;
+        const uint32_t a_raw = smem_u32(base + s * kStageBytes), b_hi = a_raw + kATile;
+#pragma unroll
+        for (int i = 0; i < kALoads; i++) {
+          const int idx = tid + i * kProd;
+          const int row = idx >> 3, chunk = idx & 7;
+          const int gm = m0 + row;
+          const float* src = A + (size_t)(gm < M ? gm : 0) * lda + k0 + chunk * 4;
+          const uint32_t dst = a_raw + row * 128 + ((chunk ^ (row & 7)) << 4);
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(gm < M ? 16 : 0));
+        }
+#pragma unroll
+        for (int i = 0; i < kBLoads; i++) {
+          const int idx = tid + i * kProd;
+          if (BN * 8 % kProd == 0 || idx < BN * 8) {
+            const int row = idx >> 3, chunk = idx & 7;
+            const int gn = n0 + row;
+            const size_t goff = (size_t)(gn < N ? gn : 0) * ldw + k0 + chunk * 4;
+            const uint32_t dst = b_hi + row * 128 + ((chunk ^ (row & 7)) << 4);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(W + goff), "r"(gn < N ? 16 : 0));
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + kBTile), "l"(W_lo + goff),
+                         "r"(gn < N ? 16 : 0));
+          }
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");   // always: keeps the group count uniform
+    };
+#pragma unroll
+    for (int g = 0; g < STAGES - 1; g++) issue_block(g);
+    const int arow = 32 * (pw & 3) + lane;                 // A row (= TMEM lane) this thread moves
+    const int ahalf = pw >> 2;                             // which 16 of the 32 k-columns
+    const uint32_t t_lane = (uint32_t)(32 * (pw & 3)) << 16;
+    for (int g = 0; g < total; g++) {
+      const int s = g % STAGES;
+      asm volatile("cp.async.wait_group %0;" ::"n"(STAGES - 2) : "memory");   // this thread's part of block g landed
+      asm volatile("bar.sync 1, %0;" ::"n"(kProd) : "memory");                // ... and every other producer's
+      const float* a_raw = reinterpret_cast<const float*>(base + s * kStageBytes);
+      uint32_t hi[16], lo[16];
+#pragma unroll
+      for (int c = 0; c < 4; c++) {
+        const int chunk = 4 * ahalf + c;
+        const float4 v = *reinterpret_cast<const float4*>(a_raw + arow * 32 + ((chunk ^ (arow & 7)) << 2));
+        const float x[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+          const uint32_t h = __float_as_uint(x[e]);
+          hi[4 * c + e] = h;                                                   // the tensor core truncates it
+          lo[4 * c + e] = __float_as_uint(x[e] - __uint_as_float(h & 0xFFFFE000u));
+        }
+      }
+      const uint32_t t_a = tmem_base + kAccCols + (uint32_t)(s * 64) + t_lane + (uint32_t)(16 * ahalf);
+      tmem_st16(t_a, hi);
+      tmem_st16(t_a + 32, lo);
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      // W blocks (cp.async, generic proxy) -> visible to the async proxy; A block in TMEM -> ordered before the arrive
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full_bar[s]);
+      const int nb = g + STAGES - 1;                       // refill the stage block g-1 occupied
+      if (nb < total && g >= 1) mbar_wait(&empty_bar[nb % STAGES], ((nb / STAGES) - 1) & 1);
+      issue_block(nb);
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+  } else if (warp == kMmaWarp) {
+    // ================================================================ MMA issuer (one lane)
+    if (lane == 0) {
+      constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) |
+                                 ((uint32_t)(BM >> 4) << 24);
+      int g = 0, gc = 0;                                   // running block / chunk counters
+      for (int ti = 0; ti < my_tiles; ti++) {
+        for (int c = 0; c < n_chunks; c++, gc++) {
+          const int b = gc & 1;
+          if (gc >= 2) {
+            mbar_wait(&acc_empty[b], ((gc >> 1) - 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          }
+          const uint32_t tmem_d = tmem_base + (uint32_t)(b * BN);
+          const int kb_end = min((c + 1) * kWsChunk, nk);
+          for (int kb = c * kWsChunk; kb < kb_end; kb++, g++) {
+            const int s = g % STAGES;
+            mbar_wait(&full_bar[s], (g / STAGES) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t b_hi = smem_u32(base + s * kStageBytes) + kATile, b_lo = b_hi + kBTile;
+            const uint32_t a_hi = tmem_base + kAccCols + (uint32_t)(s * 64), a_lo = a_hi + 32;
+#pragma unroll
+            for (int k = 0; k < BK / 8; k++) {
+              const uint32_t koff = k * 32, kc = k * 8;
+              mma_tf32_ts(tmem_d, a_hi + kc, make_desc(b_hi + koff), idesc, (kb > c * kWsChunk) || k != 0);
+              mma_tf32_ts(tmem_d, a_hi + kc, make_desc(b_lo + koff), idesc, 1);
+              mma_tf32_ts(tmem_d, a_lo + kc, make_desc(b_hi + koff), idesc, 1);
+            }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                             smem_u32(&empty_bar[s]))
+                         : "memory");
+          }
+          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                           smem_u32(&acc_full[b]))
+                       : "memory");
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ================================================================ epilogue warps
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kWsEpilogueRegs));
+    const int q = warp & 3;                                // TMEM lane quarter this warp may access
+    float* tb = reinterpret_cast<float*>(base + STAGES * kStageBytes) + warp * (32 * 33);
+    int gc = 0;
+    for (int ti = 0; ti < my_tiles; ti++) {
+      const int t = (int)blockIdx.x + ti * (int)gridDim.x;
+      const int m0 = (t / tiles_n) * BM, n0 = (t % tiles_n) * BN;
+      float acc[BN];
+#pragma unroll
+      for (int j = 0; j < BN; j++) acc[j] = 0.f;
+      for (int c = 0; c < n_chunks; c++, gc++) {
+        const int b = gc & 1;
+        mbar_wait(&acc_full[b], (gc >> 1) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * BN + c0), r);
+#pragma unroll
+          for (int j = 0; j < 32; j++) acc[c0 + j] += __uint_as_float(r[j]);
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[b]);
+      }
+      const int row0 = m0 + q * 32;
+      const float rs = (rowscale && row0 + lane < M) ? rowscale[row0 + lane] : 1.f;
+      const int split = gn_split(gnf, row0, M);
+#pragma unroll
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+#pragma unroll
+        for (int j = 0; j < 32; j++) tb[lane * 33 + j] = acc[c0 + j] * rs;
+        __syncwarp();
+        store_chunk(tb, lane, row0, M, n0 + c0 + lane, N, bias, relu, C, ldc, gnf, split);
+        __syncwarp();
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == kMmaWarp) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
+  }
+}
+
+template <int BN, int STAGES>
+int launch_tc_ts(const float* A, int lda, const float* W, const float* W_lo, int ldw, float* C, int ldc, int M, int N,
+                 int K, const float* rowscale, const float* bias, int relu, const GnFuse& gnf, cudaStream_t stream) {
+  constexpr size_t smem = (size_t)STAGES * (BM * BK * 4 + 2 * BN * BK * 4) + kWsEpilogueWarps * 32 * 33 * 4 + 1024;
+  static_assert(smem <= 227 * 1024, "shared memory budget");
+  static LcrOncePerDevice attr_done;
+  const int attr_done_dev = attr_done.need();
+  if (attr_done_dev != -1) {
+    LCR_CUDA_TRY(cudaFuncSetAttribute(gemm_tf32x3_ts_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)smem));
+    attr_done.done(attr_done_dev);
+  }
+  const long tiles = (long)((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+  const unsigned grid = (unsigned)(tiles < LCR_SM_COUNT ? tiles : LCR_SM_COUNT);
+  gemm_tf32x3_ts_kernel<BN, STAGES><<<grid, kWsThreads, smem, stream>>>(A, lda, W, W_lo, ldw, C, ldc, M, N, K, rowscale,
+                                                                        bias, relu, gnf);
+  return LCR_OK;
+}
+
 template <int BN, int STAGES>
 int launch_tc_ws(const float* A, int lda, const float* W, const float* W_lo, int ldw, float* C, int ldc, int M, int N,
                  int K, const float* rowscale, const float* bias, int relu, const GnFuse& gnf, cudaStream_t stream) {
@@ -812,7 +1070,12 @@ __global__ void tf32_split_kernel(const float* __restrict__ w, int64_t n, float*
 template <bool PS>
 int gemm_dispatch(const float* A, int lda, const float* W, const float* W_lo, int ldw, float* C, int ldc, int M, int N,
                   int K, const float* rowscale, const float* bias, int relu, const GnFuse& gnf, cudaStream_t stream) {
-  static const int ws = getenv("LCR_GEMM_WS") ? atoi(getenv("LCR_GEMM_WS")) : 1;
+  static const int ws = getenv("LCR_GEMM_WS") ? atoi(getenv("LCR_GEMM_WS")) : 3;   // 3: A operand in TMEM (default)
+  if (PS && (ws == 4 || (ws == 3 && K > 4 * BK))) {   // persistent kernel with the A operand in tensor memory
+    if (N <= 32) return launch_tc_ts<32, 6>(A, lda, W, W_lo, ldw, C, ldc, M, N, K, rowscale, bias, relu, gnf, stream);
+    if (N <= 64) return launch_tc_ts<64, 5>(A, lda, W, W_lo, ldw, C, ldc, M, N, K, rowscale, bias, relu, gnf, stream);
+    return launch_tc_ts<128, 4>(A, lda, W, W_lo, ldw, C, ldc, M, N, K, rowscale, bias, relu, gnf, stream);
+  }
   if (PS && (ws == 2 || (ws == 1 && K > 4 * BK))) {   // persistent warp-specialised kernel (needs the pre-split weights)
     if (N <= 32) return launch_tc_ws<32, 5>(A, lda, W, W_lo, ldw, C, ldc, M, N, K, rowscale, bias, relu, gnf, stream);
     if (N <= 64) return launch_tc_ws<64, 4>(A, lda, W, W_lo, ldw, C, ldc, M, N, K, rowscale, bias, relu, gnf, stream);
