@@ -21,10 +21,10 @@
 // scores for score ranges up to +-100; the torch fp32 reference itself is 4e-5 .. 3e-4 away from fp64 there.
 //
 // Kernels:
-//   sinkhorn_patch_kernel    the point-level problems (128 x 128 (+1), thousands per batch): K lives in REGISTERS
-//                            (every thread a quarter row and a quarter column); a LIN half-iteration is 33 FFMA per
-//                            thread against a vector broadcast from shared memory with 16-byte loads -- the round-1
-//                            kernel read K from shared memory: one LDS per FMA, bound by the 128 B/clk port.
+//   sinkhorn_patch_kernel    the point-level problems (128 x 128 (+1), thousands per batch): K lives in REGISTERS as
+//                            4 x 33 blocks per thread; a LIN half-iteration is 132 FFMA per thread against 33 words
+//                            of shared memory -- the round-1 kernel read K from shared memory: one LDS per FMA,
+//                            bound by the 128 B/clk port.
 //   sinkhorn_general_kernel  any size (node level, ~370 x 360): K in the output buffer (L2), warp per row, row
 //                            slabs per warp for the column sums.
 #include "common.cuh"
@@ -68,72 +68,95 @@ __device__ __forceinline__ float sk_score(const float* __restrict__ src, const u
 }
 
 // ================================================================== point level: 128 x 128 (+ dustbins)
-// Thread t = 4 q + h (q < 129, h < 4) holds a QUARTER of row q of the plan (columns 32 h .. 32 h + 31, plus the
-// dustbin column for h = 3) and a quarter of column q (rows 32 h .. 32 h + 31, plus the dustbin row): 66 registers.
-// Every thread works in both half-iterations -- 33 FFMA against 8 + 1 broadcast loads of the other side's scalings,
-// a 4-lane butterfly, one division -- so the 17 warps (4-5 per scheduler) cover the shared-memory latency that a
-// one-warp-per-scheduler layout (thread = whole row, first version of this kernel: ptxas kept only two 16-byte
-// loads in flight) left exposed: 160 -> ~30 us per problem.
-constexpr int PN = 128, PR = 129, PLD = 129, PV = 136, PQ = 33;
-constexpr int kPatchThreads = 544;                           // 17 warps: 516 threads carry data
+// The plan (129 x 129, zero-padded to 132 x 132) lives in REGISTERS as 3 x 33 blocks: thread (g, h) of the row role
+// (warps 0-5) holds rows 3 g .. 3 g + 2 x columns 33 h .. 33 h + 32, thread (g, h) of the column role (warps 6-11) the
+// transposed block (12 warps: 168 registers per thread, 99 of them the plan, 33 the scalings in flight).  A
+// half-iteration is 99 FFMA per active thread against 33 words of the other side's scalings: every word loaded from
+// shared memory feeds THREE multiply-adds.  That ratio is the point: shared memory delivers
+// one 32-bit word per lane and wavefront whatever the load width or broadcast, so a thread-per-row (1 x 129) or
+// quarter-row (1 x 33) layout needs 129 x 129 words per half-iteration -- 520 cycles of the 128 B/clk port, measured
+// 50 % busy and short-scoreboard bound (ncu, profiles/r2_ncu_sinkhorn_quarter_rows.txt) -- while the 4 x 33 blocks
+// need a third of that.  The partial sums of a row group are combined by a 4-lane butterfly; lane h < 3 finishes
+// row 3 g + h.  Scaling vectors sit in shared memory as four 36-float segments (element x at 36 (x / 33) + x % 33) so the
+// 33 words of a thread are eight aligned 16-byte loads + one, on distinct banks for the four h.
+constexpr int PN = 128, PR = 129, PLD = 129, PP = 132, PV = 144, PB = 33;
+constexpr int RB = 3;                                        // rows (columns) per thread block: 3 x 33 = 99 registers
+constexpr int NG = PP / RB;                                  // 44 row (column) groups
+constexpr int kPatchRoleThreads = 192;                       // 6 warps per role, 176 threads carry data
+constexpr int kPatchThreads = 2 * kPatchRoleThreads;
 constexpr int kPatchSFloats = 16644;                         // 129 * 129 rounded up to a multiple of 4
-constexpr size_t kPatchSmem = sizeof(float) * (kPatchSFloats + 10 * PV);
+constexpr size_t kPatchSmem = sizeof(float) * (kPatchSFloats + 4 * PV + 6 * PP);
 
-// Shared-memory layout of a scaling vector x[0..128]: the quarter h of the vector (x[32 h .. 32 h + 31]) is cut into
-// eight float4 groups m and stored group-interleaved, group (m, h) at float4 slot 4 m + h; x[128] stays at float
-// index 128.  The four threads of a row then read four CONSECUTIVE float4 (64 bytes, the same for all eight rows of
-// the warp): one conflict-free wavefront, where the plain layout put the four quarters 128 bytes apart on the same
-// banks (4-way conflict on every load).
-__device__ __forceinline__ int vec_slot(int x) {          // float index of element x (x < 128)
-  return ((((x & 31) >> 2) * 4 + (x >> 5)) << 2) | (x & 3);
+__device__ __forceinline__ int vec_slot(int x) { return 36 * (x / PB) + x % PB; }   // x < 132
+
+// s[r] = sum_c k[r][c] * x[33 h + c], then the 4-lane butterfly over h.  All nine loads are issued before the
+// first FMA: left alone, ptxas sinks every load to just before its use and recycles ONE register quad (ncu source
+// view: each of the nine LDS.128 exposed its full latency, ~30 % of the half-iteration), and neither volatile asm
+// loads nor a warp barrier keep it from doing so.  The accumulators therefore start from a zero that is
+// data-dependent on all nine loads, which forces them to be in flight together.
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "r"(addr)
+               : "memory");
+  return v;
 }
-
-// sum over this thread's quarter h: k[4 m + r] against x[32 h + 4 m + r], k[32] against x[128].  All nine loads are
-// issued before the first FMA (see the __syncwarp below).
-__device__ __forceinline__ float dot_quarter(const float (&k)[PQ], const float* __restrict__ vec, int h) {
-  const unsigned base = (unsigned)__cvta_generic_to_shared(vec) + 16u * (unsigned)h;
+__device__ __forceinline__ float lds32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts32(uint32_t addr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+// `seg` = 32-bit shared-window address of this thread's 36-float segment of the scaling vector (generic pointers cost
+// a window conversion per access: S2R + LEA showed up in every half-iteration)
+__device__ __forceinline__ void dot_block(const float (&k)[RB][PB], uint32_t seg, float (&s)[RB]) {
   float4 t[8];
 #pragma unroll
-  for (int m = 0; m < 8; m++)
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                 : "=f"(t[m].x), "=f"(t[m].y), "=f"(t[m].z), "=f"(t[m].w)
-                 : "r"(base + 64u * (unsigned)m));
-  float last;
-  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(last) : "r"((unsigned)__cvta_generic_to_shared(vec) + 4u * PN));
-  // ptxas sinks each load to just before its use to save registers (two loads in flight, one ~30-cycle stall per
-  // float4); a warp-level barrier is a memory fence it cannot move shared loads across, so all nine loads are
-  // issued back to back here and their latencies overlap
-  __syncwarp();
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  for (int m = 0; m < 8; m++) t[m] = lds128(seg + 16u * m);
+  const float last = lds32(seg + 128u);
+  // zero, but data-dependent on every load (x * 0 is not foldable in IEEE arithmetic; the scalings are finite)
+  const float z = ((((t[0].x + t[1].x) + (t[2].x + t[3].x)) + ((t[4].x + t[5].x) + (t[6].x + t[7].x))) + last) * 0.f;
+#pragma unroll
+  for (int r = 0; r < RB; r++) s[r] = z;
 #pragma unroll
   for (int m = 0; m < 8; m++) {
-    s0 = fmaf(k[4 * m], t[m].x, s0);
-    s1 = fmaf(k[4 * m + 1], t[m].y, s1);
-    s2 = fmaf(k[4 * m + 2], t[m].z, s2);
-    s3 = fmaf(k[4 * m + 3], t[m].w, s3);
+#pragma unroll
+    for (int r = 0; r < RB; r++) {
+      s[r] = fmaf(k[r][4 * m], t[m].x, s[r]);
+      s[r] = fmaf(k[r][4 * m + 1], t[m].y, s[r]);
+      s[r] = fmaf(k[r][4 * m + 2], t[m].z, s[r]);
+      s[r] = fmaf(k[r][4 * m + 3], t[m].w, s[r]);
+    }
   }
-  s0 = fmaf(k[32], last, s0);
-  float s = (s0 + s1) + (s2 + s3);
-  s += __shfl_xor_sync(0xffffffffu, s, 1);
-  s += __shfl_xor_sync(0xffffffffu, s, 2);
-  return s;
+#pragma unroll
+  for (int r = 0; r < RB; r++) {
+    s[r] = fmaf(k[r][32], last, s[r]);
+    s[r] += __shfl_xor_sync(0xffffffffu, s[r], 1);
+    s[r] += __shfl_xor_sync(0xffffffffu, s[r], 2);
+  }
 }
 
 __global__ void __launch_bounds__(kPatchThreads, 1) sinkhorn_patch_kernel(SinkhornArgs a) {
   extern __shared__ __align__(16) float sm[];
   float* S = sm;                       // padded log scores, row stride 129
-  float* u = sm + kPatchSFloats;       // absorbed log potentials
-  float* v = u + PV;
-  float* la = v + PV;                  // LIN scalings, two buffers each (current / previous iteration)
+  float* la = sm + kPatchSFloats;      // LIN scalings in slot layout, two buffers each (current / previous iteration)
   float* lb = la + 2 * PV;
-  float* mu = lb + 2 * PV;             // linear marginals (0 for masked rows / columns and the pads)
-  float* nu = mu + PV;
-  float* log_mu = nu + PV;
-  float* log_nu = log_mu + PV;
+  float* u = lb + 2 * PV;              // absorbed log potentials (plain layout, padded to 132)
+  float* v = u + PP;
+  float* mu = v + PP;                  // linear marginals (0 for masked rows / columns and the pads)
+  float* nu = mu + PP;
+  float* log_mu = nu + PP;
+  float* log_nu = log_mu + PP;
   const int b = blockIdx.x, tid = threadIdx.x;
-  const int q = tid >> 2, h = tid & 3, c0 = 32 * h;
-  const bool active = q < PR;
-  const int slot = q < PN ? vec_slot(q) : q;     // where element q of a scaling vector lives
+  const bool col_role = tid >= kPatchRoleThreads;
+  const int rt = col_role ? tid - kPatchRoleThreads : tid;
+  const int g = rt >> 2, h = rt & 3;
+  const bool active = g < NG;                    // 44 groups of 3 rows (columns)
+  const bool finisher = active && h < RB;        // lane h < 3 finishes row (column) 3 g + h
+  const int mine = finisher ? RB * g + h : PP - 1;   // pad row otherwise (marginal 0)
   const float alpha = *a.alpha;
   const uint8_t* rm = a.row_mask ? a.row_mask + (size_t)b * PN : nullptr;
   const uint8_t* cm = a.col_mask ? a.col_mask + (size_t)b * PN : nullptr;
@@ -142,7 +165,7 @@ __global__ void __launch_bounds__(kPatchThreads, 1) sinkhorn_patch_kernel(Sinkho
   const float nvr = (float)__syncthreads_count(tid < PN && (!rm || rm[tid]));
   const float nvc = (float)__syncthreads_count(tid < PN && (!cm || cm[tid]));
   const float norm = -logf(nvr + nvc);
-  if (tid < PV) {
+  if (tid < PP) {
     const int i = tid;
     const bool masked_r = i >= PR || (i < PN && rm && !rm[i]);
     const bool masked_c = i >= PR || (i < PN && cm && !cm[i]);
@@ -155,37 +178,86 @@ __global__ void __launch_bounds__(kPatchThreads, 1) sinkhorn_patch_kernel(Sinkho
     u[i] = 0.f;
     v[i] = 0.f;
   }
-  for (int e = tid; e < PR * PR; e += kPatchThreads) {
-    const int i = e / PR, j = e - i * PR;
-    S[i * PLD + j] = sk_score(src, rm, cm, PN, PN, alpha, i, j);
+  for (int e = tid; e < 2 * PV; e += kPatchThreads) {
+    la[e] = 0.f;
+    lb[e] = 0.f;
+  }
+  // padded, masked scores -> S.  The body streams in as 16-byte loads (11 per thread, all in flight together: the
+  // element-wise form with its two mask bytes per element cost 26 us per problem, a fifth of the kernel)
+  {
+    float* mr = la;            // masks as floats, staged in the (not yet used) scaling buffers: 1 = valid
+    float* mc = la + PV;
+    __syncthreads();           // the zero-fill of la / lb above is complete
+    if (tid < PN) {
+      mr[tid] = (!rm || rm[tid]) ? 1.f : 0.f;
+      mc[tid] = (!cm || cm[tid]) ? 1.f : 0.f;
+    }
+    __syncthreads();
+    constexpr int kVec = PN * PN / 4;                              // 4096 float4
+    constexpr int kPer = (kVec + kPatchThreads - 1) / kPatchThreads;
+    float4 val[kPer];
+#pragma unroll
+    for (int q = 0; q < kPer; q++) {
+      const int e = tid + q * kPatchThreads;
+      val[q] = e < kVec ? *reinterpret_cast<const float4*>(src + 4 * (size_t)e) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int q = 0; q < kPer; q++) {
+      const int e = tid + q * kPatchThreads;
+      if (e < kVec) {
+        const int i = e >> 5, j = (e & 31) << 2;
+        const bool ri = mr[i] != 0.f;
+        float* d = S + i * PLD + j;
+        d[0] = (ri && mc[j] != 0.f) ? val[q].x : -kInf;
+        d[1] = (ri && mc[j + 1] != 0.f) ? val[q].y : -kInf;
+        d[2] = (ri && mc[j + 2] != 0.f) ? val[q].z : -kInf;
+        d[3] = (ri && mc[j + 3] != 0.f) ? val[q].w : -kInf;
+      }
+    }
+    if (tid < PN) {                                                // dustbin column and row
+      S[tid * PLD + PN] = mr[tid] != 0.f ? alpha : -kInf;
+      S[PN * PLD + tid] = mc[tid] != 0.f ? alpha : -kInf;
+    }
+    if (tid == 0) S[PN * PLD + PN] = alpha;
+    __syncthreads();
+    for (int e = tid; e < 2 * PV; e += kPatchThreads) la[e] = 0.f;
   }
   __syncthreads();
 
-  float kr[PQ], kc[PQ];   // quarter row / quarter column of the absorbed plan
+  float k[RB][PB];        // this thread's block of the absorbed plan
 #pragma unroll
-  for (int w = 0; w < PQ; w++) kr[w] = kc[w] = 0.f;
+  for (int r = 0; r < RB; r++)
+#pragma unroll
+    for (int c = 0; c < PB; c++) k[r][c] = 0.f;
   int p = 0;              // current scaling buffer
   bool lin = false, need_absorb = false;   // block-uniform
   int it = 0, streak = 0;                  // streak: LIN iterations since the last absorption
   unsigned n_log = 0, n_lin = 0, n_disc = 0, n_abs = 0;
+  const float my_marg = col_role ? nu[mine] : mu[mine];
+  const int my_slot = vec_slot(mine);
   while (it < a.iters) {
     if (need_absorb) {
-      // K = exp(S + u + v) into registers, scalings = 1
+      // K = exp(S + u + v) into registers (zero outside 129 x 129), scalings = 1
       if (active) {
-        const float uq = u[q], vq = v[q];
 #pragma unroll
-        for (int w = 0; w < 32; w++) {
-          kr[w] = sk_exp(S[q * PLD + c0 + w] + uq + v[c0 + w]);
-          kc[w] = sk_exp(S[(c0 + w) * PLD + q] + u[c0 + w] + vq);
+        for (int r = 0; r < RB; r++) {
+          const int x = RB * g + r;                // row (row role) or column (column role)
+#pragma unroll
+          for (int c = 0; c < PB; c++) {
+            const int y = PB * h + c;              // column (row role) or row (column role)
+            float val = 0.f;
+            if (x < PR && y < PR)
+              val = col_role ? sk_exp(S[y * PLD + x] + u[y] + v[x]) : sk_exp(S[x * PLD + y] + u[x] + v[y]);
+            k[r][c] = val;
+          }
         }
-        kr[32] = h == 3 ? sk_exp(S[q * PLD + PN] + uq + v[PN]) : 0.f;
-        kc[32] = h == 3 ? sk_exp(S[PN * PLD + q] + u[PN] + vq) : 0.f;
       }
-      if (tid < PV) {
-        la[p * PV + tid] = tid < PR ? 1.f : 0.f;
-        lb[p * PV + tid] = tid < PR ? 1.f : 0.f;
-        la[(p ^ 1) * PV + tid] = 0.f;
-        lb[(p ^ 1) * PV + tid] = 0.f;
+      if (tid < PP) {
+        const int sl = vec_slot(tid);
+        la[p * PV + sl] = tid < PR ? 1.f : 0.f;
+        lb[p * PV + sl] = tid < PR ? 1.f : 0.f;
+        la[(p ^ 1) * PV + sl] = 0.f;
+        lb[(p ^ 1) * PV + sl] = 0.f;
       }
       __syncthreads();
       need_absorb = false;
@@ -193,43 +265,44 @@ __global__ void __launch_bounds__(kPatchThreads, 1) sinkhorn_patch_kernel(Sinkho
       n_abs++;
     }
     if (lin) {
-      float* a_new = la + (p ^ 1) * PV;
-      float* b_new = lb + (p ^ 1) * PV;
-      bool bad = false;
-      {
-        const float s = dot_quarter(kr, lb + p * PV, h);
-        const float m_ = mu[q];
-        float an = 0.f;
-        if (m_ > 0.f) {
-          an = m_ / s;
-          bad = !(an < kHi && an > kLo);
+      // tight loop over consecutive LIN iterations; leaves on the first out-of-band scaling (fail) or at the end
+      const uint32_t la_s = (uint32_t)__cvta_generic_to_shared(la), lb_s = (uint32_t)__cvta_generic_to_shared(lb);
+      const uint32_t seg_off = 4u * 36u * (uint32_t)h, slot_off = 4u * (uint32_t)my_slot;
+      bool fail = false;
+      while (it < a.iters) {
+        const uint32_t cur = 4u * PV * (uint32_t)p, nxt = 4u * PV * (uint32_t)(p ^ 1);
+        bool bad = false;
+        if (!col_role) {
+          float s[RB];
+          dot_block(k, lb_s + cur + seg_off, s);
+          const float sum = h == 0 ? s[0] : h == 1 ? s[1] : s[2];
+          const float an = my_marg > 0.f ? __fdividef(my_marg, sum) : 0.f;
+          bad = my_marg > 0.f && !(an < kHi && an > kLo);
+          if (finisher) sts32(la_s + nxt + slot_off, an);
         }
-        if (active && h == 0) a_new[slot] = an;
-      }
-      bool fail = __syncthreads_or(bad) != 0;
-      if (!fail) {
-        const float s = dot_quarter(kc, a_new, h);
-        const float n_ = nu[q];
-        float bn = 0.f;
-        bad = false;
-        if (n_ > 0.f) {
-          bn = n_ / s;
-          bad = !(bn < kHi && bn > kLo);
-        }
-        if (active && h == 0) b_new[slot] = bn;
         fail = __syncthreads_or(bad) != 0;
-      }
-      if (!fail) {
+        if (fail) break;
+        bad = false;
+        if (col_role) {
+          float s[RB];
+          dot_block(k, la_s + nxt + seg_off, s);
+          const float sum = h == 0 ? s[0] : h == 1 ? s[1] : s[2];
+          const float bn = my_marg > 0.f ? __fdividef(my_marg, sum) : 0.f;
+          bad = my_marg > 0.f && !(bn < kHi && bn > kLo);
+          if (finisher) sts32(lb_s + nxt + slot_off, bn);
+        }
+        fail = __syncthreads_or(bad) != 0;
+        if (fail) break;
         p ^= 1;
         it++;
         streak++;
         n_lin++;
-        continue;
       }
+      if (!fail) break;      // all iterations done
       // discard this iteration and absorb the previous (consistent) scalings into the potentials
       n_disc++;
       if (tid < PR) {
-        const int sl = tid < PN ? vec_slot(tid) : tid;
+        const int sl = vec_slot(tid);
         const float av = la[p * PV + sl], bv = lb[p * PV + sl];
         if (av > 0.f) u[tid] += logf(av);
         if (bv > 0.f) v[tid] += logf(bv);
@@ -282,7 +355,7 @@ __global__ void __launch_bounds__(kPatchThreads, 1) sinkhorn_patch_kernel(Sinkho
     atomicAdd(&g_sk_stats[3], (unsigned long long)n_abs);
   }
   if (lin && !need_absorb && tid < PR) {
-    const int sl = tid < PN ? vec_slot(tid) : tid;
+    const int sl = vec_slot(tid);
     const float av = la[p * PV + sl], bv = lb[p * PV + sl];
     if (av > 0.f) u[tid] += logf(av);
     if (bv > 0.f) v[tid] += logf(bv);
