@@ -15,6 +15,7 @@
 //              per stage), tcgen05.commit releases the stage / signals the epilogue
 //   warps 0-7  epilogue: tcgen05.ld 32x32b.x32 from TMEM, row scale + bias (+ReLU), 128-B row stores
 // 3-stage shared-memory ring; accumulator: BN fp32 columns of TMEM.
+#include <cuda.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -756,9 +757,8 @@ gemm_tf32x3_ws_kernel(const float* __restrict__ A, int lda, const float* __restr
 // (kind::tf32 truncates it), lo = x - trunc(x); the MMAs read A from TMEM (which has its own read path) and only
 // the W blocks from shared memory: 112 KB per k-block at BN = 128, 52 KB at BN = 32.
 //   TMEM columns: 2 accumulators x BN  +  STAGES x (32 hi + 32 lo) A columns  <= 512.
-//   producer warp pw (physical warp 4 + pw) may touch TMEM lanes 32 (pw % 4) .. + 31: lane = A row 32 (pw % 4) +
-//   lane, columns 16 (pw / 4) .. + 15 of the k-block; its 64 bytes of the row come from four conflict-free
-//   16-byte loads of the swizzled landing buffer.
+//   a producer warp may touch TMEM lanes 32 (warp % 4) .. + 31: thread = A row, all 32 columns of the k-block; its
+//   128 bytes of the row come from eight conflict-free 16-byte loads of the swizzled landing buffer.
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
@@ -778,11 +778,31 @@ __device__ __forceinline__ void mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, ui
       : "memory");
 }
 
-template <int BN, int STAGES>
+// TMA: the operand blocks are fetched by the tensor-memory-accelerator (cp.async.bulk.tensor.2d through 2-D tensor maps
+// with the 128-byte swizzle, one elected thread per producer group issues the three copies of a k-block and arms
+// the stage's transaction barrier) instead of 16-byte cp.async by every producer thread.
+struct TmaMaps {
+  CUtensorMap a, w, w_lo;
+};
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+      "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+
+template <int BN, int STAGES, bool TMA>
 __global__ void __launch_bounds__(kWsThreads, 1)
 gemm_tf32x3_ts_kernel(const float* __restrict__ A, int lda, const float* __restrict__ W, const float* __restrict__ W_lo,
                       int ldw, float* __restrict__ C, int ldc, int M, int N, int K, const float* __restrict__ rowscale,
-                      const float* __restrict__ bias, int relu, const GnFuse gnf) {
+                      const float* __restrict__ bias, int relu, const GnFuse gnf,
+                      const __grid_constant__ TmaMaps maps) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = smem_raw + ((1024u - ((uint32_t)__cvta_generic_to_shared(smem_raw) & 1023u)) & 1023u);
   constexpr int kATile = BM * BK * 4, kBTile = BN * BK * 4;
@@ -790,7 +810,7 @@ gemm_tf32x3_ts_kernel(const float* __restrict__ A, int lda, const float* __restr
   constexpr int kProd = kWsProducerWarps * 32;
   constexpr uint32_t kAccCols = 2 * BN;                     // TMEM: [0, 2 BN) accumulators, then the A stages
   static_assert(kAccCols + STAGES * 64 <= 512, "TMEM budget");
-  __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], acc_full[2], acc_empty[2];
+  __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], acc_full[2], acc_empty[2], tma_bar[STAGES];
   __shared__ uint32_t tmem_base_s;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -802,8 +822,9 @@ gemm_tf32x3_ts_kernel(const float* __restrict__ A, int lda, const float* __restr
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; s++) {
-      mbar_init(&full_bar[s], kWsProducerWarps);
+      mbar_init(&full_bar[s], kWsProducerWarps / 2);   // one arrive per warp of the group that owns the block
       mbar_init(&empty_bar[s], 1);
+      mbar_init(&tma_bar[s], 1);
     }
     for (int b = 0; b < 2; b++) {
       mbar_init(&acc_full[b], 1);
@@ -824,12 +845,31 @@ gemm_tf32x3_ts_kernel(const float* __restrict__ A, int lda, const float* __restr
 
   if (warp >= kWsEpilogueWarps && warp < kMmaWarp) {
     // ================================================================ producers
+    // Two independent groups of four warps, group j streaming the k-blocks g = j (mod 2).  A group's loop per
+    // block -- wait for its copies, barrier, 8 x LDS, split, 2 x tcgen05.st, wait::st, fences, arrive, wait for a
+    // free stage, issue the next copies -- is a chain of latencies (~1000 cycles); with all eight warps in one
+    // lock-step group only one block entered the pipeline per such chain and the bandwidth-bound shapes stalled at
+    // ~3.6 TB/s.  Two chains in flight double the rate at which loads are issued.
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kWsProducerRegs));
-    const int tid = (int)threadIdx.x - kWsEpilogueWarps * 32;   // index among the producer threads
-    const int pw = tid >> 5;                                    // producer warp; physical warp = 4 + pw
+    constexpr int kGrp = 128;                                   // threads per producer group
+    const int ptid = (int)threadIdx.x - kWsEpilogueWarps * 32;  // index among the producer threads
+    const int grp = ptid >> 7, tid = ptid & (kGrp - 1);         // group, index inside the group
     const int total = my_tiles * nk;                            // blocks this CTA streams, tile-major
-    constexpr int kALoads = BM * 8 / kProd, kBLoads = (BN * 8 + kProd - 1) / kProd;
+    constexpr int kALoads = BM * 8 / kGrp, kBLoads = (BN * 8 + kGrp - 1) / kGrp;
     auto issue_block = [&](int g) {
+      if (TMA) {
+        if (g < total && tid == 0) {
+          const int t = (int)blockIdx.x + (g / nk) * (int)gridDim.x;
+          const int m0 = (t / tiles_n) * BM, n0 = (t % tiles_n) * BN, k0 = (g % nk) * BK;
+          const int s = g % STAGES;
+          const uint32_t a_raw = smem_u32(base + s * kStageBytes), b_hi = a_raw + kATile;
+          mbar_expect_tx(&tma_bar[s], (uint32_t)kStageBytes);
+          tma_load_2d(a_raw, &maps.a, k0, m0, &tma_bar[s]);
+          tma_load_2d(b_hi, &maps.w, k0, n0, &tma_bar[s]);
+          tma_load_2d(b_hi + kBTile, &maps.w_lo, k0, n0, &tma_bar[s]);
+        }
+        return;
+      }
       if (g < total) {
         const int t = (int)blockIdx.x + (g / nk) * (int)gridDim.x;
         const int m0 = (t / tiles_n) * BM, n0 = (t % tiles_n) * BN, k0 = (g % nk) * BK;
@@ -837,7 +877,7 @@ gemm_tf32x3_ts_kernel(const float* __restrict__ A, int lda, const float* __restr
         const uint32_t a_raw = smem_u32(base + s * kStageBytes), b_hi = a_raw + kATile;
 #pragma unroll
         for (int i = 0; i < kALoads; i++) {
-          const int idx = tid + i * kProd;
+          const int idx = tid + i * kGrp;
           const int row = idx >> 3, chunk = idx & 7;
           const int gm = m0 + row;
           const float* src = A + (size_t)(gm < M ? gm : 0) * lda + k0 + chunk * 4;
@@ -846,8 +886,8 @@ gemm_tf32x3_ts_kernel(const float* __restrict__ A, int lda, const float* __restr
         }
 #pragma unroll
         for (int i = 0; i < kBLoads; i++) {
-          const int idx = tid + i * kProd;
-          if (BN * 8 % kProd == 0 || idx < BN * 8) {
+          const int idx = tid + i * kGrp;
+          if (BN * 8 % kGrp == 0 || idx < BN * 8) {
             const int row = idx >> 3, chunk = idx & 7;
             const int gn = n0 + row;
             const size_t goff = (size_t)(gn < N ? gn : 0) * ldw + k0 + chunk * 4;
@@ -860,43 +900,55 @@ gemm_tf32x3_ts_kernel(const float* __restrict__ A, int lda, const float* __restr
       }
       asm volatile("cp.async.commit_group;" ::: "memory");   // always: keeps the group count uniform
     };
+    // this group's blocks: g = grp, grp + 2, ...; it keeps kAhead of them in flight (stages g % STAGES are disjoint
+    // between the groups as long as 2 * kAhead <= STAGES)
+    constexpr int kAhead = STAGES / 2;
+    static_assert(kAhead >= 1 && 2 * kAhead <= STAGES, "stage ring too short for two producer groups");
 #pragma unroll
-    for (int g = 0; g < STAGES - 1; g++) issue_block(g);
-    const int arow = 32 * (pw & 3) + lane;                 // A row (= TMEM lane) this thread moves
-    const int ahalf = pw >> 2;                             // which 16 of the 32 k-columns
-    const uint32_t t_lane = (uint32_t)(32 * (pw & 3)) << 16;
-    for (int g = 0; g < total; g++) {
+    for (int j = 0; j < kAhead; j++) issue_block(grp + 2 * j);
+    const int arow = tid;                                  // A row (= TMEM lane) this thread moves: warp quarter = warp % 4
+    const uint32_t t_lane = (uint32_t)(32 * (tid >> 5)) << 16;
+    for (int g = grp; g < total; g += 2) {
       const int s = g % STAGES;
-      asm volatile("cp.async.wait_group %0;" ::"n"(STAGES - 2) : "memory");   // this thread's part of block g landed
-      asm volatile("bar.sync 1, %0;" ::"n"(kProd) : "memory");                // ... and every other producer's
-      const float* a_raw = reinterpret_cast<const float*>(base + s * kStageBytes);
-      uint32_t hi[16], lo[16];
-#pragma unroll
-      for (int c = 0; c < 4; c++) {
-        const int chunk = 4 * ahalf + c;
-        const float4 v = *reinterpret_cast<const float4*>(a_raw + arow * 32 + ((chunk ^ (arow & 7)) << 2));
-        const float x[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-        for (int e = 0; e < 4; e++) {
-          const uint32_t h = __float_as_uint(x[e]);
-          hi[4 * c + e] = h;                                                   // the tensor core truncates it
-          lo[4 * c + e] = __float_as_uint(x[e] - __uint_as_float(h & 0xFFFFE000u));
-        }
+      if (TMA) {
+        mbar_wait(&tma_bar[s], (g / STAGES) & 1);                              // the three copies of block g landed
+        __syncwarp();
+      } else {
+        asm volatile("cp.async.wait_group %0;" ::"n"(kAhead - 1) : "memory");   // this thread's part of block g landed
+        if (grp == 0) asm volatile("bar.sync 1, %0;" ::"n"(kGrp) : "memory");   // ... and the rest of the group's
+        else asm volatile("bar.sync 2, %0;" ::"n"(kGrp) : "memory");
       }
-      const uint32_t t_a = tmem_base + kAccCols + (uint32_t)(s * 64) + t_lane + (uint32_t)(16 * ahalf);
-      tmem_st16(t_a, hi);
-      tmem_st16(t_a + 32, lo);
+      const float* a_raw = reinterpret_cast<const float*>(base + s * kStageBytes);
+      const uint32_t t_a = tmem_base + kAccCols + (uint32_t)(s * 64) + t_lane;
+#pragma unroll
+      for (int half = 0; half < 2; half++) {
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+          const int chunk = 4 * half + c;
+          const float4 v = *reinterpret_cast<const float4*>(a_raw + arow * 32 + ((chunk ^ (arow & 7)) << 2));
+          const float x[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int e = 0; e < 4; e++) {
+            const uint32_t hb = __float_as_uint(x[e]);
+            hi[4 * c + e] = hb;                                                // the tensor core truncates it
+            lo[4 * c + e] = __float_as_uint(x[e] - __uint_as_float(hb & 0xFFFFE000u));
+          }
+        }
+        tmem_st16(t_a + (uint32_t)(16 * half), hi);
+        tmem_st16(t_a + 32 + (uint32_t)(16 * half), lo);
+      }
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       // W blocks (cp.async, generic proxy) -> visible to the async proxy; A block in TMEM -> ordered before the arrive
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(&full_bar[s]);
-      const int nb = g + STAGES - 1;                       // refill the stage block g-1 occupied
-      if (nb < total && g >= 1) mbar_wait(&empty_bar[nb % STAGES], ((nb / STAGES) - 1) & 1);
+      const int nb = g + 2 * kAhead;                       // this group's next block to put in flight
+      if (nb < total && nb >= STAGES && (!TMA || tid == 0)) mbar_wait(&empty_bar[nb % STAGES], ((nb / STAGES) - 1) & 1);
       issue_block(nb);
     }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    if (!TMA) asm volatile("cp.async.wait_group 0;" ::: "memory");
   } else if (warp == kMmaWarp) {
     // ================================================================ MMA issuer (one lane)
     if (lane == 0) {
@@ -984,22 +1036,62 @@ gemm_tf32x3_ts_kernel(const float* __restrict__ A, int lda, const float* __restr
   }
 }
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link dependency on libcuda)
+EncodeTiledFn tensor_map_encoder() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+// 2-D fp32 tensor [rows, cols] with row stride ld (floats): boxes of 32 columns (one 128-byte swizzle row) x box_rows
+bool make_map(CUtensorMap* m, const float* ptr, int rows, int cols, int ld, int box_rows) {
+  EncodeTiledFn enc = tensor_map_encoder();
+  if (!enc) return false;
+  const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+  const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) ==
+         CUDA_SUCCESS;
+}
+
 template <int BN, int STAGES>
 int launch_tc_ts(const float* A, int lda, const float* W, const float* W_lo, int ldw, float* C, int ldc, int M, int N,
-                 int K, const float* rowscale, const float* bias, int relu, const GnFuse& gnf, cudaStream_t stream) {
+                 int K, const float* rowscale, const float* bias, int relu, const GnFuse& gnf, cudaStream_t stream,
+                 bool tma) {
   constexpr size_t smem = (size_t)STAGES * (BM * BK * 4 + 2 * BN * BK * 4) + kWsEpilogueWarps * 32 * 33 * 4 + 1024;
   static_assert(smem <= 227 * 1024, "shared memory budget");
   static LcrOncePerDevice attr_done;
   const int attr_done_dev = attr_done.need();
   if (attr_done_dev != -1) {
-    LCR_CUDA_TRY(cudaFuncSetAttribute(gemm_tf32x3_ts_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)smem));
+    LCR_CUDA_TRY(cudaFuncSetAttribute(gemm_tf32x3_ts_kernel<BN, STAGES, false>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LCR_CUDA_TRY(cudaFuncSetAttribute(gemm_tf32x3_ts_kernel<BN, STAGES, true>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done.done(attr_done_dev);
   }
   const long tiles = (long)((M + BM - 1) / BM) * ((N + BN - 1) / BN);
   const unsigned grid = (unsigned)(tiles < LCR_SM_COUNT ? tiles : LCR_SM_COUNT);
-  gemm_tf32x3_ts_kernel<BN, STAGES><<<grid, kWsThreads, smem, stream>>>(A, lda, W, W_lo, ldw, C, ldc, M, N, K, rowscale,
-                                                                        bias, relu, gnf);
+  TmaMaps maps;
+  if (tma) tma = make_map(&maps.a, A, M, K, lda, BM) && make_map(&maps.w, W, N, K, ldw, BN) &&
+                 make_map(&maps.w_lo, W_lo, N, K, ldw, BN);
+  if (tma)
+    gemm_tf32x3_ts_kernel<BN, STAGES, true><<<grid, kWsThreads, smem, stream>>>(A, lda, W, W_lo, ldw, C, ldc, M, N, K,
+                                                                                rowscale, bias, relu, gnf, maps);
+  else
+    gemm_tf32x3_ts_kernel<BN, STAGES, false><<<grid, kWsThreads, smem, stream>>>(A, lda, W, W_lo, ldw, C, ldc, M, N, K,
+                                                                                 rowscale, bias, relu, gnf, maps);
   return LCR_OK;
 }
 
@@ -1070,11 +1162,14 @@ __global__ void tf32_split_kernel(const float* __restrict__ w, int64_t n, float*
 template <bool PS>
 int gemm_dispatch(const float* A, int lda, const float* W, const float* W_lo, int ldw, float* C, int ldc, int M, int N,
                   int K, const float* rowscale, const float* bias, int relu, const GnFuse& gnf, cudaStream_t stream) {
-  static const int ws = getenv("LCR_GEMM_WS") ? atoi(getenv("LCR_GEMM_WS")) : 3;   // 3: A operand in TMEM (default)
-  if (PS && (ws == 4 || (ws == 3 && K > 4 * BK))) {   // persistent kernel with the A operand in tensor memory
-    if (N <= 32) return launch_tc_ts<32, 6>(A, lda, W, W_lo, ldw, C, ldc, M, N, K, rowscale, bias, relu, gnf, stream);
-    if (N <= 64) return launch_tc_ts<64, 5>(A, lda, W, W_lo, ldw, C, ldc, M, N, K, rowscale, bias, relu, gnf, stream);
-    return launch_tc_ts<128, 4>(A, lda, W, W_lo, ldw, C, ldc, M, N, K, rowscale, bias, relu, gnf, stream);
+  static const int ws = getenv("LCR_GEMM_WS") ? atoi(getenv("LCR_GEMM_WS")) : 5;   // 5: A operand in TMEM, TMA loads (default)
+  if (PS && (ws >= 3 && ws <= 6) && ((ws & 1) == 0 || K > 4 * BK)) {   // persistent kernel, A operand in tensor memory
+    const bool tma = ws >= 5;                                             // 5 / 6: operand blocks fetched by TMA
+    // stages: as many as tensor memory allows (2 BN accumulator columns + 64 per stage <= 512): the narrow shapes are
+    // bound by the bytes in flight (ncu: nothing above 46 %, DRAM latency ~2 us under load)
+    if (N <= 32) return launch_tc_ts<32, 7>(A, lda, W, W_lo, ldw, C, ldc, M, N, K, rowscale, bias, relu, gnf, stream, tma);
+    if (N <= 64) return launch_tc_ts<64, 6>(A, lda, W, W_lo, ldw, C, ldc, M, N, K, rowscale, bias, relu, gnf, stream, tma);
+    return launch_tc_ts<128, 4>(A, lda, W, W_lo, ldw, C, ldc, M, N, K, rowscale, bias, relu, gnf, stream, tma);
   }
   if (PS && (ws == 2 || (ws == 1 && K > 4 * BK))) {   // persistent warp-specialised kernel (needs the pre-split weights)
     if (N <= 32) return launch_tc_ws<32, 5>(A, lda, W, W_lo, ldw, C, ldc, M, N, K, rowscale, bias, relu, gnf, stream);
