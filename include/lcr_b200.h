@@ -339,6 +339,19 @@ int lcr_lgr_batched(const float* ref, const float* src, const float* scores, con
                     int n_scan_pairs, int64_t capacity, float radius, int min_corr, int steps, float* out_T, void* ws,
                     size_t ws_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * RANSAC rigid registration from correspondences (utils/utils/open3d.py:145-173:
+ * open3d registration_ransac_based_on_correspondence, point-to-point estimation, ransac_n = 3,
+ * distance_threshold = 0.05, num_iterations = 10000).  src / ref float[n,3] device (correspondence t =
+ * (src[t], ref[t])); out_T float[16] row-major (maps src -> ref), out_best int32[2] = {winning
+ * hypothesis, its inlier count}.  Sample k of hypothesis h = hash(seed, h, k) % n (reproducible; the
+ * oracle evaluates the same samples).  open3d itself is third party: parity unpinned at that boundary.
+ * ---------------------------------------------------------------------------------------- */
+size_t lcr_ransac_ws_bytes(int num_iterations);
+int lcr_ransac_correspondences(const float* src, const float* ref, int64_t n, float distance_threshold, int ransac_n,
+                               int num_iterations, uint64_t seed, float* out_T, int32_t* out_best, void* ws,
+                               size_t ws_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -84,6 +84,8 @@ SIGNATURES = {
     'lcr_lgr_batched_ws_bytes': (c_sz, [c_i32, c_i32, c_i64]),
     'lcr_lgr_batched': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_vp, c_i32, c_i64, c_f32, c_i32, c_i32, c_vp,
                                 c_vp, c_sz, c_vp]),
+    'lcr_ransac_ws_bytes': (c_sz, [c_i32]),
+    'lcr_ransac_correspondences': (c_i32, [c_vp, c_vp, c_i64, c_f32, c_i32, c_i32, ctypes.c_uint64, c_vp, c_vp, c_vp, c_sz, c_vp]),
     'lcr_l2_topk': (c_i32, [c_vp, c_i64, c_vp, c_i64, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp]),
 }
 
