@@ -82,6 +82,12 @@ int lcr_radius_neighbors(const float* q_points, int64_t nq_total, const float* s
                          const int64_t* q_lengths, const int64_t* s_lengths, int batch, float radius,
                          int width, void* out_idx, int idx_is64, int32_t* out_counts,
                          int32_t* out_max_count, int32_t* out_status, void* ws, size_t ws_bytes, void* stream);
+/* As above; reuse_grid != 0 skips the support-grid build and reuses the one a previous call left in `ws` (same ws
+ * pointer, supports, support lengths, batch and radius): the pyramid asks three tables per support level. */
+int lcr_radius_neighbors_ex(const float* q_points, int64_t nq_total, const float* s_points, int64_t ns_total,
+                            const int64_t* q_lengths, const int64_t* s_lengths, int batch, float radius, int width,
+                            void* out_idx, int idx_is64, int32_t* out_counts, int32_t* out_max_count,
+                            int32_t* out_status, void* ws, size_t ws_bytes, int reuse_grid, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * a4. KPConv forward.  Replaces KPConv.forward (experiments/lcrnet/modules/kpconv/kpconv.py:79-122).

@@ -27,6 +27,8 @@ SIGNATURES = {
     'lcr_radius_neighbors_ws_bytes': (c_sz, [c_i64, c_i64, c_i32]),
     'lcr_radius_neighbors': (c_i32, [c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_i32, c_f32, c_i32, c_vp, c_i32, c_vp,
                                      c_vp, c_vp, c_vp, c_sz, c_vp]),
+    'lcr_radius_neighbors_ex': (c_i32, [c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_i32, c_f32, c_i32, c_vp, c_i32, c_vp,
+                                        c_vp, c_vp, c_vp, c_sz, c_i32, c_vp]),
     'lcr_kpconv_ws_bytes': (c_sz, [c_i64, c_i32]),
     'lcr_kpconv_ws_bytes2': (c_sz, [c_i64, c_i64, c_i32]),
     'lcr_kpconv': (c_i32, [c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_f32, c_vp, c_vp,

@@ -391,11 +391,30 @@ extern "C" size_t lcr_radius_neighbors_ws_bytes(int64_t nq_total, int64_t ns_tot
   return carve(w, nullptr, 0, nq_total > 0 ? nq_total : 1, ns_total > 0 ? ns_total : 1, batch > 0 ? batch : 1);
 }
 
+extern "C" int lcr_radius_neighbors_ex(const float* q_points, int64_t nq_total, const float* s_points,
+                                       int64_t ns_total, const int64_t* q_lengths, const int64_t* s_lengths, int batch,
+                                       float radius, int width, void* out_idx, int idx_is64, int32_t* out_counts,
+                                       int32_t* out_max_count, int32_t* out_status, void* ws, size_t ws_bytes,
+                                       int reuse_grid, void* stream_);
+
 extern "C" int lcr_radius_neighbors(const float* q_points, int64_t nq_total, const float* s_points,
                                     int64_t ns_total, const int64_t* q_lengths, const int64_t* s_lengths, int batch,
                                     float radius, int width, void* out_idx, int idx_is64, int32_t* out_counts,
                                     int32_t* out_max_count, int32_t* out_status, void* ws, size_t ws_bytes,
                                     void* stream_) {
+  return lcr_radius_neighbors_ex(q_points, nq_total, s_points, ns_total, q_lengths, s_lengths, batch, radius, width,
+                                 out_idx, idx_is64, out_counts, out_max_count, out_status, ws, ws_bytes, 0, stream_);
+}
+
+// reuse_grid != 0: the support grid in `ws` (built by a previous call with the SAME ws pointer, supports, support
+// lengths, batch and radius) is reused; only the query side is processed.  The pyramid asks three tables of every
+// support level at the same radius (self, subsampling of the next level, upsampling of the previous one,
+// data.py:28-66): one grid build instead of three.
+extern "C" int lcr_radius_neighbors_ex(const float* q_points, int64_t nq_total, const float* s_points,
+                                       int64_t ns_total, const int64_t* q_lengths, const int64_t* s_lengths, int batch,
+                                       float radius, int width, void* out_idx, int idx_is64, int32_t* out_counts,
+                                       int32_t* out_max_count, int32_t* out_status, void* ws, size_t ws_bytes,
+                                       int reuse_grid, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   LCR_REQUIRE(batch >= 1 && batch < (1 << 20), "radius_neighbors: batch out of range");
   LCR_REQUIRE(nq_total >= 0 && ns_total >= 0 && nq_total < (1ll << 31) && ns_total < (1ll << 31),
@@ -423,15 +442,18 @@ extern "C" int lcr_radius_neighbors(const float* q_points, int64_t nq_total, con
   const double idx_bytes = out_idx ? (idx_is64 ? 8.0 : 4.0) * (double)nq_total * width : 0.0;
   LcrProfScope prof_all("radius_total", 0.0, 12.0 * (nq_total + ns_total) + idx_bytes, stream);
   lcr_offsets_launch(q_lengths, batch, w.q_off, stream);
-  lcr_offsets_launch(s_lengths, batch, w.s_off, stream);
-  lcr_bbox_launch(s_points, ns_total, w.s_off, batch, w.bbox, stream);
-  grid_geom_kernel<<<(batch + T - 1) / T, T, 0, stream>>>(w.bbox, batch, w.geom);
-  LCR_CUDA_TRY(cudaMemsetAsync(w.tkeys, 0xFF, sizeof(unsigned long long) * w.tcap, stream));
-  LCR_CUDA_TRY(cudaMemsetAsync(w.tcount, 0, sizeof(uint32_t) * w.tcap, stream));
-  LCR_CUDA_TRY(cudaMemsetAsync(w.tcursor, 0, sizeof(uint32_t) * w.tcap, stream));
   LCR_CUDA_TRY(cudaMemsetAsync(w.spill_n, 0, sizeof(uint32_t), stream));
   if (!out_status) LCR_CUDA_TRY(cudaMemsetAsync(w.err, 0, sizeof(int), stream));
-  if (ns_total > 0) {
+  const bool build = !reuse_grid;
+  if (build) {
+    lcr_offsets_launch(s_lengths, batch, w.s_off, stream);
+    lcr_bbox_launch(s_points, ns_total, w.s_off, batch, w.bbox, stream);
+    grid_geom_kernel<<<(batch + T - 1) / T, T, 0, stream>>>(w.bbox, batch, w.geom);
+    LCR_CUDA_TRY(cudaMemsetAsync(w.tkeys, 0xFF, sizeof(unsigned long long) * w.tcap, stream));
+    LCR_CUDA_TRY(cudaMemsetAsync(w.tcount, 0, sizeof(uint32_t) * w.tcap, stream));
+    LCR_CUDA_TRY(cudaMemsetAsync(w.tcursor, 0, sizeof(uint32_t) * w.tcap, stream));
+  }
+  if (build && ns_total > 0) {
     const unsigned gridS = (unsigned)((ns_total + T - 1) / T);
     cell_insert_kernel<<<gridS, T, 0, stream>>>(s_points, ns_total, w.s_off, batch, w.geom, inv_cell, w.tkeys,
                                                 w.tcount, w.tcap - 1, w.slot_of, err);
@@ -475,7 +497,7 @@ extern "C" int lcr_radius_neighbors(const float* q_points, int64_t nq_total, con
           ns_total, (int32_t*)out_idx, w.spill_list, w.spill_n, err);
     }
   }
-  LCR_LAUNCHED(2 + (ns_total > 0 ? 2 : 0) + (out_idx ? 1 : 0));  // geom, query, insert, scatter, spill
+  LCR_LAUNCHED(1 + (build ? 1 : 0) + (build && ns_total > 0 ? 2 : 0) + (out_idx ? 1 : 0));  // query, geom, insert, scatter, spill
   LCR_CUDA_CHECK_LAUNCH();
   return LCR_OK;
 }

@@ -31,18 +31,27 @@ def precompute_data_stack_mode(points, lengths, num_stages, voxel_size, radius, 
         points_list.append(points)
         lengths_list.append(lengths)
         voxel_size *= 2
+    # one support grid per level (supports = level i, radius r_i): the self table, the subsampling table of level
+    # i + 1 and the upsampling table of level i - 1 (radius 2 r_{i-1} = r_i) all search it
+    radii = [radius * 2 ** i for i in range(num_stages)]
+    rows = [p.shape[0] for p in points_list]
+    grids = [ext.SupportGrid(points_list[i], lengths_list[i], radii[i], max(rows[max(i - 1, 0):i + 2]))
+             if points_list[i].is_cuda else None for i in range(num_stages)]
+    upsampling_list = [None] * (num_stages - 1)
     for i in range(num_stages):
         cur_points, cur_lengths = points_list[i], lengths_list[i]
-        neighbors_list.append(ops.radius_search(cur_points, cur_points, cur_lengths, cur_lengths, radius,
-                                                neighbor_limits[i], int32=int32, defer=defer))
+        neighbors_list.append(ops.radius_search(cur_points, cur_points, cur_lengths, cur_lengths, radii[i],
+                                                neighbor_limits[i], int32=int32, defer=defer, grid=grids[i]))
         if i < num_stages - 1:
             sub_points, sub_lengths = points_list[i + 1], lengths_list[i + 1]
-            subsampling_list.append(ops.radius_search(sub_points, cur_points, sub_lengths, cur_lengths, radius,
-                                                      neighbor_limits[i], int32=int32, defer=defer))
-            if upsampling:
-                upsampling_list.append(ops.radius_search(cur_points, sub_points, cur_lengths, sub_lengths, radius * 2,
-                                                         neighbor_limits[i + 1], int32=int32, defer=defer))
-        radius *= 2
+            subsampling_list.append(ops.radius_search(sub_points, cur_points, sub_lengths, cur_lengths, radii[i],
+                                                      neighbor_limits[i], int32=int32, defer=defer, grid=grids[i]))
+        if i > 0 and upsampling:
+            fine_points, fine_lengths = points_list[i - 1], lengths_list[i - 1]
+            upsampling_list[i - 1] = ops.radius_search(fine_points, cur_points, fine_lengths, cur_lengths, radii[i],
+                                                       neighbor_limits[i], int32=int32, defer=defer, grid=grids[i])
+    if not upsampling:
+        upsampling_list = []
     if defer:
         n_len = lengths_list[0].numel() * num_stages
         both = torch.cat([torch.stack(lengths_list).reshape(-1)] + [m.to(torch.int64) for m in defer]).cpu()

@@ -60,12 +60,25 @@ def grid_subsampling(points, lengths, voxel_size, order='reference'):
     return [s_points, s_lengths]
 
 
-def radius_neighbors(q_points, s_points, q_lengths, s_lengths, radius, limit=0, int32=False, defer=None):
+class SupportGrid:
+    """The uniform grid of one support set at one radius, kept in its own workspace so that several searches
+    (self / subsampling / upsampling tables of a pyramid level, data.py:28-66) build it once."""
+
+    def __init__(self, s_points, s_lengths, radius, max_queries):
+        self.key = (s_points.data_ptr(), s_points.shape[0], s_lengths.data_ptr(), float(radius))
+        nbytes = _lib.lib().lcr_radius_neighbors_ws_bytes(int(max_queries), s_points.shape[0], s_lengths.shape[0])
+        self.ws = torch.empty(int(nbytes) + 256, dtype=torch.uint8, device=s_points.device)
+        self.max_queries = int(max_queries)
+        self.built = False
+
+
+def radius_neighbors(q_points, s_points, q_lengths, s_lengths, radius, limit=0, int32=False, defer=None, grid=None):
     """``utils.ext.radius_neighbors`` (radius_neighbors.cpp:5-68): (Nq, max_count) int64 table,
     padded with Ns.  ``limit`` > 0 fuses the ``[:, :limit]`` cut of ops/radius_search.py:25-26.
     ``defer`` (a list, with ``limit`` > 0): do not read the [max_count, status] words back -- the table keeps
     ``limit`` columns (pads = Ns) and the device words are appended to the list for ONE later check
-    (``check_deferred``): the pyramid builder queues its 7-10 searches without draining the stream."""
+    (``check_deferred``): the pyramid builder queues its 7-10 searches without draining the stream.
+    ``grid`` (SupportGrid of these supports and this radius): built by the first search that uses it, reused after."""
     for name, t in (('q_points', q_points), ('s_points', s_points)):
         _check(t.dtype == torch.float32, '%s must be a float tensor' % name)
         _check(t.is_contiguous(), '%s must be contiguous' % name)
@@ -82,15 +95,25 @@ def radius_neighbors(q_points, s_points, q_lengths, s_lengths, radius, limit=0, 
     L = _lib.lib()
     dev = q.device
     meta = torch.zeros(2, dtype=torch.int32, device=dev)  # [max_count, status]
-    ws_bytes = L.lcr_radius_neighbors_ws_bytes(nq, ns, b)
-    ws = _lib.workspace.get(ws_bytes, dev)
+    if grid is not None and not on_cpu:
+        _check(grid.key == (s.data_ptr(), ns, sl.data_ptr(), float(radius)) and nq <= grid.max_queries,
+               'radius_neighbors: the SupportGrid belongs to other supports / radius')
+        ws = grid.ws
+    else:
+        grid = None
+        ws_bytes = L.lcr_radius_neighbors_ws_bytes(nq, ns, b)
+        ws = _lib.workspace.get(ws_bytes, dev)
     stream = _lib.stream_ptr(dev)
     dtype = torch.int32 if int32 else torch.int64
 
     def run(width, out):
-        _lib.check(L.lcr_radius_neighbors(_lib.ptr(q), nq, _lib.ptr(s), ns, _lib.ptr(ql), _lib.ptr(sl), b,
-                                          float(radius), width, _lib.ptr(out), 0 if int32 else 1, None,
-                                          _lib.ptr(meta), _lib.ptr(meta[1:]), _lib.ptr(ws), ws.numel(), stream))
+        reuse = 1 if (grid is not None and grid.built) else 0
+        _lib.check(L.lcr_radius_neighbors_ex(_lib.ptr(q), nq, _lib.ptr(s), ns, _lib.ptr(ql), _lib.ptr(sl), b,
+                                             float(radius), width, _lib.ptr(out), 0 if int32 else 1, None,
+                                             _lib.ptr(meta), _lib.ptr(meta[1:]), _lib.ptr(ws), ws.numel(), reuse,
+                                             stream))
+        if grid is not None:
+            grid.built = True
 
     if limit and limit > 0:
         out = torch.empty((nq, limit), dtype=dtype, device=dev)

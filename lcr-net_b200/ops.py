@@ -21,12 +21,12 @@ def grid_subsample(points, lengths, voxel_size, order='reference'):
     return s_points, s_lengths
 
 
-def radius_search(q_points, s_points, q_lengths, s_lengths, radius, neighbor_limit, int32=False, defer=None):
+def radius_search(q_points, s_points, q_lengths, s_lengths, radius, neighbor_limit, int32=False, defer=None, grid=None):
     """ops/radius_search.py:7-27 (the ``[:, :neighbor_limit]`` cut is fused into the kernel).
-    ``defer``: see ext.radius_neighbors."""
+    ``defer`` / ``grid``: see ext.radius_neighbors."""
     return ext.radius_neighbors(q_points, s_points, q_lengths, s_lengths, radius,
                                 limit=neighbor_limit if neighbor_limit and neighbor_limit > 0 else 0, int32=int32,
-                                defer=defer)
+                                defer=defer, grid=grid)
 
 
 def _f32c(t):
