@@ -21,13 +21,18 @@
 //   spill : queries with more hits than the warp buffer are queued and handled by a second
 //           kernel, one CTA per query with an 8192-key buffer.
 // No host synchronisation anywhere.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
 
 constexpr uint64_t kEmpty = 0xFFFFFFFFFFFFFFFFull;
-constexpr int kCellBits = 14;  // cells per axis < 16384
-constexpr int kCellMax = (1 << kCellBits) - 1;
+constexpr int kCellBits = 14;  // key field per axis
+// Supports may span at most 2048 cells per axis: beyond that the fp32 rounding of (x - o) * inv_cell can exceed the
+// 0.1 % cell margin (cell edge 1.001 r) that keeps every neighbour inside the 27-cell stencil.  KITTI-scale clouds
+// span ~130 cells at level 0.  (Query cells are clamped to [-1, kCellMax + 1] and keyed with a +1 shift.)
+constexpr int kCellMax = 2047;
 constexpr int kWarpCap = 512;     // keys per warp buffer
 constexpr int kWarpsPerCta = 8;   // query kernel: 256 threads
 constexpr int kSpillCap = LCR_RADIUS_MAX_WIDTH;  // keys per CTA in the spill kernel
@@ -194,6 +199,45 @@ __device__ __forceinline__ void sort_and_write(const unsigned long long* keys, i
   for (int t = R * 32 + lane; t < width; t += 32) row[t] = (IdxT)ns_total;
 }
 
+// Tail of a query: count / running maximum, then sort the hits and write the first `width` (or queue the query for
+// the spill kernel when it has more hits than the warp buffer).
+template <typename IdxT>
+__device__ __forceinline__ void finish_query(unsigned long long* keys, int total, int lane, int64_t qi, int width,
+                                             int64_t ns_total, IdxT* __restrict__ out_idx,
+                                             int32_t* __restrict__ out_counts, int32_t* __restrict__ out_max,
+                                             uint32_t* __restrict__ spill_list, uint32_t* __restrict__ spill_n,
+                                             int cap = kWarpCap) {
+  if (lane == 0) {
+    if (out_counts) out_counts[qi] = total;
+    // widest row so far: a (possibly stale) plain read filters almost every warp, so the warps of a CTA need no
+    // block-level reduction and retire independently (ncu: 14 % of the warp samples sat in that final barrier)
+    if (total > *reinterpret_cast<volatile int32_t*>(out_max)) atomicMax(out_max, total);
+  }
+  if (out_idx == nullptr) return;
+  if (total <= cap) {
+    IdxT* row = out_idx + (size_t)qi * width;
+    __syncwarp();
+    if (total <= 32) {
+      sort_and_write<1>(keys, total, lane, row, width, ns_total);
+    } else if (total <= 64) {
+      sort_and_write<2>(keys, total, lane, row, width, ns_total);
+    } else if (total <= 128) {
+      sort_and_write<4>(keys, total, lane, row, width, ns_total);
+    } else if (total <= 256) {
+      sort_and_write<8>(keys, total, lane, row, width, ns_total);
+    } else {
+      int n = 512;
+      for (int i = total + lane; i < n; i += 32) keys[i] = kEmpty;
+      __syncwarp();
+      bitonic_sort<false>(keys, n, lane, 32);
+      for (int t = lane; t < width; t += 32)
+        row[t] = t < total ? (IdxT)(uint32_t)(keys[t] & 0xFFFFFFFFull) : (IdxT)ns_total;
+    }
+  } else if (lane == 0) {
+    spill_list[atomicAdd(spill_n, 1u)] = (uint32_t)qi;
+  }
+}
+
 template <typename IdxT>
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
 query_kernel(const float* __restrict__ q, int64_t nq, const int64_t* __restrict__ q_off, int batch,
@@ -256,35 +300,121 @@ query_kernel(const float* __restrict__ q, int64_t nq, const int64_t* __restrict_
       }
       total += __popc(m);
     }
-    if (lane == 0) {
-      if (out_counts) out_counts[qi] = total;
-      // widest row so far: a (possibly stale) plain read filters almost every warp, so the warps of a CTA need no
-      // block-level reduction and retire independently (ncu: 14 % of the warp samples sat in that final barrier)
-      if (total > *reinterpret_cast<volatile int32_t*>(out_max)) atomicMax(out_max, total);
+    finish_query<IdxT>(keys, total, lane, qi, width, ns_total, out_idx, out_counts, out_max, spill_list, spill_n);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Self tables (queries == supports: four of the seven tables of a pyramid, 73 % of the query time): one warp per
+// occupied CELL instead of per query.  The ~8 queries of a cell share their 27-cell stencil, so the hash lookups,
+// the run prefix sums and the candidate loads happen once per cell: the candidates (~230 float4) are staged in
+// shared memory and every query of the cell walks them with one LDS.128 per lane and step -- the per-query kernel
+// spent half of its instructions on the 5-step binary search that maps a flat candidate index to its run, for
+// every query anew.  Cells are handed out through an atomic counter (costs differ by 100x between a sparse cell
+// and a dense one near the sensor); a cell with more candidates than the stage falls back to the flat stream.
+constexpr int kCellWarps = 4;        // warps per CTA
+constexpr int kCellCand = 512;       // staged candidates per warp (8 KB)
+constexpr int kCellKeys = 256;       // hit keys per warp (2 KB); more hits -> spill kernel
+
+__global__ void compact_cells_kernel(const unsigned long long* __restrict__ tkeys, uint32_t n_slots,
+                                     uint32_t* __restrict__ occ_list, uint32_t* __restrict__ n_occ) {
+  const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool occ = s < n_slots && tkeys[s] != kEmpty;
+  const unsigned m = __ballot_sync(0xffffffffu, occ);
+  if (m == 0) return;
+  const int lane = threadIdx.x & 31;
+  uint32_t base = 0;
+  if (lane == 0) base = atomicAdd(n_occ, (uint32_t)__popc(m));
+  base = __shfl_sync(0xffffffffu, base, 0);
+  if (occ) occ_list[base + __popc(m & ((1u << lane) - 1u))] = s;
+}
+
+template <typename IdxT>
+__global__ void __launch_bounds__(kCellWarps * 32)
+query_self_kernel(const uint32_t* __restrict__ occ_list, const uint32_t* __restrict__ n_occ,
+                  uint32_t* __restrict__ next_cell, float r2, const unsigned long long* __restrict__ tkeys,
+                  const uint32_t* __restrict__ tstart, const uint32_t* __restrict__ tcount, uint64_t tmask,
+                  const float4* __restrict__ sorted, int width, int64_t ns_total, IdxT* __restrict__ out_idx,
+                  int32_t* __restrict__ out_counts, int32_t* __restrict__ out_max,
+                  uint32_t* __restrict__ spill_list, uint32_t* __restrict__ spill_n) {
+  __shared__ __align__(16) float4 s_cand[kCellWarps][kCellCand];
+  __shared__ unsigned long long s_keys[kCellWarps][kCellKeys];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float4* cand = s_cand[warp];
+  unsigned long long* keys = s_keys[warp];
+  const uint32_t n_cells = *n_occ;
+  const bool want_idx = out_idx != nullptr;
+  while (true) {
+    uint32_t ci = 0;
+    if (lane == 0) ci = atomicAdd(next_cell, 1u);
+    ci = __shfl_sync(0xffffffffu, ci, 0);
+    if (ci >= n_cells) break;
+    const uint32_t slot = occ_list[ci];
+    const unsigned long long key = tkeys[slot];
+    const int b = (int)(key >> (3 * kCellBits));
+    const int cz = (int)((key >> (2 * kCellBits)) & ((1u << kCellBits) - 1u));
+    const int cy = (int)((key >> kCellBits) & ((1u << kCellBits) - 1u));
+    const int cx = (int)(key & ((1u << kCellBits) - 1u));
+    const uint32_t q_start = tstart[slot], q_n = tcount[slot];
+    uint32_t c_start = 0, c_count = 0;
+    if (lane < 27) {
+      const int nx = cx + (lane % 3) - 1, ny = cy + ((lane / 3) % 3) - 1, nz = cz + (lane / 9) - 1;
+      if (nx >= 0 && ny >= 0 && nz >= 0 && nx <= kCellMax && ny <= kCellMax && nz <= kCellMax)
+        lookup_cell(cell_key(b, nx, ny, nz), tkeys, tstart, tcount, tmask, c_start, c_count);
     }
-    if (want_idx) {
-      if (total <= kWarpCap) {
-        IdxT* row = out_idx + (size_t)qi * width;
-        __syncwarp();
-        if (total <= 32) {
-          sort_and_write<1>(keys, total, lane, row, width, ns_total);
-        } else if (total <= 64) {
-          sort_and_write<2>(keys, total, lane, row, width, ns_total);
-        } else if (total <= 128) {
-          sort_and_write<4>(keys, total, lane, row, width, ns_total);
-        } else if (total <= 256) {
-          sort_and_write<8>(keys, total, lane, row, width, ns_total);
-        } else {
-          int n = 512;
-          for (int i = total + lane; i < n; i += 32) keys[i] = kEmpty;
-          __syncwarp();
-          bitonic_sort<false>(keys, n, lane, 32);
-          for (int t = lane; t < width; t += 32)
-            row[t] = t < total ? (IdxT)(uint32_t)(keys[t] & 0xFFFFFFFFull) : (IdxT)ns_total;
-        }
-      } else if (lane == 0) {
-        spill_list[atomicAdd(spill_n, 1u)] = (uint32_t)qi;
+    uint32_t incl = c_count;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    const uint32_t excl = incl - c_count;
+    const uint32_t n_cand = __shfl_sync(0xffffffffu, incl, 31);
+    const bool staged = n_cand <= (uint32_t)kCellCand;
+    // candidate c of the flat stream -> its float4 in the cell-ordered support copy
+    auto fetch = [&](uint32_t c) -> float4 {
+      int run = 0;
+#pragma unroll
+      for (int step = 16; step > 0; step >>= 1) {
+        const uint32_t e = __shfl_sync(0xffffffffu, excl, run + step);
+        if (e <= c) run += step;
       }
+      const uint32_t st = __shfl_sync(0xffffffffu, c_start, run), ex = __shfl_sync(0xffffffffu, excl, run);
+      return c < n_cand ? sorted[st + (c - ex)] : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    __syncwarp();
+    if (staged)
+      for (uint32_t base = 0; base < n_cand; base += 32) {
+        const float4 p = fetch(base + lane);
+        if (base + lane < n_cand) cand[base + lane] = p;
+      }
+    __syncwarp();
+    for (uint32_t qk = 0; qk < q_n; qk++) {
+      const float4 qp = sorted[q_start + qk];
+      const int64_t qi = (int64_t)__float_as_uint(qp.w);
+      int total = 0;
+      for (uint32_t base = 0; base < n_cand; base += 32) {
+        const uint32_t c = base + lane;
+        float4 p;
+        if (staged) p = c < n_cand ? cand[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+        else p = fetch(c);
+        bool hit = false;
+        unsigned long long k = 0;
+        if (c < n_cand) {
+          const float d2 = ref_d2(qp.x, qp.y, qp.z, p.x, p.y, p.z);
+          hit = d2 < r2;
+          k = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned long long)__float_as_uint(p.w);
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        if (hit && want_idx) {
+          const int pos = total + __popc(m & ((1u << lane) - 1u));
+          if (pos < kCellKeys) keys[pos] = k;
+        }
+        total += __popc(m);
+      }
+      finish_query<IdxT>(keys, total, lane, qi, width, ns_total, out_idx, out_counts, out_max, spill_list, spill_n,
+                         kCellKeys);
+      __syncwarp();
     }
   }
 }
@@ -356,6 +486,7 @@ struct RadiusWs {
   uint32_t *tcount, *tstart, *tcursor, *partials, *scan_total;
   uint32_t* slot_of;
   float4* sorted;
+  uint32_t *occ_list, *n_occ, *next_cell;
   uint32_t *spill_list, *spill_n;
   int* err;
   uint64_t tcap;
@@ -378,6 +509,9 @@ size_t carve(RadiusWs& w, void* ws, size_t ws_bytes, int64_t nq, int64_t ns, int
   w.scan_total = a.take<uint32_t>(1);
   w.slot_of = a.take<uint32_t>(ns);
   w.sorted = a.take<float4>(ns);
+  w.occ_list = a.take<uint32_t>(ns);
+  w.n_occ = a.take<uint32_t>(1);
+  w.next_cell = a.take<uint32_t>(1);
   w.spill_list = a.take<uint32_t>(nq);
   w.spill_n = a.take<uint32_t>(1);
   w.err = a.take<int>(1);
@@ -460,15 +594,43 @@ extern "C" int lcr_radius_neighbors_ex(const float* q_points, int64_t nq_total, 
     int rc = lcr_scan_u32(w.tcount, w.tstart, (int64_t)w.tcap, w.scan_total, w.partials, stream);
     if (rc != LCR_OK) return rc;
     cell_scatter_kernel<<<gridS, T, 0, stream>>>(s_points, ns_total, w.slot_of, w.tstart, w.tcursor, w.sorted);
+    LCR_CUDA_TRY(cudaMemsetAsync(w.n_occ, 0, sizeof(uint32_t), stream));
+    compact_cells_kernel<<<(unsigned)((w.tcap + T - 1) / T), T, 0, stream>>>(w.tkeys, (uint32_t)w.tcap, w.occ_list, w.n_occ);
   }
   LcrProfScope prof("radius_query", 0.0, 12.0 * (nq_total + ns_total) + idx_bytes, stream);
   const unsigned gridQ = (unsigned)((nq_total + kWarpsPerCta - 1) / kWarpsPerCta);
   const size_t spill_smem = sizeof(unsigned long long) * kSpillCap;
-  if (idx_is64) {
-    query_kernel<int64_t><<<gridQ, kWarpsPerCta * 32, 0, stream>>>(
-        q_points, nq_total, w.q_off, batch, w.geom, inv_cell, r2, w.tkeys, w.tstart, w.tcount, w.tcap - 1, w.sorted,
-        width, ns_total, (int64_t*)out_idx, out_counts, out_max_count, w.spill_list, w.spill_n);
-    if (out_idx) {
+  // self table: the queries ARE the supports (same arrays), so the support grid also groups the queries by cell
+  static const int cell_mode = getenv("LCR_RADIUS_CELLS") ? atoi(getenv("LCR_RADIUS_CELLS")) : 1;
+  // (measured, 64 scans: level 0, 909 k points: 1.10 -> 0.90 ms, level 1, 361 k: 0.46 -> 0.43 ms; the small levels
+  // have too few cells to fill the persistent grid and stay on the per-query kernel.  What remains is the sort of
+  // the hits: ~300 of the ~500 instructions per query.)
+  const bool self = cell_mode && q_points == s_points && q_lengths == s_lengths && nq_total == ns_total &&
+                    (ns_total >= 200000 || cell_mode == 2);
+  if (self) {
+    LCR_CUDA_TRY(cudaMemsetAsync(w.next_cell, 0, sizeof(uint32_t), stream));
+    const unsigned gridC = LCR_SM_COUNT * 5;     // 5 CTAs of 4 warps per SM (40 KB of shared memory each)
+    if (idx_is64)
+      query_self_kernel<int64_t><<<gridC, kCellWarps * 32, 0, stream>>>(
+          w.occ_list, w.n_occ, w.next_cell, r2, w.tkeys, w.tstart, w.tcount, w.tcap - 1, w.sorted, width, ns_total,
+          (int64_t*)out_idx, out_counts, out_max_count, w.spill_list, w.spill_n);
+    else
+      query_self_kernel<int32_t><<<gridC, kCellWarps * 32, 0, stream>>>(
+          w.occ_list, w.n_occ, w.next_cell, r2, w.tkeys, w.tstart, w.tcount, w.tcap - 1, w.sorted, width, ns_total,
+          (int32_t*)out_idx, out_counts, out_max_count, w.spill_list, w.spill_n);
+  }
+  if (!self) {
+    if (idx_is64)
+      query_kernel<int64_t><<<gridQ, kWarpsPerCta * 32, 0, stream>>>(
+          q_points, nq_total, w.q_off, batch, w.geom, inv_cell, r2, w.tkeys, w.tstart, w.tcount, w.tcap - 1, w.sorted,
+          width, ns_total, (int64_t*)out_idx, out_counts, out_max_count, w.spill_list, w.spill_n);
+    else
+      query_kernel<int32_t><<<gridQ, kWarpsPerCta * 32, 0, stream>>>(
+          q_points, nq_total, w.q_off, batch, w.geom, inv_cell, r2, w.tkeys, w.tstart, w.tcount, w.tcap - 1, w.sorted,
+          width, ns_total, (int32_t*)out_idx, out_counts, out_max_count, w.spill_list, w.spill_n);
+  }
+  if (out_idx) {   // rows with more hits than a warp buffer: one CTA per queued query
+    if (idx_is64) {
       static LcrOncePerDevice attr_set64;
       const int attr_set64_dev = attr_set64.need();
       if (attr_set64_dev != -1) {
@@ -479,12 +641,7 @@ extern "C" int lcr_radius_neighbors_ex(const float* q_points, int64_t nq_total, 
       spill_kernel<int64_t><<<LCR_SM_COUNT, kSpillThreads, spill_smem, stream>>>(
           q_points, w.q_off, batch, w.geom, inv_cell, r2, w.tkeys, w.tstart, w.tcount, w.tcap - 1, w.sorted, width,
           ns_total, (int64_t*)out_idx, w.spill_list, w.spill_n, err);
-    }
-  } else {
-    query_kernel<int32_t><<<gridQ, kWarpsPerCta * 32, 0, stream>>>(
-        q_points, nq_total, w.q_off, batch, w.geom, inv_cell, r2, w.tkeys, w.tstart, w.tcount, w.tcap - 1, w.sorted,
-        width, ns_total, (int32_t*)out_idx, out_counts, out_max_count, w.spill_list, w.spill_n);
-    if (out_idx) {
+    } else {
       static LcrOncePerDevice attr_set32;
       const int attr_set32_dev = attr_set32.need();
       if (attr_set32_dev != -1) {
@@ -497,7 +654,7 @@ extern "C" int lcr_radius_neighbors_ex(const float* q_points, int64_t nq_total, 
           ns_total, (int32_t*)out_idx, w.spill_list, w.spill_n, err);
     }
   }
-  LCR_LAUNCHED(1 + (build ? 1 : 0) + (build && ns_total > 0 ? 2 : 0) + (out_idx ? 1 : 0));  // query, geom, insert, scatter, spill
+  LCR_LAUNCHED(1 + (build ? 1 : 0) + (build && ns_total > 0 ? 3 : 0) + (out_idx ? 1 : 0));  // query, geom, insert, scatter, compact, spill
   LCR_CUDA_CHECK_LAUNCH();
   return LCR_OK;
 }
