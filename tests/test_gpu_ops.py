@@ -9,6 +9,8 @@ import torch
 from oracle import native as on
 from util import GOLDEN, canonical_rows, random_clouds
 
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
 pytestmark = pytest.mark.gpu
 G = np.load(os.path.join(GOLDEN, 'ops_golden.npz'))
 
@@ -122,3 +124,30 @@ def test_cpu_tensors_round_trip_like_reference_module():
     t = ext.radius_neighbors(torch.from_numpy(pts), torch.from_numpy(pts), torch.from_numpy(lens),
                              torch.from_numpy(lens), 2.0)
     assert not t.is_cuda and np.array_equal(t.numpy(), on.radius_neighbors(pts, pts, lens, lens, 2.0))
+
+
+def test_cell_grouped_self_search_forced():
+    """The cell-grouped self-table kernel (radius.cu query_self_kernel) only takes over above 200 k supports; forced
+    on (LCR_RADIUS_CELLS=2, read once per process -> subprocess) it must reproduce the oracle bit for bit on the small
+    clouds of this file too, including rows that overflow the warp buffer (spill path) and the counting pass."""
+    import subprocess
+    import sys
+    code = r'''
+import sys
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import numpy as np, torch
+from lcrnet_b200 import ext
+from oracle import native as on
+from util import random_clouds
+for seed, sizes, radius in ((3, [4000, 2500, 1], 1.2), (4, [9000], 3.0), (5, [300, 5000, 700], 0.7)):
+    pts, lens = random_clouds(seed, sizes)
+    p, l = torch.from_numpy(pts).cuda(), torch.from_numpy(lens).cuda()
+    for limit in (0, 40):
+        got = ext.radius_neighbors(p, p, l, l, radius, limit=limit).cpu().numpy()
+        want = on.radius_neighbors(pts, pts, lens, lens, radius, limit if limit else None)
+        assert got.shape == want.shape and np.array_equal(got, want), (seed, limit, got.shape, want.shape)
+print('CELLS-OK')
+''' % (REPO, os.path.join(REPO, 'tests'))
+    env = dict(os.environ, LCR_RADIUS_CELLS='2')
+    r = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0 and 'CELLS-OK' in r.stdout, r.stderr[-3000:]
