@@ -12,14 +12,11 @@ import launch_summary as ls  # noqa: E402
 
 # kernel-name prefix -> LcrProfScope group (csrc/*.cu)
 GROUPS = [('gemm_tf32x3', 'gemm_tf32x3'), ('gemm_kernel', 'gemm_f32'), ('kpconv_gather', 'kpconv_gather'),
-          ('kpconv_c1', 'kpconv_c1'), ('query_kernel', 'radius_query'), ('spill_kernel', 'radius_query'),
+          ('kpconv_c1', 'kpconv_c1'), ('query_kernel', 'radius_query'), ('query_self_kernel', 'radius_query'), ('spill_kernel', 'radius_query'),
           ('gn_partial', 'group_norm_stats'), ('gn_finalize', 'group_norm_stats'), ('gn_apply', 'group_norm_apply'),
           ('maxpool', 'maxpool'), ('hidden_partial', 'netvlad_hidden'), ('attention_tc', 'attention_tc'),
           ('sinkhorn', 'sinkhorn'), ('l2_topk', 'l2_topk')]
 
-
-def unit_scale(rows_raw, metric):
-    return 1.0
 
 
 def main():
