@@ -73,7 +73,7 @@ __global__ void cell_insert_kernel(const float* __restrict__ s, int64_t ns, cons
   const int cy = cell_coord(s[3 * j + 1], g.oy, inv_cell);
   const int cz = cell_coord(s[3 * j + 2], g.oz, inv_cell);
   if (cx < 0 || cy < 0 || cz < 0 || cx > kCellMax || cy > kCellMax || cz > kCellMax) {
-    *err = LCR_ERR_OVERFLOW;  // cloud extent exceeds 16384 cells (or NaN coordinates)
+    *err = LCR_ERR_OVERFLOW;  // cloud extent exceeds 2048 cells per axis (or NaN coordinates)
     slot_of[j] = 0xFFFFFFFFu;
     return;
   }

@@ -4,7 +4,7 @@
  * import or call this file; only tests/, __graft_entry__.smoke() and bench.py's CPU
  * baseline legs use it, and only as the checker / reported baseline.
  *
- * Parity status: PINNED.  tests/test_oracle_vs_ref.py compares every function here with
+ * Parity status: PINNED.  tests/test_oracle_ops.py compares every function here with
  * the unmodified reference sources compiled into oracle/_ref/libref_ext.so (see
  * oracle/Makefile) and with the committed fixtures in tests/golden/ generated from them.
  *

@@ -224,9 +224,9 @@ def test_full_lcrnet_vs_oracle_and_fixture(net, oracle_run, gemm, monkeypatch):
         assert float((got[k].cpu() - out[k]).norm()) < 1e-4            # descriptors: 1e-4 relative (unit norm)
         assert np.linalg.norm(got[k].cpu().numpy() - G[k]) < 1e-4       # vs the reference itself
     assert got['length'].tolist() == list(out['length']) == list(G['node_counts'])
-    assert float((got['pos_points_c'].cpu() - out['pos_points_c']).abs().max()) < 1e-3
+    assert float((got['pos_points_c'].cpu() - out['pos_points_c']).abs().max()) < 1e-4 * float(out['pos_points_c'].abs().max())
     ref_f = out['pos_feats_f']
-    assert float((got['pos_feats_f'].cpu() - ref_f).abs().max()) < 5e-4 * max(1.0, float(ref_f.abs().max()))
+    assert float((got['pos_feats_f'].cpu() - ref_f).abs().max()) < 1e-4 * max(1.0, float(ref_f.abs().max()))
     pairs_got = set(zip(got['pos_node_corr_indices'].tolist(), got['anc_node_corr_indices'].tolist()))
     pairs_ref = set(zip(out['pos_node_corr_indices'].tolist(), out['anc_node_corr_indices'].tolist()))
     jacc = len(pairs_got & pairs_ref) / len(pairs_got | pairs_ref)
@@ -237,12 +237,18 @@ def test_full_lcrnet_vs_oracle_and_fixture(net, oracle_run, gemm, monkeypatch):
     assert abs(got['corr_scores'].shape[0] - n_ref) <= max(2, n_ref // 200)
     T, T_ref = got['estimated_transform'].cpu(), out['estimated_transform']
     assert T.shape == (4, 4)
-    # pose: the north-star bar is 1e-4 relative (measured on B200: 9.1e-6 vs the oracle)
+    # pose: the north-star bar is 1e-4 relative.  Always: the GPU pose equals the oracle's LGR run on the GPU's own
+    # correspondence lists (a flipped near-tie correspondence changes the weighted-SVD INPUT, not the arithmetic);
+    # and end to end whenever the node-correspondence sets are identical
+    T_cond = po.lgr_from_lists(got['pos_corr_points'].cpu(), got['anc_corr_points'].cpu(), got['corr_scores'].cpu(),
+                               got['_corr_patch'].cpu().long())
+    e_cond = float((T - T_cond).abs().max()) / max(1.0, float(T_cond.abs().max()))
     err = float((T - T_ref).abs().max()) / max(1.0, float(T_ref.abs().max()))
-    print('[%s] pose max-abs relative error vs oracle: %.3e' % (gemm, err))
-    # identical correspondence sets -> 1e-4 (north-star bar); a flipped near-tie correspondence moves
-    # the weighted-SVD input itself, so the bound is then the oracle-vs-reference bound of 1e-3
-    assert err < (1e-4 if pairs_got == pairs_ref else 1e-3)
+    print('[%s] pose max-abs relative error: vs oracle LGR on the GPU lists %.3e, end to end vs oracle %.3e' % (
+        gemm, e_cond, err))
+    assert e_cond < 1e-4
+    if pairs_got == pairs_ref:
+        assert err < 1e-4
     assert np.abs(T.numpy() - G['estimated_transform']).max() < 2e-3     # vs the reference (oracle: < 1e-3)
 
 
@@ -265,7 +271,12 @@ def test_demo_pair_and_batched_pairs(net):
         one = net(mk(pairs[2 * p:2 * p + 2]))
         T1, T2 = one['estimated_transform'].cpu(), both['estimated_transform'][p].cpu()
         n1, n2 = one['corr_scores'].shape[0], both['corr_scores'][p].shape[0]
-        assert float((T1 - T2).abs().max()) < (1e-4 if n1 == n2 else 1e-3) * max(1.0, float(T1.abs().max()))
+        if n1 == n2:         # same correspondence lists -> same pose; otherwise compare each with the oracle's LGR
+            assert float((T1 - T2).abs().max()) < 1e-4 * max(1.0, float(T1.abs().max()))
+        for o, T, sel in ((one, T1, None), (both, T2, p)):
+            f = (lambda k: o[k].cpu()) if sel is None else (lambda k: o[k][sel].cpu())
+            Tc = po.lgr_from_lists(f('pos_corr_points'), f('anc_corr_points'), f('corr_scores'), f('_corr_patch').long())
+            assert float((T - Tc).abs().max()) < 1e-4 * max(1.0, float(Tc.abs().max()))
         assert float((one['pos_feature_global'] - both['pos_feature_global'][p]).norm()) < 1e-5
         R = T1[:3, :3].double()
         assert float((R @ R.t() - torch.eye(3, dtype=torch.float64)).abs().max()) < 1e-5
