@@ -56,6 +56,8 @@ def parse():
     ap.add_argument('--ncu', action='store_true', help='one warm-up step + one step only (for ncu captures)')
     ap.add_argument('--streams', type=int, default=2,
                     help='descriptor workload: chunks of the batch in flight on separate CUDA streams (pipeline.py)')
+    ap.add_argument('--pair-streams', type=int, default=1,
+                    help='registration workload: chunks of the pair batch in flight (1 = one batched forward: fastest)')
     ap.add_argument('--workload', default='all', choices=['all', 'descriptor', 'db', 'pairs'],
                     help='all: the headline (configs[1]) with the pairs and db workloads as sub-records; or one of '
                          'them alone: descriptor (configs[1]); db: descriptor-database build + all-gather + top-25 '
@@ -501,7 +503,7 @@ def bench_pairs(ctx, args, inp):
     n_pairs = len(inp.lens) // 2
     mk = lambda n: pipeline.PairPipeline(net, inp.limits, NUM_STAGES, VOXEL, RADIUS, pre_voxel=VOXEL, n_streams=n)
     pipe1 = mk(1)
-    pipe = pipe1 if args.streams <= 1 or args.ncu else mk(args.streams)
+    pipe = pipe1 if args.pair_streams <= 1 or args.ncu else mk(args.pair_streams)
     out_T = torch.empty((n_pairs, 4, 4), dtype=torch.float32).pin_memory()
     out_desc = torch.empty((2 * n_pairs, 256), dtype=torch.float32).pin_memory()
     last = {}
@@ -547,7 +549,7 @@ def bench_pairs(ctx, args, inp):
            'steps': steps, 'warmup': warm, 'ms_per_step': total / steps,
            'config': {'workload': 'configs[2]: scan-pair registration (LCRNet full forward: descriptors + pose), batch '
                                   '%d pairs of 65536-point scans per step per GPU' % n_pairs,
-                      'neighbor_limits': inp.limits, 'streams': args.streams, 'cache': 'L2 flushed between timed steps',
+                      'neighbor_limits': inp.limits, 'streams': args.pair_streams, 'cache': 'L2 flushed between timed steps',
                       'weights': 'seeded random: correspondences are not meaningful, the work is'},
            'e2e': {'value': pairs_all / (total_e2e * 1e-3), 'unit': 'pairs/s', 'h2d_bytes_per_step': inp.h2d_bytes,
                    'd2h_bytes_per_step': int(out_T.numel() * 4 + out_desc.numel() * 4), 'ms_per_step': total_e2e / steps},

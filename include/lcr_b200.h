@@ -288,7 +288,8 @@ int lcr_coarse_matching(const float* log_scores, int rows, int cols, int32_t* ou
  * lcr_patch_scores: out[p] = F_a[knn_a[node_a[p]]] . F_b[knn_b[node_b[p]]]^T / sqrt(128), [128 x 128].
  * lcr_fine_correspondences: from the Sinkhorn output [n_pairs, 129, 129]: (i, j) kept iff row- or
  *   column-top-1 beating the dustbin, both points valid; row-major per pair; pair_off = exclusive
- *   scan of the per-pair counts (pair_off[n_pairs] = total); outputs have capacity n_pairs * 256.
+ *   scan of the per-pair counts (pair_off[n_pairs] = total); outputs have capacity n_pairs * 256 (only arg-max
+ *   entries can be kept: <= 256 per pair); ws = lcr_fine_correspondences_ws_bytes(n_pairs) of scratch.
  * lcr_corr_points: the 3-D points of the correspondences.
  * lcr_local_global_registration: per-pair weighted Procrustes (pairs with >= min_corr
  *   correspondences), hypothesis with most inliers (< radius) over all correspondences, then
@@ -297,9 +298,11 @@ int lcr_coarse_matching(const float* log_scores, int rows, int cols, int32_t* ou
 int lcr_patch_scores(const float* feats_a, int64_t n_a, const int32_t* knn_a, const int32_t* node_a,
                      const float* feats_b, int64_t n_b, const int32_t* knn_b, const int32_t* node_b, int n_pairs,
                      int k, int channels, float* out, void* stream);
+size_t lcr_fine_correspondences_ws_bytes(int n_pairs);
 int lcr_fine_correspondences(const float* log_scores, int n_pairs, const uint8_t* knn_mask_a, const int32_t* node_a,
                              const uint8_t* knn_mask_b, const int32_t* node_b, int32_t* pair_cnt, int32_t* pair_off,
-                             int32_t* out_pair, int32_t* out_i, int32_t* out_j, float* out_scores, void* stream);
+                             int32_t* out_pair, int32_t* out_i, int32_t* out_j, float* out_scores, void* ws,
+                             size_t ws_bytes, void* stream);
 int lcr_corr_points(const int32_t* c_pair, const int32_t* c_i, const int32_t* c_j, const int32_t* n_corr,
                     int64_t capacity, const float* pts_a, const int32_t* knn_a, const int32_t* node_a,
                     const float* pts_b, const int32_t* knn_b, const int32_t* node_b, float* ref, float* src,

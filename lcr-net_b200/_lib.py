@@ -72,8 +72,9 @@ SIGNATURES = {
     'lcr_coarse_matching_ws_bytes': (c_sz, [c_i32, c_i32]),
     'lcr_coarse_matching': (c_i32, [c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
     'lcr_patch_scores': (c_i32, [c_vp, c_i64, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp]),
+    'lcr_fine_correspondences_ws_bytes': (c_sz, [c_i32]),
     'lcr_fine_correspondences': (c_i32, [c_vp, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,
-                                         c_vp]),
+                                         c_vp, c_sz, c_vp]),
     'lcr_corr_points': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     'lcr_lgr_ws_bytes': (c_sz, [c_i32, c_i64]),
     'lcr_local_global_registration': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i64, c_f32, c_i32, c_i32, c_vp, c_vp,

@@ -222,55 +222,71 @@ coarse_match_kernel(const float* __restrict__ ls, int M, int N, int32_t* __restr
 }
 
 // ================================================================== patch score matrices
-// out[p, a, b] = <fa[knn_a[p, a]], fb[knn_b[p, b]]> / sqrt(C)  (pad index -> zero row); K = 128, C = 128
-constexpr int PK = 128, PC = 128;
-__global__ void __launch_bounds__(256)
+// out[p, a, b] = <fa[knn_a[p, a]], fb[knn_b[p, b]]> / sqrt(C)  (pad index -> zero row); K = 128, C = 128.
+// One CTA per patch pair, 8 x 8 register tile per thread, operands transposed into shared memory ([channel][point])
+// in two 64-channel stages (66 KB: two CTAs per SM, so one CTA's gather overlaps the other's FMAs).  Staging map:
+// a warp covers 16 points x 2 float4 per step, lane = (point & 15, float4 & 1): the transposed store
+// sa[4 c4 + k][r] then lands on bank 16 (c4 & 1) + (r & 15) -- conflict free (the first version had the 32 lanes
+// on the 32 float4 of ONE point: 16-way conflicts on every store, 2/3 of the kernel time).
+constexpr int PK = 128, PC = 128, PCH = 64;
+__global__ void __launch_bounds__(256, 2)
 patch_scores_kernel(const float* __restrict__ fa, int na, const int32_t* __restrict__ knn_a,
                     const int32_t* __restrict__ node_a, const float* __restrict__ fb, int nb,
                     const int32_t* __restrict__ knn_b, const int32_t* __restrict__ node_b, float div,
                     float* __restrict__ out) {
-  extern __shared__ float sp[];  // A^T [PC][PK+4], B^T [PC][PK+4]
+  extern __shared__ float sp[];  // A^T [PCH][PK+4], B^T [PCH][PK+4]
   float(*sa)[PK + 4] = reinterpret_cast<float(*)[PK + 4]>(sp);
-  float(*sb)[PK + 4] = reinterpret_cast<float(*)[PK + 4]>(sp + PC * (PK + 4));
+  float(*sb)[PK + 4] = reinterpret_cast<float(*)[PK + 4]>(sp + PCH * (PK + 4));
   const int p = blockIdx.x, tid = threadIdx.x;
-  const int32_t* ka = knn_a + (size_t)node_a[p] * PK;
-  const int32_t* kb = knn_b + (size_t)node_b[p] * PK;
-  for (int e = tid; e < PK * (PC / 4); e += 256) {
-    const int r = e / (PC / 4), c4 = e % (PC / 4);
-    const int ia = ka[r], ib = kb[r];
-    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-    const float4 va = ia < na ? *reinterpret_cast<const float4*>(fa + (size_t)ia * PC + c4 * 4) : z;
-    const float4 vb = ib < nb ? *reinterpret_cast<const float4*>(fb + (size_t)ib * PC + c4 * 4) : z;
-    sa[c4 * 4 + 0][r] = va.x; sa[c4 * 4 + 1][r] = va.y; sa[c4 * 4 + 2][r] = va.z; sa[c4 * 4 + 3][r] = va.w;
-    sb[c4 * 4 + 0][r] = vb.x; sb[c4 * 4 + 1][r] = vb.y; sb[c4 * 4 + 2][r] = vb.z; sb[c4 * 4 + 3][r] = vb.w;
-  }
-  __syncthreads();
+  const int r = (tid >> 5) * 16 + (tid & 15), c4l = (tid >> 4) & 1;   // staging: this thread's point and float4 parity
+  const int ia = knn_a[(size_t)node_a[p] * PK + r], ib = knn_b[(size_t)node_b[p] * PK + r];
+  const float4* ra = ia < na ? reinterpret_cast<const float4*>(fa + (size_t)ia * PC) : nullptr;
+  const float4* rb = ib < nb ? reinterpret_cast<const float4*>(fb + (size_t)ib * PC) : nullptr;
   const int tx = tid & 15, ty = tid >> 4;
   float acc[8][8];
 #pragma unroll
   for (int i = 0; i < 8; i++)
 #pragma unroll
     for (int j = 0; j < 8; j++) acc[i][j] = 0.f;
+#pragma unroll 1
+  for (int half = 0; half < PC / PCH; half++) {
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 va[8], vb[8];
+#pragma unroll
+    for (int it = 0; it < 8; it++) {           // all 16 loads in flight before the first store
+      const int c4 = half * (PCH / 4) + 2 * it + c4l;
+      va[it] = ra ? ra[c4] : z;
+      vb[it] = rb ? rb[c4] : z;
+    }
+    if (half) __syncthreads();                 // the previous stage has been consumed
+#pragma unroll
+    for (int it = 0; it < 8; it++) {
+      const int c = 4 * (2 * it + c4l);
+      sa[c + 0][r] = va[it].x; sa[c + 1][r] = va[it].y; sa[c + 2][r] = va[it].z; sa[c + 3][r] = va[it].w;
+      sb[c + 0][r] = vb[it].x; sb[c + 1][r] = vb[it].y; sb[c + 2][r] = vb[it].z; sb[c + 3][r] = vb[it].w;
+    }
+    __syncthreads();
 #pragma unroll 4
-  for (int c = 0; c < PC; c++) {
-    float a[8], b[8];
-    *reinterpret_cast<float4*>(a) = *reinterpret_cast<const float4*>(&sa[c][ty * 4]);
-    *reinterpret_cast<float4*>(a + 4) = *reinterpret_cast<const float4*>(&sa[c][64 + ty * 4]);
-    *reinterpret_cast<float4*>(b) = *reinterpret_cast<const float4*>(&sb[c][tx * 4]);
-    *reinterpret_cast<float4*>(b + 4) = *reinterpret_cast<const float4*>(&sb[c][64 + tx * 4]);
+    for (int c = 0; c < PCH; c++) {
+      float a[8], b[8];
+      *reinterpret_cast<float4*>(a) = *reinterpret_cast<const float4*>(&sa[c][ty * 4]);
+      *reinterpret_cast<float4*>(a + 4) = *reinterpret_cast<const float4*>(&sa[c][64 + ty * 4]);
+      *reinterpret_cast<float4*>(b) = *reinterpret_cast<const float4*>(&sb[c][tx * 4]);
+      *reinterpret_cast<float4*>(b + 4) = *reinterpret_cast<const float4*>(&sb[c][64 + tx * 4]);
 #pragma unroll
-    for (int i = 0; i < 8; i++)
+      for (int i = 0; i < 8; i++)
 #pragma unroll
-      for (int j = 0; j < 8; j++) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        for (int j = 0; j < 8; j++) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
   }
   float* o = out + (size_t)p * PK * PK;
 #pragma unroll
   for (int i = 0; i < 8; i++) {
-    const int r = (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+    const int row = (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
 #pragma unroll
     for (int h = 0; h < 2; h++) {
       const int cidx = h * 64 + tx * 4;
-      *reinterpret_cast<float4*>(o + (size_t)r * PK + cidx) =
+      *reinterpret_cast<float4*>(o + (size_t)row * PK + cidx) =
           make_float4(acc[i][h * 4 + 0] / div, acc[i][h * 4 + 1] / div, acc[i][h * 4 + 2] / div, acc[i][h * 4 + 3] / div);
     }
   }
@@ -278,24 +294,37 @@ patch_scores_kernel(const float* __restrict__ fa, int na, const int32_t* __restr
 
 // ================================================================== fine correspondences
 // per pair p: log scores [129 x 129]; (i,j), i,j < 128, kept iff (row-argmax and > dustbin col) or
-// (col-argmax and > dustbin row) in the exp domain, and both points valid.  Two passes: count, emit.
-__global__ void __launch_bounds__(256)
-fine_corr_kernel(const float* __restrict__ ls, const uint8_t* __restrict__ mask_a, const int32_t* __restrict__ node_a,
-                 const uint8_t* __restrict__ mask_b, const int32_t* __restrict__ node_b,
-                 const int32_t* __restrict__ pair_off /* NULL in the counting pass */, int32_t* __restrict__ pair_cnt,
-                 int32_t* __restrict__ out_pair, int32_t* __restrict__ out_i, int32_t* __restrict__ out_j,
-                 float* __restrict__ out_s) {
-  constexpr int R = PK + 1;
-  __shared__ int row_best[R], col_best[R], row_cnt[PK];
+// (col-argmax and > dustbin row) in the exp domain, and both points valid (LCRNet.py:239-249).
+// Only the row / column arg-max entries can be kept: at most 256 candidates per pair.  Pass 1 (one CTA per pair)
+// stages E = exp(S) in shared memory ONCE (66.5 KB, 3 CTAs per SM; the first version re-read S from L2 seven times:
+// row arg-max, column arg-max, the 128 x 128 `kept` scan, all of it again in the emit pass), finds the arg-maxima,
+// marks the kept candidates in a 128 x 128 bitmap and writes them in row-major order into the pair's 256-entry slot
+// of a scratch buffer; after the scan of the counts, pass 2 copies the slots to their final offsets.
+constexpr int FR = PK + 1;
+constexpr size_t kFineSmem = sizeof(float) * FR * FR + sizeof(int) * (2 * FR + PK + 4 * PK) + 64;
+__global__ void __launch_bounds__(256, 3)
+fine_corr_find_kernel(const float* __restrict__ ls, const uint8_t* __restrict__ mask_a,
+                      const int32_t* __restrict__ node_a, const uint8_t* __restrict__ mask_b,
+                      const int32_t* __restrict__ node_b, int32_t* __restrict__ pair_cnt,
+                      int32_t* __restrict__ slot_ij, float* __restrict__ slot_s) {
+  extern __shared__ __align__(16) float fsm[];
+  float* E = fsm;                                          // [129][129]
+  int* row_best = reinterpret_cast<int*>(E + FR * FR);     // [129]
+  int* col_best = row_best + FR;                           // [129]
+  int* row_off = col_best + FR;                            // [128]
+  unsigned* bm = reinterpret_cast<unsigned*>(row_off + PK);   // [128][4]
   const int p = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const float* S = ls + (size_t)p * R * R;
+  const float* S = ls + (size_t)p * FR * FR;
   const uint8_t* ma = mask_a + (size_t)node_a[p] * PK;
   const uint8_t* mb = mask_b + (size_t)node_b[p] * PK;
-  for (int i = warp; i < R; i += 8) {
+  for (int e = tid; e < FR * FR; e += 256) E[e] = expf(S[e]);
+  for (int e = tid; e < 4 * PK; e += 256) bm[e] = 0u;
+  __syncthreads();
+  for (int i = warp; i < FR; i += 8) {                     // row arg-max, lowest index among equals
     float best = -INFINITY;
     int bj = 0x7fffffff;
-    for (int j = lane; j < R; j += 32) {
-      const float e = expf(S[i * R + j]);
+    for (int j = lane; j < FR; j += 32) {
+      const float e = E[i * FR + j];
       if (e > best) { best = e; bj = j; }
     }
     for (int o = 16; o > 0; o >>= 1) {
@@ -305,56 +334,71 @@ fine_corr_kernel(const float* __restrict__ ls, const uint8_t* __restrict__ mask_
     }
     if (lane == 0) row_best[i] = bj;
   }
-  for (int j = tid; j < R; j += 256) {
-    float best = -INFINITY;
-    int bi = 0;
-    for (int i = 0; i < R; i++) {
-      const float e = expf(S[i * R + j]);
-      if (e > best) { best = e; bi = i; }
+  if (tid < FR) {                                          // column arg-max, lowest index among equals
+    float b0 = -INFINITY, b1 = -INFINITY;
+    int i0 = 0, i1 = 0;
+    for (int i = 0; i + 1 < FR; i += 2) {                  // two interleaved chains (even / odd rows)
+      const float e0 = E[i * FR + tid], e1 = E[(i + 1) * FR + tid];
+      if (e0 > b0) { b0 = e0; i0 = i; }
+      if (e1 > b1) { b1 = e1; i1 = i + 1; }
     }
-    col_best[j] = bi;
+    const float el = E[(FR - 1) * FR + tid];               // FR is odd: the last row
+    if (el > b0) { b0 = el; i0 = FR - 1; }
+    col_best[tid] = (b1 > b0 || (b1 == b0 && i1 < i0)) ? i1 : i0;
   }
   __syncthreads();
-  auto kept = [&](int i, int j) -> bool {
-    if (!ma[i] || !mb[j]) return false;
-    const float e = expf(S[i * R + j]);
-    return (row_best[i] == j && e > expf(S[i * R + PK])) || (col_best[j] == i && e > expf(S[PK * R + j]));
-  };
-  for (int i = warp; i < PK; i += 8) {
-    int c = 0;
-    for (int j = lane; j < PK; j += 32) c += kept(i, j);
-    c = lcr_warp_sum(c);
-    if (lane == 0) row_cnt[i] = c;
+  if (tid < PK) {
+    const int i = tid, j = row_best[i];
+    if (j < PK && ma[i] && mb[j] && E[i * FR + j] > E[i * FR + PK]) atomicOr(&bm[i * 4 + (j >> 5)], 1u << (j & 31));
+  } else {
+    const int j = tid - PK, i = col_best[j];
+    if (i < PK && ma[i] && mb[j] && E[i * FR + j] > E[PK * FR + j]) atomicOr(&bm[i * 4 + (j >> 5)], 1u << (j & 31));
   }
   __syncthreads();
-  if (tid == 0) {
-    int acc = 0;
-    for (int i = 0; i < PK; i++) {
-      const int c = row_cnt[i];
-      row_cnt[i] = acc;
-      acc += c;
+  if (tid < PK) {                                          // exclusive scan of the row counts (4 warps)
+    const int c = __popc(bm[tid * 4]) + __popc(bm[tid * 4 + 1]) + __popc(bm[tid * 4 + 2]) + __popc(bm[tid * 4 + 3]);
+    int incl = c;
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
     }
-    if (!pair_off) pair_cnt[p] = acc;
+    row_off[tid] = incl - c;
+    if (lane == 31) row_best[warp] = incl;                 // (row_best is dead by now: warp totals)
   }
   __syncthreads();
-  if (!pair_off) return;
-  const int base0 = pair_off[p];
-  for (int i = warp; i < PK; i += 8) {
-    int base = base0 + row_cnt[i];
-    for (int j0 = 0; j0 < PK; j0 += 32) {
-      const int j = j0 + lane;
-      const bool k = kept(i, j);
-      const unsigned m = __ballot_sync(0xffffffffu, k);
-      if (k) {
-        const int pos = base + __popc(m & ((1u << lane) - 1u));
-        out_pair[pos] = p;
-        out_i[pos] = i;
-        out_j[pos] = j;
-        out_s[pos] = expf(S[i * R + j]);
+  if (tid < PK) {
+    int base = row_off[tid];
+    for (int w = 0; w < warp; w++) base += row_best[w];
+    int32_t* dij = slot_ij + (size_t)p * 256;
+    float* ds = slot_s + (size_t)p * 256;
+#pragma unroll
+    for (int w = 0; w < 4; w++) {
+      unsigned bits = bm[tid * 4 + w];
+      while (bits) {
+        const int j = 32 * w + __ffs(bits) - 1;
+        bits &= bits - 1;
+        dij[base] = (tid << 8) | j;
+        ds[base] = E[tid * FR + j];
+        base++;
       }
-      base += __popc(m);
     }
+    if (tid == PK - 1) pair_cnt[p] = base;
   }
+}
+
+__global__ void fine_corr_compact_kernel(const int32_t* __restrict__ slot_ij, const float* __restrict__ slot_s,
+                                         const int32_t* __restrict__ pair_cnt, const int32_t* __restrict__ pair_off,
+                                         int n_pairs, int32_t* __restrict__ out_pair, int32_t* __restrict__ out_i,
+                                         int32_t* __restrict__ out_j, float* __restrict__ out_s) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int p = (int)(idx >> 8), t = (int)(idx & 255);
+  if (p >= n_pairs || t >= pair_cnt[p]) return;
+  const int ij = slot_ij[idx];
+  const int pos = pair_off[p] + t;
+  out_pair[pos] = p;
+  out_i[pos] = ij >> 8;
+  out_j[pos] = ij & 255;
+  out_s[pos] = slot_s[idx];
 }
 
 __global__ void exclusive_scan_i32_kernel(const int32_t* __restrict__ in, int n, int32_t* __restrict__ out) {
@@ -801,7 +845,7 @@ extern "C" int lcr_patch_scores(const float* feats_a, int64_t n_a, const int32_t
   cudaStream_t stream = (cudaStream_t)stream_;
   LCR_REQUIRE(k == PK && channels == PC, "patch_scores: specialised to 128 points x 128 channels");
   if (n_pairs == 0) return LCR_OK;
-  const size_t smem = sizeof(float) * 2 * PC * (PK + 4);
+  const size_t smem = sizeof(float) * 2 * PCH * (PK + 4);
   LCR_CUDA_TRY(cudaFuncSetAttribute(patch_scores_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   LcrProfScope prof("patch_scores", 2.0 * n_pairs * PK * PK * PC, 4.0 * n_pairs * (2.0 * PK * PC + PK * PK), stream);
   patch_scores_kernel<<<n_pairs, 256, smem, stream>>>(feats_a, (int)n_a, knn_a, node_a, feats_b, (int)n_b, knn_b,
@@ -814,21 +858,36 @@ extern "C" int lcr_patch_scores(const float* feats_a, int64_t n_a, const int32_t
 // Fine correspondences of all node pairs, row-major per pair (the reference's torch.nonzero order).
 // pair_off[n_pairs+1] (device) receives the exclusive scan of the per-pair counts; outputs have
 // capacity n_pairs * 256.
+extern "C" size_t lcr_fine_correspondences_ws_bytes(int n_pairs) {
+  return lcr_align_up((size_t)n_pairs * 256 * 4) * 2 + 256;
+}
+
 extern "C" int lcr_fine_correspondences(const float* log_scores, int n_pairs, const uint8_t* knn_mask_a,
                                         const int32_t* node_a, const uint8_t* knn_mask_b, const int32_t* node_b,
                                         int32_t* pair_cnt, int32_t* pair_off, int32_t* out_pair, int32_t* out_i,
-                                        int32_t* out_j, float* out_scores, void* stream_) {
+                                        int32_t* out_j, float* out_scores, void* ws, size_t ws_bytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (n_pairs == 0) {
     LCR_CUDA_TRY(cudaMemsetAsync(pair_off, 0, sizeof(int32_t), stream));
     return LCR_OK;
   }
-  LcrProfScope prof("fine_correspondences", 0.0, 8.0 * n_pairs * 129.0 * 129.0, stream);
-  fine_corr_kernel<<<n_pairs, 256, 0, stream>>>(log_scores, knn_mask_a, node_a, knn_mask_b, node_b, nullptr, pair_cnt,
-                                                nullptr, nullptr, nullptr, nullptr);
+  LCR_REQUIRE(ws && ws_bytes >= lcr_fine_correspondences_ws_bytes(n_pairs), "fine_correspondences: workspace too small");
+  LcrArena a(ws, ws_bytes);
+  int32_t* slot_ij = a.take<int32_t>((size_t)n_pairs * 256);
+  float* slot_s = a.take<float>((size_t)n_pairs * 256);
+  static LcrOncePerDevice once;
+  const int dev = once.need();
+  if (dev != -1) {
+    LCR_CUDA_TRY(cudaFuncSetAttribute(fine_corr_find_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)kFineSmem));
+    once.done(dev);
+  }
+  LcrProfScope prof("fine_correspondences", 0.0, 4.0 * n_pairs * 129.0 * 129.0, stream);
+  fine_corr_find_kernel<<<n_pairs, 256, kFineSmem, stream>>>(log_scores, knn_mask_a, node_a, knn_mask_b, node_b,
+                                                             pair_cnt, slot_ij, slot_s);
   exclusive_scan_i32_kernel<<<1, 1024, 0, stream>>>(pair_cnt, n_pairs, pair_off);
-  fine_corr_kernel<<<n_pairs, 256, 0, stream>>>(log_scores, knn_mask_a, node_a, knn_mask_b, node_b, pair_off, pair_cnt,
-                                                out_pair, out_i, out_j, out_scores);
+  fine_corr_compact_kernel<<<(unsigned)n_pairs, 256, 0, stream>>>(slot_ij, slot_s, pair_cnt, pair_off, n_pairs, out_pair,
+                                                                  out_i, out_j, out_scores);
   LCR_LAUNCHED(3);
   LCR_CUDA_CHECK_LAUNCH();
   return LCR_OK;

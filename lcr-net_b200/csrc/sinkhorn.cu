@@ -27,6 +27,8 @@
 //                            bound by the 128 B/clk port.
 //   sinkhorn_general_kernel  any size (node level, ~370 x 360): K in the output buffer (L2), warp per row, row
 //                            slabs per warp for the column sums.
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 
 namespace {
@@ -68,32 +70,34 @@ __device__ __forceinline__ float sk_score(const float* __restrict__ src, const u
 }
 
 // ================================================================== point level: 128 x 128 (+ dustbins)
-// The plan (129 x 129, zero-padded to 132 x 132) lives in REGISTERS as 3 x 33 blocks: thread (g, h) of the row role
-// (warps 0-5) holds rows 3 g .. 3 g + 2 x columns 33 h .. 33 h + 32, thread (g, h) of the column role (warps 6-11) the
-// transposed block (12 warps: 168 registers per thread, 99 of them the plan, 33 the scalings in flight).  A
-// half-iteration is 99 FFMA per active thread against 33 words of the other side's scalings: every word loaded from
-// shared memory feeds THREE multiply-adds.  That ratio is the point: shared memory delivers
-// one 32-bit word per lane and wavefront whatever the load width or broadcast, so a thread-per-row (1 x 129) or
-// quarter-row (1 x 33) layout needs 129 x 129 words per half-iteration -- 520 cycles of the 128 B/clk port, measured
-// 50 % busy and short-scoreboard bound (ncu, profiles/r2_ncu_sinkhorn_quarter_rows.txt) -- while the 4 x 33 blocks
-// need a third of that.  The partial sums of a row group are combined by a 4-lane butterfly; lane h < 3 finishes
-// row 3 g + h.  Scaling vectors sit in shared memory as four 36-float segments (element x at 36 (x / 33) + x % 33) so the
-// 33 words of a thread are eight aligned 16-byte loads + one, on distinct banks for the four h.
-constexpr int PN = 128, PR = 129, PLD = 129, PP = 132, PV = 144, PB = 33;
-constexpr int RB = 3;                                        // rows (columns) per thread block: 3 x 33 = 99 registers
+// The plan (129 x 129, zero-padded to 132 x 136) lives in REGISTERS, twice: thread (g, h) -- 44 groups x 8 chunks,
+// 352 of the 384 threads -- holds the ROW-form block  K[3 g .. 3 g + 2][17 h .. 17 h + 16]  and the COLUMN-form block
+// K[17 h .. 17 h + 16][3 g .. 3 g + 2]  (2 x 51 registers).  A half-iteration is 51 FFMA per thread against 17 words
+// of the other side's scalings: every word loaded from shared memory feeds THREE multiply-adds.  That ratio is the
+// point: shared memory delivers one 32-bit word per lane and wavefront whatever the load width or broadcast, so a
+// thread-per-row (1 x 129) or quarter-row (1 x 33) layout needs 129 x 129 words per half-iteration -- 520 cycles of
+// the 128 B/clk port, measured 50 % busy and short-scoreboard bound (ncu, profiles/r2_ncu_sinkhorn_quarter_rows.txt).
+// Both forms in EVERY thread (rather than 3 x 33 row blocks in one half of the CTA and column blocks in the other,
+// the previous version of this kernel) keeps all 12 warps busy in both half-iterations: with role-split warps only 6
+// warps -- 1.5 per scheduler -- were runnable at any time and the half-iteration sat on FMA / shuffle / barrier
+// latency (ncu: issue 33 %, FMA pipe 20 %, profiles/r2_ncu_sinkhorn_patch.txt).  The partial sums of a row
+// (column) group are combined by an 8-lane butterfly; lane h < 3 finishes row (column) 3 g + h.  Scaling vectors sit
+// in shared memory as eight 20-float segments (element x at 20 (x / 17) + x % 17): the 17 words of a thread are four
+// aligned 16-byte loads + one, and the eight segments of a quarter-warp fall on distinct banks (20 h mod 32).
+constexpr int PN = 128, PR = 129, PLD = 129, PP = 132, PB = 17, PH = 8, PSEG = 20, PV = PH * PSEG;
+constexpr int RB = 3;                                        // rows (columns) per thread block: 3 x 17 = 51 registers
 constexpr int NG = PP / RB;                                  // 44 row (column) groups
-constexpr int kPatchRoleThreads = 192;                       // 6 warps per role, 176 threads carry data
-constexpr int kPatchThreads = 2 * kPatchRoleThreads;
+constexpr int kPatchThreads = 384;                           // 12 warps, 352 threads carry data
 constexpr int kPatchSFloats = 16644;                         // 129 * 129 rounded up to a multiple of 4
 constexpr size_t kPatchSmem = sizeof(float) * (kPatchSFloats + 4 * PV + 6 * PP);
 
-__device__ __forceinline__ int vec_slot(int x) { return 36 * (x / PB) + x % PB; }   // x < 132
+__device__ __forceinline__ int vec_slot(int x) { return PSEG * (x / PB) + x % PB; }   // x < 136
 
-// s[r] = sum_c k[r][c] * x[33 h + c], then the 4-lane butterfly over h.  All nine loads are issued before the
+// s[r] = sum_c k[r][c] * x[17 h + c], then the 8-lane butterfly over h.  All five loads are issued before the
 // first FMA: left alone, ptxas sinks every load to just before its use and recycles ONE register quad (ncu source
-// view: each of the nine LDS.128 exposed its full latency, ~30 % of the half-iteration), and neither volatile asm
+// view: each LDS.128 exposed its full latency, ~30 % of the half-iteration), and neither volatile asm
 // loads nor a warp barrier keep it from doing so.  The accumulators therefore start from a zero that is
-// data-dependent on all nine loads, which forces them to be in flight together.
+// data-dependent on all loads, which forces them to be in flight together.
 __device__ __forceinline__ float4 lds128(uint32_t addr) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
@@ -110,19 +114,19 @@ __device__ __forceinline__ float lds32(uint32_t addr) {
 __device__ __forceinline__ void sts32(uint32_t addr, float v) {
   asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
 }
-// `seg` = 32-bit shared-window address of this thread's 36-float segment of the scaling vector (generic pointers cost
+// `seg` = 32-bit shared-window address of this thread's 20-float segment of the scaling vector (generic pointers cost
 // a window conversion per access: S2R + LEA showed up in every half-iteration)
 __device__ __forceinline__ void dot_block(const float (&k)[RB][PB], uint32_t seg, float (&s)[RB]) {
-  float4 t[8];
+  float4 t[4];
 #pragma unroll
-  for (int m = 0; m < 8; m++) t[m] = lds128(seg + 16u * m);
-  const float last = lds32(seg + 128u);
+  for (int m = 0; m < 4; m++) t[m] = lds128(seg + 16u * m);
+  const float last = lds32(seg + 64u);
   // zero, but data-dependent on every load (x * 0 is not foldable in IEEE arithmetic; the scalings are finite)
-  const float z = ((((t[0].x + t[1].x) + (t[2].x + t[3].x)) + ((t[4].x + t[5].x) + (t[6].x + t[7].x))) + last) * 0.f;
+  const float z = (((t[0].x + t[1].x) + (t[2].x + t[3].x)) + last) * 0.f;
 #pragma unroll
   for (int r = 0; r < RB; r++) s[r] = z;
 #pragma unroll
-  for (int m = 0; m < 8; m++) {
+  for (int m = 0; m < 4; m++) {
 #pragma unroll
     for (int r = 0; r < RB; r++) {
       s[r] = fmaf(k[r][4 * m], t[m].x, s[r]);
@@ -132,10 +136,11 @@ __device__ __forceinline__ void dot_block(const float (&k)[RB][PB], uint32_t seg
     }
   }
 #pragma unroll
-  for (int r = 0; r < RB; r++) {
-    s[r] = fmaf(k[r][32], last, s[r]);
-    s[r] += __shfl_xor_sync(0xffffffffu, s[r], 1);
-    s[r] += __shfl_xor_sync(0xffffffffu, s[r], 2);
+  for (int r = 0; r < RB; r++) s[r] = fmaf(k[r][16], last, s[r]);
+#pragma unroll
+  for (int d = 1; d < PH; d <<= 1) {
+#pragma unroll
+    for (int r = 0; r < RB; r++) s[r] += __shfl_xor_sync(0xffffffffu, s[r], d);
   }
 }
 
@@ -151,11 +156,9 @@ __global__ void __launch_bounds__(kPatchThreads, 1) sinkhorn_patch_kernel(Sinkho
   float* log_mu = nu + PP;
   float* log_nu = log_mu + PP;
   const int b = blockIdx.x, tid = threadIdx.x;
-  const bool col_role = tid >= kPatchRoleThreads;
-  const int rt = col_role ? tid - kPatchRoleThreads : tid;
-  const int g = rt >> 2, h = rt & 3;
+  const int g = tid >> 3, h = tid & (PH - 1);
   const bool active = g < NG;                    // 44 groups of 3 rows (columns)
-  const bool finisher = active && h < RB;        // lane h < 3 finishes row (column) 3 g + h
+  const bool finisher = active && h < RB;        // lane h < 3 finishes row AND column 3 g + h
   const int mine = finisher ? RB * g + h : PP - 1;   // pad row otherwise (marginal 0)
   const float alpha = *a.alpha;
   const uint8_t* rm = a.row_mask ? a.row_mask + (size_t)b * PN : nullptr;
@@ -224,16 +227,16 @@ __global__ void __launch_bounds__(kPatchThreads, 1) sinkhorn_patch_kernel(Sinkho
   }
   __syncthreads();
 
-  float k[RB][PB];        // this thread's block of the absorbed plan
+  float kr[RB][PB], kc[RB][PB];        // this thread's row-form and column-form blocks of the absorbed plan
 #pragma unroll
   for (int r = 0; r < RB; r++)
 #pragma unroll
-    for (int c = 0; c < PB; c++) k[r][c] = 0.f;
+    for (int c = 0; c < PB; c++) kr[r][c] = kc[r][c] = 0.f;
   int p = 0;              // current scaling buffer
   bool lin = false, need_absorb = false;   // block-uniform
   int it = 0, streak = 0;                  // streak: LIN iterations since the last absorption
   unsigned n_log = 0, n_lin = 0, n_disc = 0, n_abs = 0;
-  const float my_marg = col_role ? nu[mine] : mu[mine];
+  const float my_mu = mu[mine], my_nu = nu[mine];
   const int my_slot = vec_slot(mine);
   while (it < a.iters) {
     if (need_absorb) {
@@ -241,14 +244,13 @@ __global__ void __launch_bounds__(kPatchThreads, 1) sinkhorn_patch_kernel(Sinkho
       if (active) {
 #pragma unroll
         for (int r = 0; r < RB; r++) {
-          const int x = RB * g + r;                // row (row role) or column (column role)
+          const int x = RB * g + r;                // row of the row-form block, column of the column-form block
 #pragma unroll
           for (int c = 0; c < PB; c++) {
-            const int y = PB * h + c;              // column (row role) or row (column role)
-            float val = 0.f;
-            if (x < PR && y < PR)
-              val = col_role ? sk_exp(S[y * PLD + x] + u[y] + v[x]) : sk_exp(S[x * PLD + y] + u[x] + v[y]);
-            k[r][c] = val;
+            const int y = PB * h + c;              // column of the row-form block, row of the column-form block
+            const bool in = x < PR && y < PR;
+            kr[r][c] = in ? sk_exp(S[x * PLD + y] + u[x] + v[y]) : 0.f;
+            kc[r][c] = in ? sk_exp(S[y * PLD + x] + u[y] + v[x]) : 0.f;
           }
         }
       }
@@ -267,28 +269,27 @@ __global__ void __launch_bounds__(kPatchThreads, 1) sinkhorn_patch_kernel(Sinkho
     if (lin) {
       // tight loop over consecutive LIN iterations; leaves on the first out-of-band scaling (fail) or at the end
       const uint32_t la_s = (uint32_t)__cvta_generic_to_shared(la), lb_s = (uint32_t)__cvta_generic_to_shared(lb);
-      const uint32_t seg_off = 4u * 36u * (uint32_t)h, slot_off = 4u * (uint32_t)my_slot;
+      const uint32_t seg_off = 4u * PSEG * (uint32_t)h, slot_off = 4u * (uint32_t)my_slot;
       bool fail = false;
       while (it < a.iters) {
         const uint32_t cur = 4u * PV * (uint32_t)p, nxt = 4u * PV * (uint32_t)(p ^ 1);
-        bool bad = false;
-        if (!col_role) {
+        bool bad;
+        {
           float s[RB];
-          dot_block(k, lb_s + cur + seg_off, s);
+          dot_block(kr, lb_s + cur + seg_off, s);
           const float sum = h == 0 ? s[0] : h == 1 ? s[1] : s[2];
-          const float an = my_marg > 0.f ? __fdividef(my_marg, sum) : 0.f;
-          bad = my_marg > 0.f && !(an < kHi && an > kLo);
+          const float an = my_mu > 0.f ? __fdividef(my_mu, sum) : 0.f;
+          bad = my_mu > 0.f && !(an < kHi && an > kLo);
           if (finisher) sts32(la_s + nxt + slot_off, an);
         }
         fail = __syncthreads_or(bad) != 0;
         if (fail) break;
-        bad = false;
-        if (col_role) {
+        {
           float s[RB];
-          dot_block(k, la_s + nxt + seg_off, s);
+          dot_block(kc, la_s + nxt + seg_off, s);
           const float sum = h == 0 ? s[0] : h == 1 ? s[1] : s[2];
-          const float bn = my_marg > 0.f ? __fdividef(my_marg, sum) : 0.f;
-          bad = my_marg > 0.f && !(bn < kHi && bn > kLo);
+          const float bn = my_nu > 0.f ? __fdividef(my_nu, sum) : 0.f;
+          bad = my_nu > 0.f && !(bn < kHi && bn > kLo);
           if (finisher) sts32(lb_s + nxt + slot_off, bn);
         }
         fail = __syncthreads_or(bad) != 0;
@@ -314,31 +315,63 @@ __global__ void __launch_bounds__(kPatchThreads, 1) sinkhorn_patch_kernel(Sinkho
       }
       lin = false;           // a single step left the band (> e^30): redo the iteration in LOG form
     }
-    // ---- LOG iteration on the shared-memory scores: one thread per row, then one thread per column
+    // ---- LOG iteration on the shared-memory scores: two threads per row (then per column), lanes 0-15 of a warp
+    // take elements 0..63 and the dustbin of 16 consecutive lines, lanes 16-31 elements 64..127 of the same lines in an
+    // order rotated by 16 -- with the odd line stride (129) both halves then sit on disjoint banks in either direction
     float step = 0.f;
-    if (tid < PR) {
-      const float* row = S + tid * PLD;
-      float mx = -INFINITY;
+    {
+      const int line = 16 * (tid >> 5) + (tid & 15), q = (tid >> 4) & 1;
+      const bool on = line < PR;
+      // max-subtracted logsumexp over this thread's half of `line`; element e at S[line * sl + e * se], potential pot[e]
+      auto half_lse = [&](int sl, int se, const float* pot, float& mx, float& sum) {
+        const float* base = S + line * sl;
+        mx = -INFINITY;
+        if (q == 0) {
 #pragma unroll 4
-      for (int j = 0; j < PR; j++) mx = fmaxf(mx, row[j] + v[j]);
-      float sum = 0.f;
+          for (int e = 0; e < 64; e++) mx = fmaxf(mx, base[e * se] + pot[e]);
+          mx = fmaxf(mx, base[PN * se] + pot[PN]);
+        } else {
 #pragma unroll 4
-      for (int j = 0; j < PR; j++) sum += sk_exp(row[j] + v[j] - mx);
-      const float un = log_mu[tid] - (mx + logf(sum));
-      if (mu[tid] > 0.f) step = fabsf(un - u[tid]);
-      u[tid] = un;
-    }
-    __syncthreads();
-    if (tid < PR) {
-      float mx = -INFINITY;
+          for (int k = 0; k < 64; k++) {
+            const int e = 64 + ((k + 16) & 63);
+            mx = fmaxf(mx, base[e * se] + pot[e]);
+          }
+        }
+        sum = 0.f;
+        if (q == 0) {
 #pragma unroll 4
-      for (int i = 0; i < PR; i++) mx = fmaxf(mx, S[i * PLD + tid] + u[i]);
-      float sum = 0.f;
+          for (int e = 0; e < 64; e++) sum += sk_exp(base[e * se] + pot[e] - mx);
+          sum += sk_exp(base[PN * se] + pot[PN] - mx);
+        } else {
 #pragma unroll 4
-      for (int i = 0; i < PR; i++) sum += sk_exp(S[i * PLD + tid] + u[i] - mx);
-      const float vn = log_nu[tid] - (mx + logf(sum));
-      if (nu[tid] > 0.f) step = fmaxf(step, fabsf(vn - v[tid]));
-      v[tid] = vn;
+          for (int k = 0; k < 64; k++) {
+            const int e = 64 + ((k + 16) & 63);
+            sum += sk_exp(base[e * se] + pot[e] - mx);
+          }
+        }
+      };
+      auto merged_lse = [&](float mx, float sum) -> float {      // combine the two halves (lanes l and l ^ 16)
+        const float om = __shfl_xor_sync(0xffffffffu, mx, 16), os = __shfl_xor_sync(0xffffffffu, sum, 16);
+        const float m = fmaxf(mx, om);
+        return m + logf(sum * sk_exp(mx - m) + os * sk_exp(om - m));
+      };
+      float mx = 0.f, sum = 1.f;
+      if (on) half_lse(PLD, 1, v, mx, sum);
+      const float lse_r = merged_lse(mx, sum);
+      if (on && q == 0) {
+        const float un = log_mu[line] - lse_r;
+        if (mu[line] > 0.f) step = fabsf(un - u[line]);
+        u[line] = un;
+      }
+      __syncthreads();
+      mx = 0.f, sum = 1.f;
+      if (on) half_lse(1, PLD, u, mx, sum);
+      const float lse_c = merged_lse(mx, sum);
+      if (on && q == 0) {
+        const float vn = log_nu[line] - lse_c;
+        if (nu[line] > 0.f) step = fmaxf(step, fabsf(vn - v[line]));
+        v[line] = vn;
+      }
     }
     const bool big = __syncthreads_or(!(step < kBigStep)) != 0;
     it++;
@@ -362,9 +395,9 @@ __global__ void __launch_bounds__(kPatchThreads, 1) sinkhorn_patch_kernel(Sinkho
   }
   __syncthreads();
   float* dst = a.out + (size_t)b * PR * PR;
-  for (int e = tid; e < PR * PR; e += kPatchThreads) {
-    const int i = e / PR, j = e - i * PR;
-    dst[e] = S[i * PLD + j] + u[i] + v[j] - norm;
+  for (int i = tid >> 5; i < PR; i += kPatchThreads / 32) {     // warp per row: no integer division per element
+    const float ui = u[i] - norm;
+    for (int j = tid & 31; j < PR; j += 32) dst[i * PR + j] = S[i * PLD + j] + ui + v[j];
   }
 }
 
@@ -580,6 +613,373 @@ __global__ void __launch_bounds__(kGenThreads) sinkhorn_general_kernel(SinkhornA
   }
 }
 
+
+// ================================================================== node level on a thread-block cluster
+// One CLUSTER of CL CTAs per problem: rank r keeps rows [r rs, (r + 1) rs) of the plan in SHARED memory (a 98 x 388
+// slab = 150 KB for the ~390 x 385 node problems), so a LIN iteration reads the plan from shared memory instead of
+// L2 (the single-CTA kernel above is bound by L2 latency: 55 us per iteration, 32 CTAs on a 148-SM GPU).  The row
+// update is local to a rank (a_i only feeds the column sums of the same rows); the column update needs the sum over
+// all ranks: every rank writes its partial column sums (LOG form: partial max / sum pairs) and its "row check
+// failed" flag into EVERY peer's shared memory through DSMEM, one cluster barrier, then all ranks combine the CL
+// partials in rank order -- bit-identical b_j, potentials and control decisions on every rank, no second barrier.
+// The exchange buffers are double-buffered on the exchange counter: a peer can run at most one exchange ahead.
+constexpr int kClThreads = 512;
+constexpr int kClChunks = 16;                      // columns <= 32 * kClChunks
+constexpr size_t kClSmemMax = 226 * 1024;          // 227 KB opt-in limit minus the static shared memory
+
+__host__ __device__ inline size_t cluster_smem_floats(int CL, int C, int rs) {
+  const size_t Cs = (size_t)(C + 3) & ~(size_t)3;
+  return (size_t)rs * Cs      // plan slab
+         + 6 * (size_t)rs     // u, la x 2, mu, log_mu, row mask of the local rows
+         + 6 * Cs             // v, lb x 2, nu, log_nu, column mask (replicated)
+         + 4 * CL * Cs        // exchange: [2 buffers][2 planes][CL ranks][Cs]
+         + 2 * CL + 8;        // flags [2][CL]
+}
+
+template <int CL>
+__global__ void __launch_bounds__(kClThreads, 1) sinkhorn_cluster_kernel(SinkhornArgs a, int rs) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  extern __shared__ __align__(16) float sm[];
+  const int M = a.M, N = a.N, R = M + 1, C = N + 1;
+  const int Cs = (C + 3) & ~3;
+  const int rank = (int)cluster.block_rank();
+  const int b = blockIdx.x / CL, tid = threadIdx.x, nt = kClThreads;
+  const int lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+  const int i0 = rank * rs, nloc = max(0, min(rs, R - i0));
+  float* Ks = sm;                          // [rs][Cs]
+  float* u = Ks + (size_t)rs * Cs;         // local rows
+  float* la = u + rs;                      // [2][rs]
+  float* mu = la + 2 * rs;
+  float* log_mu = mu + rs;
+  float* rmask = log_mu + rs;              // 1 = valid row (the dustbin row is valid)
+  float* v = rmask + rs;                   // replicated columns
+  float* lb = v + Cs;                      // [2][Cs]
+  float* nu = lb + 2 * Cs;
+  float* log_nu = nu + Cs;
+  float* cmask = log_nu + Cs;
+  float* exch = cmask + Cs;                // [2][2][CL][Cs]
+  int* flags = reinterpret_cast<int*>(exch + 4 * CL * Cs);   // [2][CL]
+  const float alpha = *a.alpha;
+  const uint8_t* rm = a.row_mask ? a.row_mask + (size_t)b * M : nullptr;
+  const uint8_t* cm = a.col_mask ? a.col_mask + (size_t)b * N : nullptr;
+  const float* src = a.scores + (size_t)b * M * N;
+  float* out = a.out + (size_t)b * R * C;
+  float* peer_exch[CL];
+  int* peer_flags[CL];
+#pragma unroll
+  for (int r = 0; r < CL; r++) {
+    peer_exch[r] = cluster.map_shared_rank(exch, r);
+    peer_flags[r] = cluster.map_shared_rank(flags, r);
+  }
+  // padded, masked score of local row i (global row i0 + i) and column j, masks from shared memory
+  auto score = [&](int i, int j) -> float {
+    if (rmask[i] == 0.f || cmask[j] == 0.f) return -kInf;
+    return (i0 + i < M && j < N) ? src[(size_t)(i0 + i) * N + j] : alpha;
+  };
+
+  __shared__ int s_cnt[2];
+  if (tid < 2) s_cnt[tid] = 0;
+  __syncthreads();
+  int c0 = 0, c1 = 0;
+  for (int i = tid; i < M; i += nt) c0 += rm ? rm[i] : 1;
+  for (int j = tid; j < N; j += nt) c1 += cm ? cm[j] : 1;
+  c0 = lcr_warp_sum(c0);
+  c1 = lcr_warp_sum(c1);
+  if (lane == 0) {
+    atomicAdd(&s_cnt[0], c0);
+    atomicAdd(&s_cnt[1], c1);
+  }
+  __syncthreads();
+  const float nvr = (float)s_cnt[0], nvc = (float)s_cnt[1];
+  const float norm = -logf(nvr + nvc);
+  for (int i = tid; i < nloc; i += nt) {
+    const int gi = i0 + i;
+    const bool masked = gi < M && rm && !rm[gi];
+    const float lm = masked ? -kInf : (gi < M ? norm : logf(nvc) + norm);
+    log_mu[i] = lm;
+    mu[i] = lm > -1e11f ? expf(lm) : 0.f;
+    rmask[i] = masked ? 0.f : 1.f;
+    u[i] = 0.f;
+  }
+  for (int j = tid; j < C; j += nt) {
+    const bool masked = j < N && cm && !cm[j];
+    const float ln = masked ? -kInf : (j < N ? norm : logf(nvr) + norm);
+    log_nu[j] = ln;
+    nu[j] = ln > -1e11f ? expf(ln) : 0.f;
+    cmask[j] = masked ? 0.f : 1.f;
+    v[j] = 0.f;
+  }
+  cluster.sync();        // every rank's shared memory is live before the first remote store
+
+  int p = 0, x = 0;      // scaling buffer, exchange counter
+  bool lin = false, need_absorb = false;
+  int it = 0, streak = 0;
+  unsigned n_log = 0, n_lin = 0, n_disc = 0, n_abs = 0;
+  while (it < a.iters) {
+    if (need_absorb) {
+      for (int i = warp; i < nloc; i += nw) {      // warp per row, lanes over columns: coalesced score loads
+        const float ui = u[i];
+        float sc[kClChunks];
+#pragma unroll
+        for (int k = 0; k < kClChunks; k++) {
+          const int j = lane + 32 * k;
+          sc[k] = j < C ? score(i, j) : 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < kClChunks; k++) {
+          const int j = lane + 32 * k;
+          if (j < C) Ks[(size_t)i * Cs + j] = sk_exp(sc[k] + ui + v[j]);
+        }
+      }
+      for (int i = tid; i < nloc; i += nt) {
+        la[p * rs + i] = 1.f;
+        la[(p ^ 1) * rs + i] = 0.f;
+      }
+      for (int j = tid; j < C; j += nt) {
+        lb[p * Cs + j] = 1.f;
+        lb[(p ^ 1) * Cs + j] = 0.f;
+      }
+      __syncthreads();
+      need_absorb = false;
+      streak = 0;
+      n_abs++;
+    }
+    float* ex = exch + (size_t)(x & 1) * 2 * CL * Cs;           // this exchange: [2][CL][Cs]
+    const size_t ex_off = (size_t)(x & 1) * 2 * CL * Cs + (size_t)rank * Cs;
+    int* fl = flags + (x & 1) * CL;
+    if (lin) {
+      float* a_new = la + (p ^ 1) * rs;
+      float* b_new = lb + (p ^ 1) * Cs;
+      const float* b_cur = lb + p * Cs;
+      bool bad = false;
+      {
+        float bc[kClChunks];                        // this lane's columns of the current scalings
+#pragma unroll
+        for (int k = 0; k < kClChunks; k++) {
+          const int j = lane + 32 * k;
+          bc[k] = j < C ? b_cur[j] : 0.f;
+        }
+        for (int i = warp; i < nloc; i += nw) {     // warp per row of the slab
+          const float* row = Ks + (size_t)i * Cs;
+          float kv[kClChunks];
+#pragma unroll
+          for (int k = 0; k < kClChunks; k++) {
+            const int j = lane + 32 * k;
+            kv[k] = j < C ? row[j] : 0.f;
+          }
+          float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+          for (int k = 0; k < kClChunks; k += 4) {
+            s0 = fmaf(kv[k], bc[k], s0);
+            s1 = fmaf(kv[k + 1], bc[k + 1], s1);
+            s2 = fmaf(kv[k + 2], bc[k + 2], s2);
+            s3 = fmaf(kv[k + 3], bc[k + 3], s3);
+          }
+          const float sum = lcr_warp_sum((s0 + s1) + (s2 + s3));
+          if (lane == 0) {
+            const float m_ = mu[i];
+            float an = 0.f;
+            if (m_ > 0.f) {
+              an = __fdividef(m_, sum);
+              bad |= !(an < kHi && an > kLo);
+            }
+            a_new[i] = an;
+          }
+        }
+      }
+      const int row_bad = __syncthreads_or(bad);
+      for (int j = tid; j < C; j += nt) {           // thread per column over the slab's rows
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        int i = 0;
+        for (; i + 3 < nloc; i += 4) {
+          s0 = fmaf(Ks[(size_t)i * Cs + j], a_new[i], s0);
+          s1 = fmaf(Ks[(size_t)(i + 1) * Cs + j], a_new[i + 1], s1);
+          s2 = fmaf(Ks[(size_t)(i + 2) * Cs + j], a_new[i + 2], s2);
+          s3 = fmaf(Ks[(size_t)(i + 3) * Cs + j], a_new[i + 3], s3);
+        }
+        for (; i < nloc; i++) s0 = fmaf(Ks[(size_t)i * Cs + j], a_new[i], s0);
+        const float part = (s0 + s1) + (s2 + s3);
+#pragma unroll
+        for (int r = 0; r < CL; r++) peer_exch[r][ex_off + j] = part;
+      }
+      if (tid < CL) peer_flags[tid][(x & 1) * CL + rank] = row_bad;
+      cluster.sync();
+      bad = false;
+      for (int j = tid; j < C; j += nt) {
+        float sum = 0.f;
+#pragma unroll
+        for (int r = 0; r < CL; r++) sum += ex[(size_t)r * Cs + j];
+        const float n_ = nu[j];
+        float bn = 0.f;
+        if (n_ > 0.f) {
+          bn = __fdividef(n_, sum);
+          bad |= !(bn < kHi && bn > kLo);
+        }
+        b_new[j] = bn;
+      }
+#pragma unroll
+      for (int r = 0; r < CL; r++) bad |= fl[r] != 0;
+      const bool fail = __syncthreads_or(bad) != 0;
+      x++;
+      if (!fail) {
+        p ^= 1;
+        it++;
+        streak++;
+        n_lin++;
+        continue;
+      }
+      n_disc++;
+      for (int i = tid; i < nloc; i += nt) {
+        const float av = la[p * rs + i];
+        if (av > 0.f) u[i] += logf(av);
+      }
+      for (int j = tid; j < C; j += nt) {
+        const float bv = lb[p * Cs + j];
+        if (bv > 0.f) v[j] += logf(bv);
+      }
+      __syncthreads();
+      if (streak > 0) {
+        need_absorb = true;
+        continue;
+      }
+      lin = false;
+      continue;            // (the exchange buffers of the next round are selected at the top of the loop)
+    }
+    // ---- LOG iteration straight from the input scores
+    bool big = false;
+    for (int i = warp; i < nloc; i += nw) {
+      float sc[kClChunks];
+      float mx = -INFINITY;
+#pragma unroll
+      for (int k = 0; k < kClChunks; k++) {
+        const int j = lane + 32 * k;
+        sc[k] = j < C ? score(i, j) + v[j] : -INFINITY;
+        mx = fmaxf(mx, sc[k]);
+      }
+      mx = lcr_warp_max(mx);
+      float sum = 0.f;
+#pragma unroll
+      for (int k = 0; k < kClChunks; k++)
+        if (lane + 32 * k < C) sum += sk_exp(sc[k] - mx);
+      sum = lcr_warp_sum(sum);
+      if (lane == 0) {
+        const float un = log_mu[i] - (mx + logf(sum));
+        if (mu[i] > 0.f) big |= !(fabsf(un - u[i]) < kBigStep);
+        u[i] = un;
+      }
+    }
+    const int row_big = __syncthreads_or(big);
+    for (int j = tid; j < C; j += nt) {            // online max / sum over the slab's rows, 4 rows in flight
+      float mx = -INFINITY, sum = 0.f;
+      for (int i = 0; i < nloc; i += 4) {
+        float t[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) t[q] = i + q < nloc ? score(i + q, j) + u[i + q] : -INFINITY;
+        const float m4 = fmaxf(fmaxf(t[0], t[1]), fmaxf(t[2], t[3]));
+        if (m4 > mx) {
+          sum = mx > -INFINITY ? sum * sk_exp(mx - m4) : 0.f;   // (first group: nothing summed yet)
+          mx = m4;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+          if (i + q < nloc) sum += sk_exp(t[q] - mx);
+      }
+#pragma unroll
+      for (int r = 0; r < CL; r++) {
+        peer_exch[r][ex_off + j] = mx;
+        peer_exch[r][ex_off + (size_t)CL * Cs + j] = sum;
+      }
+    }
+    if (tid < CL) peer_flags[tid][(x & 1) * CL + rank] = row_big;
+    cluster.sync();
+    big = false;
+    for (int j = tid; j < C; j += nt) {
+      float mx = -INFINITY;
+#pragma unroll
+      for (int r = 0; r < CL; r++) mx = fmaxf(mx, ex[(size_t)r * Cs + j]);
+      float sum = 0.f;
+#pragma unroll
+      for (int r = 0; r < CL; r++) {
+        const float pm = ex[(size_t)r * Cs + j];
+        if (pm > -INFINITY) sum += ex[(size_t)(CL + r) * Cs + j] * sk_exp(pm - mx);
+      }
+      const float vn = log_nu[j] - (mx + logf(sum));
+      if (nu[j] > 0.f) big |= !(fabsf(vn - v[j]) < kBigStep);
+      v[j] = vn;
+    }
+#pragma unroll
+    for (int r = 0; r < CL; r++) big |= fl[r] != 0;
+    big = __syncthreads_or(big) != 0;
+    x++;
+    it++;
+    n_log++;
+    if (!big && it < a.iters) {
+      need_absorb = true;
+      lin = true;
+    }
+  }
+  if (tid == 0 && rank == 0) {
+    atomicAdd(&g_sk_stats[0], (unsigned long long)n_log);
+    atomicAdd(&g_sk_stats[1], (unsigned long long)n_lin);
+    atomicAdd(&g_sk_stats[2], (unsigned long long)n_disc);
+    atomicAdd(&g_sk_stats[3], (unsigned long long)n_abs);
+  }
+  if (lin && !need_absorb) {
+    for (int i = tid; i < nloc; i += nt) {
+      const float av = la[p * rs + i];
+      if (av > 0.f) u[i] += logf(av);
+    }
+    for (int j = tid; j < C; j += nt) {
+      const float bv = lb[p * Cs + j];
+      if (bv > 0.f) v[j] += logf(bv);
+    }
+  }
+  __syncthreads();
+  for (int i = warp; i < nloc; i += nw) {
+    const float ui = u[i] - norm;
+    float sc[kClChunks];
+#pragma unroll
+    for (int k = 0; k < kClChunks; k++) {
+      const int j = lane + 32 * k;
+      sc[k] = j < C ? score(i, j) : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < kClChunks; k++) {
+      const int j = lane + 32 * k;
+      if (j < C) out[(size_t)(i0 + i) * C + j] = sc[k] + ui + v[j];
+    }
+  }
+  cluster.sync();          // no rank may exit while a peer can still write into its shared memory
+}
+
+template <int CL>
+int launch_sinkhorn_cluster(const SinkhornArgs& a, int batch, int rs, size_t smem, cudaStream_t stream) {
+  static LcrOncePerDevice once;
+  const int dev = once.need();
+  if (dev != -1) {
+    LCR_CUDA_TRY(cudaFuncSetAttribute(sinkhorn_cluster_kernel<CL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)kClSmemMax));
+    if (CL > 8)
+      LCR_CUDA_TRY(cudaFuncSetAttribute(sinkhorn_cluster_kernel<CL>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    once.done(dev);
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)batch * CL);
+  cfg.blockDim = dim3(kClThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  LCR_CUDA_TRY(cudaLaunchKernelEx(&cfg, sinkhorn_cluster_kernel<CL>, a, rs));
+  return LCR_OK;
+}
+
 }  // namespace
 
 // Debug / tuning: iteration statistics of all Sinkhorn problems since the last reset (see g_sk_stats); synchronises.
@@ -615,11 +1015,29 @@ extern "C" int lcr_sinkhorn(const float* scores, int batch, int rows, int cols, 
     }
     sinkhorn_patch_kernel<<<batch, kPatchThreads, kPatchSmem, stream>>>(a);
   } else {
-    const size_t R = (size_t)rows + 1, C = (size_t)cols + 1;
-    const size_t smem = sizeof(float) * (5 * R + 5 * C + 2 * (kGenThreads / 32) * C) + 64;
-    LCR_REQUIRE(smem <= 200 * 1024, "sinkhorn: problem too large (5 (rows + cols) + 64 cols floats of shared memory)");
-    LCR_CUDA_TRY(cudaFuncSetAttribute(sinkhorn_general_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    sinkhorn_general_kernel<<<batch, kGenThreads, smem, stream>>>(a);
+    const int R = rows + 1, C = cols + 1;
+    // 0: single-CTA kernel; otherwise the smallest cluster (4, then 8 CTAs per problem) whose row slab fits
+    static const int use_cluster = getenv("LCR_SINKHORN_CLUSTER") ? atoi(getenv("LCR_SINKHORN_CLUSTER")) : 1;
+    int cl = 0;
+    for (int c : {4, 8}) {
+      if (use_cluster > 1 && c != use_cluster) continue;       // 4 / 8: force that cluster size (tests)
+      if (C <= 32 * kClChunks && sizeof(float) * cluster_smem_floats(c, C, (R + c - 1) / c) <= kClSmemMax) {
+        cl = c;
+        break;
+      }
+    }
+    if (use_cluster && cl) {
+      const int rs = (R + cl - 1) / cl;
+      const size_t cl_smem = sizeof(float) * cluster_smem_floats(cl, C, rs);
+      const int rc = cl == 4 ? launch_sinkhorn_cluster<4>(a, batch, rs, cl_smem, stream)
+                             : launch_sinkhorn_cluster<8>(a, batch, rs, cl_smem, stream);
+      if (rc != LCR_OK) return rc;
+    } else {
+      const size_t smem = sizeof(float) * (5 * (size_t)R + 5 * (size_t)C + 2 * (kGenThreads / 32) * (size_t)C) + 64;
+      LCR_REQUIRE(smem <= 200 * 1024, "sinkhorn: problem too large (5 (rows + cols) + 64 cols floats of shared memory)");
+      LCR_CUDA_TRY(cudaFuncSetAttribute(sinkhorn_general_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      sinkhorn_general_kernel<<<batch, kGenThreads, smem, stream>>>(a);
+    }
   }
   LCR_LAUNCHED(1);
   LCR_CUDA_CHECK_LAUNCH();

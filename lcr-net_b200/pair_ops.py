@@ -170,10 +170,12 @@ def fine_correspondences(log_scores, knn_mask_a, node_a, knn_mask_b, node_b):
          'pair': torch.empty(cap, dtype=torch.int32, device=dev), 'i': torch.empty(cap, dtype=torch.int32, device=dev),
          'j': torch.empty(cap, dtype=torch.int32, device=dev), 'score': torch.empty(cap, dtype=torch.float32, device=dev)}
     ma, mb = knn_mask_a.to(torch.uint8).contiguous(), knn_mask_b.to(torch.uint8).contiguous()
+    ws = torch.empty(max(int(_L().lcr_fine_correspondences_ws_bytes(p)), 1), dtype=torch.uint8, device=dev)
     _lib.check(_L().lcr_fine_correspondences(_lib.ptr(_f32c(log_scores)), p, _lib.ptr(ma), _lib.ptr(node_a),
                                              _lib.ptr(mb), _lib.ptr(node_b), _lib.ptr(r['pair_cnt']),
                                              _lib.ptr(r['pair_off']), _lib.ptr(r['pair']), _lib.ptr(r['i']),
-                                             _lib.ptr(r['j']), _lib.ptr(r['score']), _s(log_scores)))
+                                             _lib.ptr(r['j']), _lib.ptr(r['score']), _lib.ptr(ws), ws.numel(),
+                                             _s(log_scores)))
     return r
 
 

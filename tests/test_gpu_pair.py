@@ -284,6 +284,36 @@ def test_demo_pair_and_batched_pairs(net):
         assert abs(n1 - n2) <= max(2, n1 // 200)
 
 
+def test_pair_pipeline_chunks_equal_single_forward(net):
+    """pipeline.PairPipeline (the call bench.py's registration workload times): host points in, per-pair dicts out;
+    one chunk and two chunks on two streams / host threads give the poses and descriptors of the plain forward."""
+    from lcrnet_b200 import data as gdata
+    from lcrnet_b200 import pipeline, synth
+    scans = []
+    for s in (7, 8, 9):
+        ref, src, _ = synth.make_pair(s, 200 + s)
+        scans += [np.ascontiguousarray(ref[::6]), np.ascontiguousarray(src[::6])]
+    pts = torch.from_numpy(np.concatenate(scans, 0)).pin_memory()
+    lens = [len(x) for x in scans]
+    want = net(gdata.scans_collate_fn_stack_mode(scans, 4, 0.3, 1.275, LIMITS, pre_voxel=0.3, stack_size=2, int32=True,
+                                                 upsampling=True))
+    for n_streams in (1, 2):
+        pipe = pipeline.PairPipeline(net, LIMITS, n_streams=n_streams)
+        outs = pipe(pts, lens)
+        pipe.close()
+        torch.cuda.synchronize()
+        assert len(outs) == 3
+        for p, o in enumerate(outs):
+            T, Tw = o['estimated_transform'].cpu(), want['estimated_transform'][p].cpu()
+            same = o['corr_scores'].shape[0] == want['corr_scores'][p].shape[0]
+            if same:
+                assert float((T - Tw).abs().max()) < 1e-4 * max(1.0, float(Tw.abs().max()))
+            Tc = po.lgr_from_lists(o['pos_corr_points'].cpu(), o['anc_corr_points'].cpu(), o['corr_scores'].cpu(),
+                                   o['_corr_patch'].cpu().long())
+            assert float((T - Tc).abs().max()) < 1e-4 * max(1.0, float(Tc.abs().max()))
+            assert float((o['pos_feature_global'] - want['pos_feature_global'][p]).norm()) < 1e-5
+
+
 def test_loop_candidates_vs_oracle():
     from lcrnet_b200 import retrieval
     rng = np.random.default_rng(4)
