@@ -315,63 +315,31 @@ __global__ void __launch_bounds__(kPatchThreads, 1) sinkhorn_patch_kernel(Sinkho
       }
       lin = false;           // a single step left the band (> e^30): redo the iteration in LOG form
     }
-    // ---- LOG iteration on the shared-memory scores: two threads per row (then per column), lanes 0-15 of a warp
-    // take elements 0..63 and the dustbin of 16 consecutive lines, lanes 16-31 elements 64..127 of the same lines in an
-    // order rotated by 16 -- with the odd line stride (129) both halves then sit on disjoint banks in either direction
+    // ---- LOG iteration on the shared-memory scores: one thread per row, then one thread per column
     float step = 0.f;
-    {
-      const int line = 16 * (tid >> 5) + (tid & 15), q = (tid >> 4) & 1;
-      const bool on = line < PR;
-      // max-subtracted logsumexp over this thread's half of `line`; element e at S[line * sl + e * se], potential pot[e]
-      auto half_lse = [&](int sl, int se, const float* pot, float& mx, float& sum) {
-        const float* base = S + line * sl;
-        mx = -INFINITY;
-        if (q == 0) {
+    if (tid < PR) {
+      const float* row = S + tid * PLD;
+      float mx = -INFINITY;
 #pragma unroll 4
-          for (int e = 0; e < 64; e++) mx = fmaxf(mx, base[e * se] + pot[e]);
-          mx = fmaxf(mx, base[PN * se] + pot[PN]);
-        } else {
+      for (int j = 0; j < PR; j++) mx = fmaxf(mx, row[j] + v[j]);
+      float sum = 0.f;
 #pragma unroll 4
-          for (int k = 0; k < 64; k++) {
-            const int e = 64 + ((k + 16) & 63);
-            mx = fmaxf(mx, base[e * se] + pot[e]);
-          }
-        }
-        sum = 0.f;
-        if (q == 0) {
+      for (int j = 0; j < PR; j++) sum += sk_exp(row[j] + v[j] - mx);
+      const float un = log_mu[tid] - (mx + logf(sum));
+      if (mu[tid] > 0.f) step = fabsf(un - u[tid]);
+      u[tid] = un;
+    }
+    __syncthreads();
+    if (tid < PR) {
+      float mx = -INFINITY;
 #pragma unroll 4
-          for (int e = 0; e < 64; e++) sum += sk_exp(base[e * se] + pot[e] - mx);
-          sum += sk_exp(base[PN * se] + pot[PN] - mx);
-        } else {
+      for (int i = 0; i < PR; i++) mx = fmaxf(mx, S[i * PLD + tid] + u[i]);
+      float sum = 0.f;
 #pragma unroll 4
-          for (int k = 0; k < 64; k++) {
-            const int e = 64 + ((k + 16) & 63);
-            sum += sk_exp(base[e * se] + pot[e] - mx);
-          }
-        }
-      };
-      auto merged_lse = [&](float mx, float sum) -> float {      // combine the two halves (lanes l and l ^ 16)
-        const float om = __shfl_xor_sync(0xffffffffu, mx, 16), os = __shfl_xor_sync(0xffffffffu, sum, 16);
-        const float m = fmaxf(mx, om);
-        return m + logf(sum * sk_exp(mx - m) + os * sk_exp(om - m));
-      };
-      float mx = 0.f, sum = 1.f;
-      if (on) half_lse(PLD, 1, v, mx, sum);
-      const float lse_r = merged_lse(mx, sum);
-      if (on && q == 0) {
-        const float un = log_mu[line] - lse_r;
-        if (mu[line] > 0.f) step = fabsf(un - u[line]);
-        u[line] = un;
-      }
-      __syncthreads();
-      mx = 0.f, sum = 1.f;
-      if (on) half_lse(1, PLD, u, mx, sum);
-      const float lse_c = merged_lse(mx, sum);
-      if (on && q == 0) {
-        const float vn = log_nu[line] - lse_c;
-        if (nu[line] > 0.f) step = fmaxf(step, fabsf(vn - v[line]));
-        v[line] = vn;
-      }
+      for (int i = 0; i < PR; i++) sum += sk_exp(S[i * PLD + tid] + u[i] - mx);
+      const float vn = log_nu[tid] - (mx + logf(sum));
+      if (nu[tid] > 0.f) step = fmaxf(step, fabsf(vn - v[tid]));
+      v[tid] = vn;
     }
     const bool big = __syncthreads_or(!(step < kBigStep)) != 0;
     it++;
@@ -395,9 +363,9 @@ __global__ void __launch_bounds__(kPatchThreads, 1) sinkhorn_patch_kernel(Sinkho
   }
   __syncthreads();
   float* dst = a.out + (size_t)b * PR * PR;
-  for (int i = tid >> 5; i < PR; i += kPatchThreads / 32) {     // warp per row: no integer division per element
-    const float ui = u[i] - norm;
-    for (int j = tid & 31; j < PR; j += 32) dst[i * PR + j] = S[i * PLD + j] + ui + v[j];
+  for (int e = tid; e < PR * PR; e += kPatchThreads) {
+    const int i = e / PR, j = e - i * PR;
+    dst[e] = S[i * PLD + j] + u[i] + v[j] - norm;
   }
 }
 
