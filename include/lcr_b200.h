@@ -243,6 +243,11 @@ int lcr_attention(const float* q, int ld_q, const float* k, int ld_k, const floa
 int lcr_attention_tc(const float* q, int ld_q, const float* k, int ld_k, const float* v, int ld_v,
                      const int64_t* q_off, const int64_t* k_off, int n_problems, int64_t max_q_rows, int heads,
                      int head_dim, float* out, int ld_out, double flops_hint, void* stream);
+/* lcr_attention_tma: the same operator with every q / k / v tile fetched by ONE TMA tensor copy (CUtensorMap with
+ * the 128-byte swizzle) -- the default; q_rows / k_rows = row counts of the q and the k / v operands. */
+int lcr_attention_tma(const float* q, int ld_q, int64_t q_rows, const float* k, int ld_k, const float* v, int ld_v,
+                      int64_t k_rows, const int64_t* q_off, const int64_t* k_off, int n_problems, int64_t max_q_rows,
+                      int heads, int head_dim, float* out, int ld_out, double flops_hint, void* stream);
 
 int lcr_vote_shift(const float* points, const float* offsets, int ld_offsets, float max_range, int64_t n, float* out,
                    void* stream);

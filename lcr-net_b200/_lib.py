@@ -60,6 +60,8 @@ SIGNATURES = {
                               c_i32, ctypes.c_double, c_vp]),
     'lcr_attention_tc': (c_i32, [c_vp, c_i32, c_vp, c_i32, c_vp, c_i32, c_vp, c_vp, c_i32, c_i64, c_i32, c_i32, c_vp,
                                  c_i32, ctypes.c_double, c_vp]),
+    'lcr_attention_tma': (c_i32, [c_vp, c_i32, c_i64, c_vp, c_i32, c_vp, c_i32, c_i64, c_vp, c_vp, c_i32, c_i64, c_i32, c_i32,
+                                  c_vp, c_i32, ctypes.c_double, c_vp]),
     'lcr_vote_shift': (c_i32, [c_vp, c_vp, c_i32, c_f32, c_i64, c_vp, c_vp]),
     'lcr_nms_greedy': (c_i32, [c_vp, c_vp, c_i32, c_i64, c_f32, c_vp, c_vp, c_vp, c_vp]),
     'lcr_neighbor_mean': (c_i32, [c_vp, c_i64, c_vp, c_i32, c_i32, c_i64, c_vp, c_vp]),

@@ -18,6 +18,8 @@
 //             accuracy, which the discrete stages downstream of the transformer (NMS, arg-max
 //             correspondences) need; completion via tcgen05.commit -> mbarrier.
 // TMEM: S in columns [0, 64), O_j in [64, 96), P_hi in [96, 160), P_lo in [160, 224).
+#include <cuda.h>
+
 #include "common.cuh"
 
 namespace {
@@ -338,6 +340,257 @@ attention_tc_kernel(const float* __restrict__ q, int ld_q, const float* __restri
   }
 }
 
+
+// ================================================================== tensor-map variant (default)
+// Same pipeline, but every tile is ONE TMA tensor copy (cp.async.bulk.tensor.2d through a CUtensorMap over the
+// [rows, heads * 32] operand with the 128-byte swizzle) instead of 64 / 128 per-row bulk copies issued lane by lane:
+// the tile lands in the canonical K-major SWIZZLE_128B layout, so the raw fp32 Q and K tiles ARE the `hi` operands
+// (kind::tf32 reads the upper 19 bits: the tensor core truncates) and the workers only write lo = x - trunc(x);
+// V is still transposed by the workers (keys become the K dimension of the second MMA), now from conflict-free
+// 16-byte reads of the swizzled tile (the per-row staging buffer had all 32 lanes on one bank).  Rows past the end of
+// a problem belong to the next problem (or are zero-filled past the tensor): their scores are masked to -inf before
+// the softmax and V rows past the end are zeroed, Q rows past the end are never stored.
+constexpr int k2Qhi = 0, k2Qlo = 16384;                    // 128 x 32 (hi = raw TMA tile)
+constexpr int k2Kraw = 32768;                              // 64 x 32, two stages (+ 8192): the hi operand
+constexpr int k2Klo = 49152;
+constexpr int k2Vraw = 57344;                              // 64 x 32, two stages (+ 8192)
+constexpr int k2Vhi = 73728, k2Vlo = 81920;                // V^T: 2 sub-tiles of 32 (dims) x 32 (keys)
+constexpr int k2SmemBytes = 90112 + 1024;
+
+__device__ __forceinline__ void tma_tile_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+      "l"(map), "r"(c0), "r"(c1), "r"(smem_addr(bar))
+      : "memory");
+}
+__device__ __forceinline__ float trunc_tf32(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+
+__global__ void __launch_bounds__(kThreadsA, 2)
+attention_tma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+                     const __grid_constant__ CUtensorMap map_v, const int64_t* __restrict__ q_off,
+                     const int64_t* __restrict__ k_off, int heads, float scale_mul, float* __restrict__ out,
+                     int ld_o) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = smem_raw + ((1024u - ((uint32_t)__cvta_generic_to_shared(smem_raw) & 1023u)) & 1023u);
+  __shared__ uint64_t bar_tq, bar_tkv[2], bar_kv_ready, bar_s_full, bar_p_ready, bar_o_full;
+  __shared__ uint32_t tmem_base_s;
+  const int prob = blockIdx.y / heads, head = blockIdx.y % heads;
+  const int64_t q0 = q_off[prob] + (int64_t)blockIdx.x * QT, q1 = q_off[prob + 1];
+  if (q0 >= q1) return;
+  const int64_t k0 = k_off[prob], k1 = k_off[prob + 1];
+  const int n_tiles = (int)((k1 - k0 + KT - 1) / KT);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    bar_init(&bar_tq, 1);
+    bar_init(&bar_tkv[0], 1);
+    bar_init(&bar_tkv[1], 1);
+    bar_init(&bar_kv_ready, kWorkers / 32);
+    bar_init(&bar_s_full, 1);
+    bar_init(&bar_p_ready, kWorkers / 32);
+    bar_init(&bar_o_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(&tmem_base_s)),
+                 "n"(256));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_s;
+  const uint32_t tmem_s = tmem_base, tmem_o = tmem_base + 64, tmem_phi = tmem_base + 96, tmem_plo = tmem_base + 160;
+  const float* Qhi = reinterpret_cast<const float*>(base + k2Qhi);
+  float* Qlo = reinterpret_cast<float*>(base + k2Qlo);
+  float* Klo = reinterpret_cast<float*>(base + k2Klo);
+  float* Vhi = reinterpret_cast<float*>(base + k2Vhi);
+  float* Vlo = reinterpret_cast<float*>(base + k2Vlo);
+  // one thread arms the stage's transaction barrier and issues the two tile copies of key tile j
+  auto issue_kv = [&](int j) {
+    const int b = j & 1;
+    bar_expect_tx(&bar_tkv[b], 2u * KT * HD * 4);
+    const int row = (int)(k0 + (int64_t)j * KT);
+    tma_tile_2d(smem_addr(base + k2Kraw + b * 8192), &map_k, head * HD, row, &bar_tkv[b]);
+    tma_tile_2d(smem_addr(base + k2Vraw + b * 8192), &map_v, head * HD, row, &bar_tkv[b]);
+  };
+
+  if (warp < 4) {
+    const int nq = (int)min((int64_t)QT, q1 - q0);
+    if (tid == 0) {
+      bar_expect_tx(&bar_tq, (uint32_t)QT * HD * 4);
+      tma_tile_2d(smem_addr(base + k2Qhi), &map_q, head * HD, (int)q0, &bar_tq);
+      issue_kv(0);
+    }
+    bar_wait(&bar_tq, 0);
+#pragma unroll
+    for (int c = 0; c < HD; c += 4) {        // Q lo (row = query)
+      const float4 x = *reinterpret_cast<const float4*>(Qhi + sw_off(tid, c));
+      *reinterpret_cast<float4*>(Qlo + sw_off(tid, c)) =
+          make_float4(x.x - trunc_tf32(x.x), x.y - trunc_tf32(x.y), x.z - trunc_tf32(x.z), x.w - trunc_tf32(x.w));
+    }
+    float o_acc[HD];
+#pragma unroll
+    for (int c = 0; c < HD; c++) o_acc[c] = 0.f;
+    float m_run = -INFINITY, l_run = 0.f;
+
+    for (int j = 0; j < n_tiles; j++) {
+      const int64_t kb = k0 + (int64_t)j * KT;
+      const int nkv = (int)min((int64_t)KT, k1 - kb);
+      const uint32_t ph = j & 1;
+      const float* Kraw = reinterpret_cast<const float*>(base + k2Kraw + (j & 1) * 8192);
+      const float* Vraw = reinterpret_cast<const float*>(base + k2Vraw + (j & 1) * 8192);
+      if (tid == 0 && j + 1 < n_tiles) issue_kv(j + 1);
+      bar_wait(&bar_tkv[j & 1], (j >> 1) & 1);
+      if (tid < KT) {  // K lo (row = key)
+#pragma unroll
+        for (int c = 0; c < HD; c += 4) {
+          const float4 x = *reinterpret_cast<const float4*>(Kraw + sw_off(tid, c));
+          *reinterpret_cast<float4*>(Klo + sw_off(tid, c)) =
+              make_float4(x.x - trunc_tf32(x.x), x.y - trunc_tf32(x.y), x.z - trunc_tf32(x.z), x.w - trunc_tf32(x.w));
+        }
+      } else {         // V row -> transposed: V^T[dim][key], keys are the K dimension of the second MMA
+        const int key = tid - KT, sub = key >> 5, kc = key & 31;
+        const bool live = key < nkv;
+#pragma unroll
+        for (int c = 0; c < HD; c += 4) {
+          const float4 x4 = *reinterpret_cast<const float4*>(Vraw + sw_off(key, c));
+          const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
+#pragma unroll
+          for (int e = 0; e < 4; e++) {
+            const float x = live ? xs[e] : 0.f;
+            const float h = rn_tf32(x);
+            Vhi[sub * 1024 + sw_off(c + e, kc)] = h;
+            Vlo[sub * 1024 + sw_off(c + e, kc)] = rn_tf32(x - h);
+          }
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) bar_arrive(&bar_kv_ready);
+      // ---------------------------------------------------------- softmax on the score row
+      bar_wait(&bar_s_full, ph);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      uint32_t sr[KT];
+      ld_tmem32(tmem_s + ((uint32_t)(warp * 32) << 16), sr);
+      ld_tmem32(tmem_s + ((uint32_t)(warp * 32) << 16) + 32, sr + 32);
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < KT; c++) {
+        const float s_ = c < nkv ? __uint_as_float(sr[c]) * scale_mul : -INFINITY;
+        sr[c] = __float_as_uint(s_);
+        mx = fmaxf(mx, s_);
+      }
+      const float m_new = fmaxf(m_run, mx);
+      const float corr = fast_exp(m_run - m_new);
+      float psum = 0.f;
+      const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+#pragma unroll
+      for (int c0 = 0; c0 < KT; c0 += 32) {
+        uint32_t hi[32], lo[32];
+#pragma unroll
+        for (int e = 0; e < 32; e++) {
+          const float p = fast_exp(__uint_as_float(sr[c0 + e]) - m_new);
+          psum += p;
+          const float h = rn_tf32(p);
+          hi[e] = __float_as_uint(h);
+          lo[e] = __float_as_uint(rn_tf32(p - h));
+        }
+        st_tmem32(tmem_phi + lane_base + c0, hi);
+        st_tmem32(tmem_plo + lane_base + c0, lo);
+      }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      l_run = l_run * corr + psum;
+      m_run = m_new;
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) bar_arrive(&bar_p_ready);
+      // ---------------------------------------------------------- fold this tile's P.V
+      bar_wait(&bar_o_full, ph);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      uint32_t orr[HD];
+      ld_tmem32(tmem_o + ((uint32_t)(warp * 32) << 16), orr);
+#pragma unroll
+      for (int c = 0; c < HD; c++) o_acc[c] = fmaf(o_acc[c], corr, __uint_as_float(orr[c]));
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    if (tid < nq) {
+      float* o = out + (q0 + tid) * ld_o + head * HD;
+#pragma unroll
+      for (int c = 0; c < HD; c += 4)
+        *reinterpret_cast<float4*>(o + c) =
+            make_float4(o_acc[c] / l_run, o_acc[c + 1] / l_run, o_acc[c + 2] / l_run, o_acc[c + 3] / l_run);
+    }
+  } else if (lane == 0) {
+    // -------------------------------------------------------------- MMA issuer
+    constexpr uint32_t idesc_s = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(KT >> 3) << 17) | ((uint32_t)(QT >> 4) << 24);
+    constexpr uint32_t idesc_o = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(HD >> 3) << 17) | ((uint32_t)(QT >> 4) << 24);
+    const uint32_t qhi = smem_addr(base + k2Qhi), qlo = smem_addr(base + k2Qlo), klo = smem_addr(base + k2Klo),
+                   vhi = smem_addr(base + k2Vhi), vlo = smem_addr(base + k2Vlo);
+    for (int j = 0; j < n_tiles; j++) {
+      const uint32_t ph = j & 1;
+      const uint32_t khi = smem_addr(base + k2Kraw + (j & 1) * 8192);
+      bar_wait(&bar_kv_ready, ph);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+      for (int ks = 0; ks < HD / 8; ks++) {   // S = Q . K^T
+        const uint32_t koff = ks * 32;
+        umma_tf32(tmem_s, sw128_desc(qhi + koff), sw128_desc(khi + koff), idesc_s, ks != 0);
+        umma_tf32(tmem_s, sw128_desc(qhi + koff), sw128_desc(klo + koff), idesc_s, 1);
+        umma_tf32(tmem_s, sw128_desc(qlo + koff), sw128_desc(khi + koff), idesc_s, 1);
+      }
+      umma_commit(&bar_s_full);
+      bar_wait(&bar_p_ready, ph);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+      for (int ks = 0; ks < KT / 8; ks++) {   // O_j = P . V  (K = keys: 2 sub-tiles of 32)
+        const uint32_t sub = ks >> 2, koff = (ks & 3) * 32;
+        const uint32_t vb = sub * 4096 + koff, pc = ks * 8;
+        umma_tf32_ts(tmem_o, tmem_phi + pc, sw128_desc(vhi + vb), idesc_o, ks != 0);
+        umma_tf32_ts(tmem_o, tmem_phi + pc, sw128_desc(vlo + vb), idesc_o, 1);
+        umma_tf32_ts(tmem_o, tmem_plo + pc, sw128_desc(vhi + vb), idesc_o, 1);
+      }
+      umma_commit(&bar_o_full);
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 4) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(256));
+  }
+}
+
+typedef CUresult (*EncodeTiledFnA)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link dependency on libcuda)
+EncodeTiledFnA attn_map_encoder() {
+  static EncodeTiledFnA fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFnA)p;
+  }
+  return fn;
+}
+// [rows, cols] fp32 operand with row stride ld (floats): boxes of one head (32 floats = one swizzle row) x box_rows
+bool attn_make_map(CUtensorMap* m, const float* ptr, int64_t rows, int cols, int ld, int box_rows) {
+  EncodeTiledFnA enc = attn_map_encoder();
+  if (!enc) return false;
+  const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+  const cuuint32_t box[2] = {(cuuint32_t)HD, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) ==
+         CUDA_SUCCESS;
+}
+
 }  // namespace
 
 extern "C" int lcr_attention_tc(const float* q, int ld_q, const float* k, int ld_k, const float* v, int ld_v,
@@ -360,6 +613,40 @@ extern "C" int lcr_attention_tc(const float* q, int ld_q, const float* k, int ld
   dim3 grid((unsigned)((max_q_rows + QT - 1) / QT), (unsigned)(n_problems * heads));
   attention_tc_kernel<<<grid, kThreadsA, kSmemBytes, stream>>>(q, ld_q, k, ld_k, v, ld_v, q_off, k_off, heads,
                                                                1.0f / sqrtf((float)head_dim), out, ld_out);
+  LCR_LAUNCHED(1);
+  LCR_CUDA_CHECK_LAUNCH();
+  return LCR_OK;
+}
+
+// Tensor-map variant of lcr_attention_tc (same arguments + the row counts of the q and k / v operands, which bound
+// the tensor maps).  Default attention of the registration path.
+extern "C" int lcr_attention_tma(const float* q, int ld_q, int64_t q_rows, const float* k, int ld_k, const float* v,
+                                 int ld_v, int64_t k_rows, const int64_t* q_off, const int64_t* k_off, int n_problems,
+                                 int64_t max_q_rows, int heads, int head_dim, float* out, int ld_out,
+                                 double flops_hint, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  LCR_REQUIRE(head_dim == HD, "attention_tma: head_dim must be 32");
+  LCR_REQUIRE(n_problems >= 1 && heads >= 1 && max_q_rows >= 0 && q_rows >= 0 && k_rows >= 0, "attention_tma: bad sizes");
+  LCR_REQUIRE((ld_q % 4) == 0 && (ld_k % 4) == 0 && (ld_v % 4) == 0 && (ld_out % 4) == 0 &&
+                  (((uintptr_t)q | (uintptr_t)k | (uintptr_t)v | (uintptr_t)out) & 15) == 0,
+              "attention_tma: rows must be 16-byte aligned (TMA)");
+  LCR_REQUIRE(q_rows < (1ll << 31) && k_rows < (1ll << 31), "attention_tma: more than 2^31 rows");
+  if (max_q_rows == 0 || q_rows == 0) return LCR_OK;
+  LCR_REQUIRE(k_rows >= 1, "attention_tma: empty key operand");
+  CUtensorMap mq, mk, mv;
+  LCR_REQUIRE(attn_make_map(&mq, q, q_rows, heads * HD, ld_q, QT) && attn_make_map(&mk, k, k_rows, heads * HD, ld_k, KT) &&
+                  attn_make_map(&mv, v, k_rows, heads * HD, ld_v, KT),
+              "attention_tma: cuTensorMapEncodeTiled failed");
+  static LcrOncePerDevice attr_done;
+  const int attr_done_dev = attr_done.need();
+  if (attr_done_dev != -1) {
+    LCR_CUDA_TRY(cudaFuncSetAttribute(attention_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, k2SmemBytes));
+    attr_done.done(attr_done_dev);
+  }
+  LcrProfScope prof("attention_tc", flops_hint, 0.0, stream);
+  dim3 grid((unsigned)((max_q_rows + QT - 1) / QT), (unsigned)(n_problems * heads));
+  attention_tma_kernel<<<grid, kThreadsA, k2SmemBytes, stream>>>(mq, mk, mv, q_off, k_off, heads,
+                                                                 1.0f / sqrtf((float)head_dim), out, ld_out);
   LCR_LAUNCHED(1);
   LCR_CUDA_CHECK_LAUNCH();
   return LCR_OK;

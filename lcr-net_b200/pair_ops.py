@@ -58,7 +58,13 @@ def attention(q, k, v, q_off, k_off, n_problems, max_q_rows, heads=4, flops=0.0)
     """softmax(q k^T / sqrt(32)) v per head and problem.  q/k/v: [rows, heads*32] views."""
     out = torch.empty((q.shape[0], heads * 32), dtype=torch.float32, device=q.device)
     import os
-    fn = _L().lcr_attention if os.environ.get('LCR_ATTN', 'tc') == 'simt' else _L().lcr_attention_tc
+    impl = os.environ.get('LCR_ATTN', 'tma')      # tma (default): tcgen05 + tensor-map TMA; tc: tcgen05 + per-row bulk
+    if impl == 'tma':                              # copies; simt: fp32 flash-style kernel
+        _lib.check(_L().lcr_attention_tma(_lib.ptr(q), q.stride(0), q.shape[0], _lib.ptr(k), k.stride(0), _lib.ptr(v),
+                                          v.stride(0), k.shape[0], _lib.ptr(q_off), _lib.ptr(k_off), n_problems,
+                                          max_q_rows, heads, 32, _lib.ptr(out), out.stride(0), float(flops), _s(q)))
+        return out
+    fn = _L().lcr_attention if impl == 'simt' else _L().lcr_attention_tc
     _lib.check(fn(_lib.ptr(q), q.stride(0), _lib.ptr(k), k.stride(0), _lib.ptr(v), v.stride(0),
                                   _lib.ptr(q_off), _lib.ptr(k_off), n_problems, max_q_rows, heads, 32, _lib.ptr(out),
                                   out.stride(0), float(flops), _s(q)))

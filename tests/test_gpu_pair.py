@@ -330,7 +330,7 @@ def test_loop_candidates_vs_oracle():
     assert all(first[int(q)] == int(idx[n, 0]) for n, q in enumerate(q_ids))
 
 
-@pytest.mark.parametrize('impl', ['simt', 'tc'])
+@pytest.mark.parametrize('impl', ['simt', 'tc', 'tma'])
 def test_attention_kernels_vs_torch(impl, monkeypatch):
     """Both attention kernels (fp32 SIMT flash-style; tcgen05 3xTF32 + TMA) against torch fp64 on
     ragged problems (lengths not multiples of the 64/128 tiles, strided q/k/v views)."""
