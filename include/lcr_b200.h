@@ -283,6 +283,10 @@ int lcr_sinkhorn(const float* scores, int batch, int rows, int cols, const uint8
 /* Debug / tuning: out4 = {LOG iterations, LIN iterations, discarded LIN iterations, absorptions} summed over all
  * problems since the last reset (sinkhorn.cu); synchronises the device. */
 int lcr_sinkhorn_stats(int64_t* out4, int reset);
+/* Node-level Sinkhorn kernel: 0 single CTA per problem (plan in L2), 1 (default) the smallest thread-block cluster
+ * whose shared-memory row slabs hold the plan, 4 / 8 force that cluster size.  Point-level (128 x 128) problems always
+ * use the register-resident kernel. */
+void lcr_set_sinkhorn_cluster(int mode);
 size_t lcr_coarse_matching_ws_bytes(int rows, int cols);
 int lcr_coarse_matching(const float* log_scores, int rows, int cols, int32_t* out_i, int32_t* out_j,
                         float* out_scores, int32_t* out_count, void* ws, size_t ws_bytes, void* stream);

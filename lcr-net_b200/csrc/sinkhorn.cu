@@ -21,12 +21,14 @@
 // scores for score ranges up to +-100; the torch fp32 reference itself is 4e-5 .. 3e-4 away from fp64 there.
 //
 // Kernels:
-//   sinkhorn_patch_kernel    the point-level problems (128 x 128 (+1), thousands per batch): K lives in REGISTERS as
-//                            4 x 33 blocks per thread; a LIN half-iteration is 132 FFMA per thread against 33 words
-//                            of shared memory -- the round-1 kernel read K from shared memory: one LDS per FMA,
-//                            bound by the 128 B/clk port.
-//   sinkhorn_general_kernel  any size (node level, ~370 x 360): K in the output buffer (L2), warp per row, row
-//                            slabs per warp for the column sums.
+//   sinkhorn_patch_kernel    the point-level problems (128 x 128 (+1), thousands per batch): K lives in REGISTERS in
+//                            row form and in column form (3 x 17 blocks per thread each); a LIN half-iteration is
+//                            51 FFMA per thread against 17 words of shared memory -- the round-1 kernel read K from
+//                            shared memory: one LDS per FMA, bound by the 128 B/clk port.
+//   sinkhorn_cluster_kernel  node level (~390 x 385, one problem per pair): a cluster of 4 / 8 CTAs per problem, row
+//                            slabs of K in shared memory, column partials exchanged through DSMEM.
+//   sinkhorn_general_kernel  any size: K in the output buffer (L2), warp per row, row slabs per warp for the column
+//                            sums (fallback when the slabs do not fit, LCR_SINKHORN_CLUSTER=0).
 #include <cooperative_groups.h>
 
 #include "common.cuh"
@@ -950,6 +952,15 @@ int launch_sinkhorn_cluster(const SinkhornArgs& a, int batch, int rs, size_t sme
 
 }  // namespace
 
+// Node-level kernel selection: 0 single-CTA kernel, 1 (default) smallest cluster that fits, 4 / 8 that cluster size.
+// LCR_SINKHORN_CLUSTER sets the default; lcr_set_sinkhorn_cluster overrides it (tests).
+static int g_sinkhorn_cluster = -1;
+static int sinkhorn_cluster_mode() {
+  if (g_sinkhorn_cluster < 0) g_sinkhorn_cluster = getenv("LCR_SINKHORN_CLUSTER") ? atoi(getenv("LCR_SINKHORN_CLUSTER")) : 1;
+  return g_sinkhorn_cluster;
+}
+extern "C" void lcr_set_sinkhorn_cluster(int mode) { g_sinkhorn_cluster = (mode == 0 || mode == 4 || mode == 8) ? mode : 1; }
+
 // Debug / tuning: iteration statistics of all Sinkhorn problems since the last reset (see g_sk_stats); synchronises.
 extern "C" int lcr_sinkhorn_stats(int64_t* out4, int reset) {
   unsigned long long h[4] = {0, 0, 0, 0};
@@ -985,7 +996,7 @@ extern "C" int lcr_sinkhorn(const float* scores, int batch, int rows, int cols, 
   } else {
     const int R = rows + 1, C = cols + 1;
     // 0: single-CTA kernel; otherwise the smallest cluster (4, then 8 CTAs per problem) whose row slab fits
-    static const int use_cluster = getenv("LCR_SINKHORN_CLUSTER") ? atoi(getenv("LCR_SINKHORN_CLUSTER")) : 1;
+    const int use_cluster = sinkhorn_cluster_mode();
     int cl = 0;
     for (int c : {4, 8}) {
       if (use_cluster > 1 && c != use_cluster) continue;       // 4 / 8: force that cluster size (tests)

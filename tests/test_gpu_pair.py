@@ -158,6 +158,32 @@ def test_sinkhorn_vs_oracle(b, m, n, scale):
     print('   iterations per problem: LOG %.1f, LIN %.1f, discarded %.1f, absorptions %.1f' % tuple(x / b for x in st))
 
 
+@pytest.mark.parametrize('mode', [0, 4, 8])
+def test_node_sinkhorn_kernel_variants_agree(mode):
+    """Node-level problems run on a thread-block cluster (row slabs of the plan in shared memory, column partials
+    exchanged through DSMEM): the single-CTA kernel (0) and both cluster sizes (4, 8) against the fp64 oracle on a
+    ragged masked batch, incl. a shape whose rows do not divide by the cluster size and one-row slabs."""
+    from lcrnet_b200 import _lib
+    from lcrnet_b200 import pair_ops as P
+    try:
+        _lib.lib().lcr_set_sinkhorn_cluster(mode)
+        for b, m, n, scale in ((3, 391, 377, 30.0), (2, 6, 9, 2.0), (1, 257, 130, 8.0)):
+            g = torch.Generator().manual_seed(17 * m + n)
+            s = torch.randn(b, m, n, generator=g) * scale
+            rm = torch.arange(m)[None, :] < torch.randint(max(m - 60, 2), m + 1, (b, 1), generator=g)
+            cm = torch.arange(n)[None, :] < torch.randint(max(n - 60, 2), n + 1, (b, 1), generator=g)
+            alpha = torch.tensor(0.3)
+            ref64 = po.sinkhorn(s.double(), rm, cm, alpha.double())
+            got = P.sinkhorn(c(s), rm.cuda(), cm.cuda(), alpha.cuda()).cpu()
+            valid = ref64 > -1e11
+            assert torch.equal(valid, got > -1e11)
+            d64 = (got.double() - ref64).abs() * valid
+            assert float((d64 * (ref64 > -30.0)).max()) < 1e-4
+            assert float((d64 / ref64.abs().clamp(min=1.0)).max()) < 5e-5
+    finally:
+        _lib.lib().lcr_set_sinkhorn_cluster(1)
+
+
 def test_coarse_and_fine_matching_vs_oracle(oracle_run):
     from lcrnet_b200 import pair_ops as P
     data, out = oracle_run
