@@ -92,9 +92,13 @@ def test_vote_encoder_vs_oracle(net, oracle_run):
     with torch.no_grad():
         got = net.vote_encoder(c(out['_stages']['enhanced']), dd, ops.Stacks([sum(lens)], 'cuda'), lens, 2)
     assert got['counts'] == vd['counts']
-    assert float((got['centres'].cpu() - vd['centres']).abs().max()) < 1e-3
+    e_c = float((got['centres'].cpu() - vd['centres']).abs().max())
     ref = vd['feats']
-    assert float((got['feats'].cpu() - ref).abs().max()) < 2e-4 * max(1.0, float(ref.abs().max()))
+    e_f = float((got['feats'].cpu() - ref).abs().max()) / max(1.0, float(ref.abs().max()))
+    print('vote encoder: node centres %.2e m (coordinates up to %.0f m), node features %.2e relative' % (
+        e_c, float(vd['centres'].abs().max()), e_f))
+    assert e_c < 1e-4          # metres, absolute (measured 8e-6 at coordinates up to 70 m)
+    assert e_f < 2e-5          # measured 1.5e-6
 
 
 def test_partition_vs_oracle(oracle_run):
@@ -275,7 +279,8 @@ def test_full_lcrnet_vs_oracle_and_fixture(net, oracle_run, gemm, monkeypatch):
     assert e_cond < 1e-4
     if pairs_got == pairs_ref:
         assert err < 1e-4
-    assert np.abs(T.numpy() - G['estimated_transform']).max() < 2e-3     # vs the reference (oracle: < 1e-3)
+    if pairs_got == pairs_ref:                                           # vs the reference itself (oracle: 1.9e-5)
+        assert np.abs(T.numpy() - G['estimated_transform']).max() < 1e-4 * max(1.0, np.abs(G['estimated_transform']).max())
 
 
 def test_demo_pair_and_batched_pairs(net):

@@ -48,21 +48,24 @@ def test_oracle_matches_reference_fixture(run):
     assert np.array_equal(torch.stack(data['lengths']).numpy(), G['lengths'])
     st = out['_stages']
     n_c0 = int(G['lengths'][-1][0])
-    assert np.abs(st['enhanced'][:8].numpy() - G['enhanced_pos_head']).max() < 2e-4
-    assert np.abs(st['enhanced'][n_c0:n_c0 + 8].numpy() - G['enhanced_anc_head']).max() < 2e-4
+    e = {'enhanced': max(np.abs(st['enhanced'][:8].numpy() - G['enhanced_pos_head']).max(),
+                         np.abs(st['enhanced'][n_c0:n_c0 + 8].numpy() - G['enhanced_anc_head']).max()),
+         'points_c': max(np.abs(out['pos_points_c'].numpy() - G['pos_points_c']).max(),
+                         np.abs(out['anc_points_c'].numpy() - G['anc_points_c']).max()),
+         'feats_f': np.abs(st['feats_f'][:8].numpy() - G['feats_f_head']).max(),
+         'node_ot_diag': np.abs(st['node_ot'].diagonal().numpy() - G['node_ot_diag']).max()}
+    print('oracle vs reference fixture:', {k: '%.2e' % v for k, v in e.items()})
     assert list(out['length']) == list(G['node_counts'])
-    assert np.abs(out['pos_points_c'].numpy() - G['pos_points_c']).max() < 1e-3
-    assert np.abs(out['anc_points_c'].numpy() - G['anc_points_c']).max() < 1e-3
-    assert np.abs(st['feats_f'][:8].numpy() - G['feats_f_head']).max() < 5e-4
+    assert e['enhanced'] < 2e-5 and e['points_c'] < 1e-4 and e['feats_f'] < 2e-5 and e['node_ot_diag'] < 5e-4
     for k in ('pos_feature_global', 'anc_feature_global'):
         assert np.linalg.norm(out[k].numpy() - G[k]) < 1e-4
-    assert np.abs(st['node_ot'].diagonal().numpy() - G['node_ot_diag']).max() < 5e-3
     # discrete stages: identical node correspondences and correspondence count
     assert np.array_equal(out['pos_node_corr_indices'].numpy(), G['pos_node_corr_indices'])
     assert np.array_equal(out['anc_node_corr_indices'].numpy(), G['anc_node_corr_indices'])
     assert out['corr_scores'].shape[0] == int(G['n_corr'])
     T, Tref = out['estimated_transform'].numpy(), G['estimated_transform']
-    assert np.abs(T - Tref).max() < 1e-3 * max(1.0, np.abs(Tref).max())
+    print('   pose vs fixture: %.2e' % np.abs(T - Tref).max())
+    assert np.abs(T - Tref).max() < 1e-4 * max(1.0, np.abs(Tref).max())
 
 
 @pytest.mark.skipif(not REF_PRESENT, reason='reference tree not present')
@@ -87,23 +90,34 @@ def test_oracle_matches_reference_live(run):
     st = out['_stages']
     n_c0 = int(rdata['lengths'][-1][0])
     enh = torch.cat([taps['transformer'][0][0], taps['transformer'][1][0]], 0)
-    assert float((st['enhanced'] - enh).abs().max()) < 2e-4
-    assert float((st['vote']['shifted'][:n_c0] - rout['shifted_pos_points_c']).abs().max()) < 1e-4
-    assert float((out['pos_feats_c'] - rout['pos_feats_c']).abs().max()) < 1e-3
-    assert float((st['feats_f'] - taps['kpdecoder'][0]).abs().max()) < 1e-3
+    rel = lambda a, b: float((a - b).abs().max()) / max(1.0, float(b.abs().max()))
+    m = {'enhanced': rel(st['enhanced'], enh),
+         'shifted': float((st['vote']['shifted'][:n_c0] - rout['shifted_pos_points_c']).abs().max()),
+         'pos_feats_c': rel(out['pos_feats_c'], rout['pos_feats_c']),
+         'feats_f': rel(st['feats_f'], taps['kpdecoder'][0]),
+         'node_ot': float((st['node_ot'] - taps['node_ot'][0]).abs().max()),
+         'node_ot_scale': float(taps['node_ot'][0][taps['node_ot'][0] > -1e11].abs().max())}
+    print('oracle vs reference (live, fp32 both):', {k: '%.2e' % v for k, v in m.items()})
+    # bars = a few times the measured fp32-vs-fp32 differences (2e-6, 4e-6, 2e-6, 7e-7; node OT 6e-5 at |L| <= 58)
+    assert m['enhanced'] < 1e-5 and m['shifted'] < 2e-5 and m['pos_feats_c'] < 1e-5 and m['feats_f'] < 1e-5
     assert torch.equal(st['pos_knn'].sort(1)[0], rout['pos_node_knn_indices'][0].sort(1)[0])
-    assert float((st['node_ot'] - taps['node_ot'][0]).abs().max()) < 1e-2
+    assert m['node_ot'] < 5e-6 * max(1.0, m['node_ot_scale'])
     # per-patch point lists agree as sets; torch.topk orders near-equal distances differently in a
     # few patches (SURVEY trap 5), which permutes rows/cols of those patches' OT matrices: compare
     # the patches whose order is identical
     same = ((st['pos_knn'] == rout['pos_node_knn_indices'][0]).all(1)[out['pos_node_corr_indices']]
             & (st['anc_knn'] == rout['anc_node_knn_indices'][0]).all(1)[out['anc_node_corr_indices']])
-    assert float(same.float().mean()) > 0.8
+    assert float(same.float().mean()) > 0.95
     valid = taps['point_ot'][same] > -1e11
-    assert float(((st['point_ot'][same] - taps['point_ot'][same]).abs() * valid).max()) < 1e-2
+    e_pot = float(((st['point_ot'][same] - taps['point_ot'][same]).abs() * valid).max())
+    e_T = float((out['estimated_transform'] - rout['estimated_transform']).abs().max())
+    print('   point_ot %.2e on %.0f %% of the patches (|L| up to %.0f), pose %.2e' % (
+        e_pot, 100 * float(same.float().mean()), float((taps['point_ot'][same].abs() * valid).max()), e_T))
+    # 100 fp32 logsumexp iterations on log scores up to |L| = 645: measured 6.6e-4 = 1e-6 |L| (an ulp of |L| is 6e-5)
+    assert e_pot < 5e-6 * max(1.0, float((taps['point_ot'][same].abs() * valid).max()))
     assert torch.equal(out['pos_node_corr_indices'], rout['pos_node_corr_indices'])
     assert float((out['pos_corr_points'] - rout['pos_corr_points']).abs().max()) == 0.0
-    assert float((out['estimated_transform'] - rout['estimated_transform']).abs().max()) < 1e-3
+    assert e_T < 1e-4                       # measured 1.9e-5
 
 
 def test_sinkhorn_properties():
