@@ -634,9 +634,11 @@ extern "C" int lcr_attention_tma(const float* q, int ld_q, int64_t q_rows, const
   if (max_q_rows == 0 || q_rows == 0) return LCR_OK;
   LCR_REQUIRE(k_rows >= 1, "attention_tma: empty key operand");
   CUtensorMap mq, mk, mv;
-  LCR_REQUIRE(attn_make_map(&mq, q, q_rows, heads * HD, ld_q, QT) && attn_make_map(&mk, k, k_rows, heads * HD, ld_k, KT) &&
-                  attn_make_map(&mv, v, k_rows, heads * HD, ld_v, KT),
-              "attention_tma: cuTensorMapEncodeTiled failed");
+  if (!(attn_make_map(&mq, q, q_rows, heads * HD, ld_q, QT) && attn_make_map(&mk, k, k_rows, heads * HD, ld_k, KT) &&
+        attn_make_map(&mv, v, k_rows, heads * HD, ld_v, KT)))
+    // the driver refused a tensor map (e.g. no cuTensorMapEncodeTiled entry point): per-row bulk-copy variant
+    return lcr_attention_tc(q, ld_q, k, ld_k, v, ld_v, q_off, k_off, n_problems, max_q_rows, heads, head_dim, out,
+                            ld_out, flops_hint, stream_);
   static LcrOncePerDevice attr_done;
   const int attr_done_dev = attr_done.need();
   if (attr_done_dev != -1) {

@@ -362,6 +362,28 @@ def test_loop_candidates_vs_oracle():
 
 
 @pytest.mark.parametrize('impl', ['simt', 'tc', 'tma'])
+def test_attention_tiny_operands(impl, monkeypatch):
+    """Operands smaller than one tile (fewer rows than the 128 x 32 / 64 x 32 TMA boxes)."""
+    from lcrnet_b200 import pair_ops as P
+    monkeypatch.setenv('LCR_ATTN', impl)
+    g = torch.Generator().manual_seed(5)
+    q_len, k_len = [5, 2], [3, 9]
+    q = torch.randn(sum(q_len), 128, generator=g).cuda()
+    kv = torch.randn(sum(k_len), 256, generator=g).cuda()
+    k, v = kv[:, :128], kv[:, 128:]
+    qo = torch.tensor([0] + list(np.cumsum(q_len)), dtype=torch.int64).cuda()
+    ko = torch.tensor([0] + list(np.cumsum(k_len)), dtype=torch.int64).cuda()
+    got = P.attention(q, k, v, qo, ko, 2, max(q_len), heads=4).cpu().double()
+    for p in range(2):
+        qs, ks = slice(int(qo[p]), int(qo[p + 1])), slice(int(ko[p]), int(ko[p + 1]))
+        for h in range(4):
+            hs = slice(32 * h, 32 * h + 32)
+            s_ = q[qs, hs].double().cpu() @ k[ks, hs].double().cpu().t() / 32 ** 0.5
+            ref = torch.softmax(s_, dim=-1) @ v[ks, hs].double().cpu()
+            assert float((got[qs, hs] - ref).abs().max()) < 2e-5
+
+
+@pytest.mark.parametrize('impl', ['simt', 'tc', 'tma'])
 def test_attention_kernels_vs_torch(impl, monkeypatch):
     """Both attention kernels (fp32 SIMT flash-style; tcgen05 3xTF32 + TMA) against torch fp64 on
     ragged problems (lengths not multiples of the 64/128 tiles, strided q/k/v views)."""
