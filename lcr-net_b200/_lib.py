@@ -131,7 +131,17 @@ def ptr(t):
     return None if t is None else ctypes.c_void_p(t.data_ptr())
 
 
+_raw_stream = getattr(torch._C, '_cuda_getCurrentRawStream', None)
+
+
 def stream_ptr(device=None):
+    """cudaStream_t of torch's current stream on ``device`` (every operator is queued there).  The raw accessor is
+    ~10x cheaper than building a torch.cuda.Stream object: this is called once per kernel launch."""
+    if _raw_stream is not None:
+        idx = getattr(device, 'index', device)
+        if not isinstance(idx, int):
+            idx = torch.cuda.current_device()
+        return ctypes.c_void_p(_raw_stream(idx))
     return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 

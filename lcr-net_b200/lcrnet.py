@@ -226,7 +226,7 @@ class Vote_Encoder(nn.Module):
         for n in lengths_c_host:
             off_host.append(off_host[-1] + int(n))
         sel_host = np.concatenate([np.arange(o, o + c, dtype=np.int64) for o, c in zip(off_host[:-1], counts_host)])
-        sel = kept_idx[torch.from_numpy(sel_host).to(dev)].long()      # kept points, compacted per cloud
+        sel = kept_idx[ops.host_to_device(torch.from_numpy(sel_host), dev)].long()      # kept points, compacted per cloud
         nms_points = shifted[sel].contiguous()
         lim = self.neighbor_limits
         node_knn = ops.radius_search(nms_points, shifted, node_len, lengths_c, self.NMS_radius, lim[-1], int32=True)
@@ -330,8 +330,8 @@ class LCRNet(nn.Module):
         off_c = [0]
         for n in n_c:
             off_c.append(off_c[-1] + n)
-        rows = lambda first: torch.from_numpy(np.concatenate(
-            [np.arange(off_c[2 * p + first], off_c[2 * p + first + 1], dtype=np.int64) for p in range(n_pairs)])).to(dev)
+        rows = lambda first: ops.host_to_device(torch.from_numpy(np.concatenate(
+            [np.arange(off_c[2 * p + first], off_c[2 * p + first + 1], dtype=np.int64) for p in range(n_pairs)])), dev)
         ref_rows, src_rows = rows(0), rows(1)
         ref_st, src_st = ops.Stacks(n_c[0::2], dev), ops.Stacks(n_c[1::2], dev)
         e0, e1 = self.transformer(points_c[ref_rows].contiguous(), points_c[src_rows].contiguous(),
@@ -361,7 +361,7 @@ class LCRNet(nn.Module):
         for c in cnt.tolist():                                                       # D2H: node correspondence counts
             patch_off_host.append(patch_off_host[-1] + int(c))
         total = patch_off_host[-1]
-        patch_off = torch.tensor(patch_off_host, dtype=torch.int32).to(dev)
+        patch_off = ops.host_to_device(torch.tensor(patch_off_host, dtype=torch.int32), dev)
         ci_g, cj_g, ci_l, cj_l, _, patch_pair = P.gather_coarse(oi, oj, os_, patch_off, node_st, total)
         ms = P.patch_scores(feats_f, knn_g, ci_g, feats_f, knn_g, cj_g)               # LCRNet.py:231-233
         km_bool = knn_mask.bool()
@@ -380,7 +380,7 @@ class LCRNet(nn.Module):
         ci_l64, cj_l64 = ci_l.long(), cj_l.long()
         cp = corr['pair'][:corr_off[-1]]                                              # valid prefix (capacity arrays)
         corr_patch_local = cp - patch_off[patch_pair.long()][cp.long()] if total else cp
-        off_f, node_off = clouds_f.off.tolist(), node_st.off.tolist()
+        off_f, node_off = clouds_f.off_host, node_st.off_host
         outs = []
         for p in range(n_pairs):
             a, b = 2 * p, 2 * p + 1
