@@ -82,8 +82,11 @@ int lcr_radius_neighbors(const float* q_points, int64_t nq_total, const float* s
                          const int64_t* q_lengths, const int64_t* s_lengths, int batch, float radius,
                          int width, void* out_idx, int idx_is64, int32_t* out_counts,
                          int32_t* out_max_count, int32_t* out_status, void* ws, size_t ws_bytes, void* stream);
-/* As above; reuse_grid != 0 skips the support-grid build and reuses the one a previous call left in `ws` (same ws
- * pointer, supports, support lengths, batch and radius): the pyramid asks three tables per support level. */
+/* As above; reuse_grid is a bit set.  Bit 0 (1): skip the support-grid build and reuse the one a previous call left
+ * in `ws` (same ws pointer, supports, support lengths, batch and radius): the pyramid asks three tables per support
+ * level.  Bit 1 (2): nearest-only -- width must be 1; writes column 0 of the table (the closest support inside the
+ * radius, ties by index, pad = ns_total) without collecting and sorting the other hits: what the decoder's
+ * nearest_upsample reads from the up-sampling tables (backbone4.py:333-373, modules/ops/index_select... [:, 0]). */
 int lcr_radius_neighbors_ex(const float* q_points, int64_t nq_total, const float* s_points, int64_t ns_total,
                             const int64_t* q_lengths, const int64_t* s_lengths, int batch, float radius, int width,
                             void* out_idx, int idx_is64, int32_t* out_counts, int32_t* out_max_count,

@@ -238,7 +238,10 @@ __device__ __forceinline__ void finish_query(unsigned long long* keys, int total
   }
 }
 
-template <typename IdxT>
+// NEAREST: only the closest support inside the radius is wanted (the up-sampling tables: the decoder reads column 0
+// only, backbone4.py:333-373) -- every lane keeps the minimum (d2, index) key of its candidates, one warp reduction,
+// no key buffer and no sort.
+template <typename IdxT, bool NEAREST = false>
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
 query_kernel(const float* __restrict__ q, int64_t nq, const int64_t* __restrict__ q_off, int batch,
              const GridGeom* __restrict__ geom, float inv_cell, float r2,
@@ -264,6 +267,7 @@ query_kernel(const float* __restrict__ q, int64_t nq, const int64_t* __restrict_
     }
     unsigned long long* keys = s_keys[warp];
     const bool want_idx = out_idx != nullptr;
+    unsigned long long best = kEmpty;
     // The 27 candidate runs are walked as ONE flat stream of T candidates, 32 per step (a cell holds ~18 points:
     // a per-cell loop left 44 % of the lanes idle and paid 27 loop iterations): an inclusive warp scan of the run
     // lengths, then every lane finds the run of its candidate by a 5-step binary search over the lanes' exclusive
@@ -294,13 +298,28 @@ query_kernel(const float* __restrict__ q, int64_t nq, const int64_t* __restrict_
         key = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned long long)__float_as_uint(p.w);
       }
       const unsigned m = __ballot_sync(0xffffffffu, hit);
-      if (hit && want_idx) {
+      if (NEAREST) {
+        if (hit && key < best) best = key;
+      } else if (hit && want_idx) {
         const int pos = total + __popc(m & ((1u << lane) - 1u));
         if (pos < kWarpCap) keys[pos] = key;
       }
       total += __popc(m);
     }
-    finish_query<IdxT>(keys, total, lane, qi, width, ns_total, out_idx, out_counts, out_max, spill_list, spill_n);
+    if (NEAREST) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+        if (other < best) best = other;
+      }
+      if (lane == 0) {
+        if (out_counts) out_counts[qi] = total;
+        if (total > *reinterpret_cast<volatile int32_t*>(out_max)) atomicMax(out_max, total);
+        if (out_idx) out_idx[(size_t)qi * width] = total > 0 ? (IdxT)(uint32_t)(best & 0xFFFFFFFFull) : (IdxT)ns_total;
+      }
+    } else {
+      finish_query<IdxT>(keys, total, lane, qi, width, ns_total, out_idx, out_counts, out_max, spill_list, spill_n);
+    }
   }
 }
 
@@ -540,7 +559,8 @@ extern "C" int lcr_radius_neighbors(const float* q_points, int64_t nq_total, con
                                  out_idx, idx_is64, out_counts, out_max_count, out_status, ws, ws_bytes, 0, stream_);
 }
 
-// reuse_grid != 0: the support grid in `ws` (built by a previous call with the SAME ws pointer, supports, support
+// reuse_grid is a bit set.  Bit 1 (value 2): nearest-only mode, width must be 1 -- column 0 of the full table without
+// the sort.  Bit 0: the support grid in `ws` (built by a previous call with the SAME ws pointer, supports, support
 // lengths, batch and radius) is reused; only the query side is processed.  The pyramid asks three tables of every
 // support level at the same radius (self, subsampling of the next level, upsampling of the previous one,
 // data.py:28-66): one grid build instead of three.
@@ -578,7 +598,9 @@ extern "C" int lcr_radius_neighbors_ex(const float* q_points, int64_t nq_total, 
   lcr_offsets_launch(q_lengths, batch, w.q_off, stream);
   LCR_CUDA_TRY(cudaMemsetAsync(w.spill_n, 0, sizeof(uint32_t), stream));
   if (!out_status) LCR_CUDA_TRY(cudaMemsetAsync(w.err, 0, sizeof(int), stream));
-  const bool build = !reuse_grid;
+  const bool nearest = (reuse_grid & 2) != 0;
+  LCR_REQUIRE(!nearest || (out_idx && width == 1), "radius_neighbors: the nearest-only mode writes one column");
+  const bool build = !(reuse_grid & 1);
   if (build) {
     lcr_offsets_launch(s_lengths, batch, w.s_off, stream);
     lcr_bbox_launch(s_points, ns_total, w.s_off, batch, w.bbox, stream);
@@ -605,7 +627,7 @@ extern "C" int lcr_radius_neighbors_ex(const float* q_points, int64_t nq_total, 
   // (measured, 64 scans: level 0, 909 k points: 1.10 -> 0.90 ms, level 1, 361 k: 0.46 -> 0.43 ms; the small levels
   // have too few cells to fill the persistent grid and stay on the per-query kernel.  What remains is the sort of
   // the hits: ~300 of the ~500 instructions per query.)
-  const bool self = cell_mode && q_points == s_points && q_lengths == s_lengths && nq_total == ns_total &&
+  const bool self = cell_mode && !nearest && q_points == s_points && q_lengths == s_lengths && nq_total == ns_total &&
                     (ns_total >= 200000 || cell_mode == 2);
   if (self) {
     LCR_CUDA_TRY(cudaMemsetAsync(w.next_cell, 0, sizeof(uint32_t), stream));
@@ -619,7 +641,16 @@ extern "C" int lcr_radius_neighbors_ex(const float* q_points, int64_t nq_total, 
           w.occ_list, w.n_occ, w.next_cell, r2, w.tkeys, w.tstart, w.tcount, w.tcap - 1, w.sorted, width, ns_total,
           (int32_t*)out_idx, out_counts, out_max_count, w.spill_list, w.spill_n);
   }
-  if (!self) {
+  if (nearest) {
+    if (idx_is64)
+      query_kernel<int64_t, true><<<gridQ, kWarpsPerCta * 32, 0, stream>>>(
+          q_points, nq_total, w.q_off, batch, w.geom, inv_cell, r2, w.tkeys, w.tstart, w.tcount, w.tcap - 1, w.sorted,
+          width, ns_total, (int64_t*)out_idx, out_counts, out_max_count, w.spill_list, w.spill_n);
+    else
+      query_kernel<int32_t, true><<<gridQ, kWarpsPerCta * 32, 0, stream>>>(
+          q_points, nq_total, w.q_off, batch, w.geom, inv_cell, r2, w.tkeys, w.tstart, w.tcount, w.tcap - 1, w.sorted,
+          width, ns_total, (int32_t*)out_idx, out_counts, out_max_count, w.spill_list, w.spill_n);
+  } else if (!self) {
     if (idx_is64)
       query_kernel<int64_t><<<gridQ, kWarpsPerCta * 32, 0, stream>>>(
           q_points, nq_total, w.q_off, batch, w.geom, inv_cell, r2, w.tkeys, w.tstart, w.tcount, w.tcap - 1, w.sorted,
@@ -629,7 +660,7 @@ extern "C" int lcr_radius_neighbors_ex(const float* q_points, int64_t nq_total, 
           q_points, nq_total, w.q_off, batch, w.geom, inv_cell, r2, w.tkeys, w.tstart, w.tcount, w.tcap - 1, w.sorted,
           width, ns_total, (int32_t*)out_idx, out_counts, out_max_count, w.spill_list, w.spill_n);
   }
-  if (out_idx) {   // rows with more hits than a warp buffer: one CTA per queued query
+  if (out_idx && !nearest) {   // rows with more hits than a warp buffer: one CTA per queued query
     if (idx_is64) {
       static LcrOncePerDevice attr_set64;
       const int attr_set64_dev = attr_set64.need();
@@ -654,7 +685,7 @@ extern "C" int lcr_radius_neighbors_ex(const float* q_points, int64_t nq_total, 
           ns_total, (int32_t*)out_idx, w.spill_list, w.spill_n, err);
     }
   }
-  LCR_LAUNCHED(1 + (build ? 1 : 0) + (build && ns_total > 0 ? 3 : 0) + (out_idx ? 1 : 0));  // query, geom, insert, scatter, compact, spill
+  LCR_LAUNCHED(1 + (build ? 1 : 0) + (build && ns_total > 0 ? 3 : 0) + (out_idx && !nearest ? 1 : 0));  // query, geom, insert, scatter, compact, spill
   LCR_CUDA_CHECK_LAUNCH();
   return LCR_OK;
 }

@@ -17,7 +17,8 @@ def precompute_data_stack_mode(points, lengths, num_stages, voxel_size, radius, 
     """Same arguments / result dict as data.py:10-74.  Extra keys: ``lengths_host`` (list of
     python int lists, saves the model a device sync).  ``int32`` keeps the tables in the kernels'
     native index width; ``upsampling=False`` skips the three tables only the registration decoder
-    reads (the descriptor path never touches them).  With ``int32`` the searches are queued back to back
+    reads (the descriptor path never touches them); ``upsampling='nearest'`` keeps only their column 0 (shape [N, 1]: all
+    the decoder's nearest_upsample reads), found without the sort.  With ``int32`` the searches are queued back to back
     (no per-table read-back: tables keep ``neighbor_limits[i]`` columns, pads = number of support rows) and their
     status words ride on the single device->host read of the level lengths."""
     assert num_stages == len(neighbor_limits)
@@ -49,7 +50,8 @@ def precompute_data_stack_mode(points, lengths, num_stages, voxel_size, radius, 
         if i > 0 and upsampling:
             fine_points, fine_lengths = points_list[i - 1], lengths_list[i - 1]
             upsampling_list[i - 1] = ops.radius_search(fine_points, cur_points, fine_lengths, cur_lengths, radii[i],
-                                                       neighbor_limits[i], int32=int32, defer=defer, grid=grids[i])
+                                                       neighbor_limits[i], int32=int32, defer=defer, grid=grids[i],
+                                                       nearest=(upsampling == 'nearest'))
     if not upsampling:
         upsampling_list = []
     if defer:

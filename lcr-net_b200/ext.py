@@ -72,13 +72,15 @@ class SupportGrid:
         self.built = False
 
 
-def radius_neighbors(q_points, s_points, q_lengths, s_lengths, radius, limit=0, int32=False, defer=None, grid=None):
+def radius_neighbors(q_points, s_points, q_lengths, s_lengths, radius, limit=0, int32=False, defer=None, grid=None,
+                     nearest=False):
     """``utils.ext.radius_neighbors`` (radius_neighbors.cpp:5-68): (Nq, max_count) int64 table,
     padded with Ns.  ``limit`` > 0 fuses the ``[:, :limit]`` cut of ops/radius_search.py:25-26.
     ``defer`` (a list, with ``limit`` > 0): do not read the [max_count, status] words back -- the table keeps
     ``limit`` columns (pads = Ns) and the device words are appended to the list for ONE later check
     (``check_deferred``): the pyramid builder queues its 7-10 searches without draining the stream.
-    ``grid`` (SupportGrid of these supports and this radius): built by the first search that uses it, reused after."""
+    ``grid`` (SupportGrid of these supports and this radius): built by the first search that uses it, reused after.
+    ``nearest``: only column 0 of the table (Nq, 1) -- the closest support inside the radius -- without the sort."""
     for name, t in (('q_points', q_points), ('s_points', s_points)):
         _check(t.dtype == torch.float32, '%s must be a float tensor' % name)
         _check(t.is_contiguous(), '%s must be contiguous' % name)
@@ -107,7 +109,7 @@ def radius_neighbors(q_points, s_points, q_lengths, s_lengths, radius, limit=0, 
     dtype = torch.int32 if int32 else torch.int64
 
     def run(width, out):
-        reuse = 1 if (grid is not None and grid.built) else 0
+        reuse = (1 if (grid is not None and grid.built) else 0) | (2 if nearest else 0)
         _lib.check(L.lcr_radius_neighbors_ex(_lib.ptr(q), nq, _lib.ptr(s), ns, _lib.ptr(ql), _lib.ptr(sl), b,
                                              float(radius), width, _lib.ptr(out), 0 if int32 else 1, None,
                                              _lib.ptr(meta), _lib.ptr(meta[1:]), _lib.ptr(ws), ws.numel(), reuse,
@@ -115,7 +117,14 @@ def radius_neighbors(q_points, s_points, q_lengths, s_lengths, radius, limit=0, 
         if grid is not None:
             grid.built = True
 
-    if limit and limit > 0:
+    if nearest:
+        out = torch.empty((nq, 1), dtype=dtype, device=dev)
+        run(1, out)
+        if defer is not None and not on_cpu:
+            defer.append(meta)
+            return out
+        st = int(meta[1])
+    elif limit and limit > 0:
         out = torch.empty((nq, limit), dtype=dtype, device=dev)
         run(limit, out)
         if defer is not None and not on_cpu:

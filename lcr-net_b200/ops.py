@@ -21,12 +21,13 @@ def grid_subsample(points, lengths, voxel_size, order='reference'):
     return s_points, s_lengths
 
 
-def radius_search(q_points, s_points, q_lengths, s_lengths, radius, neighbor_limit, int32=False, defer=None, grid=None):
+def radius_search(q_points, s_points, q_lengths, s_lengths, radius, neighbor_limit, int32=False, defer=None, grid=None,
+                  nearest=False):
     """ops/radius_search.py:7-27 (the ``[:, :neighbor_limit]`` cut is fused into the kernel).
-    ``defer`` / ``grid``: see ext.radius_neighbors."""
+    ``defer`` / ``grid`` / ``nearest``: see ext.radius_neighbors."""
     return ext.radius_neighbors(q_points, s_points, q_lengths, s_lengths, radius,
                                 limit=neighbor_limit if neighbor_limit and neighbor_limit > 0 else 0, int32=int32,
-                                defer=defer, grid=grid)
+                                defer=defer, grid=grid, nearest=nearest)
 
 
 def _f32c(t):

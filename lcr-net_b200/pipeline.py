@@ -124,7 +124,7 @@ class PairPipeline:
                 p = p.to(self.device, non_blocking=True)
             l = torch.tensor(lens[lo:hi], dtype=torch.int64).to(self.device, non_blocking=True)
             d = gdata.device_collate(p, l, self.num_stages, self.voxel, self.radius, self.limits,
-                                     pre_voxel=self.pre_voxel, stack_size=2, int32=True, upsampling=True)
+                                     pre_voxel=self.pre_voxel, stack_size=2, int32=True, upsampling='nearest')
             out = self.net(d)
             done = torch.cuda.Event()
             done.record(stream)

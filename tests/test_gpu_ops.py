@@ -151,3 +151,29 @@ print('CELLS-OK')
     env = dict(os.environ, LCR_RADIUS_CELLS='2')
     r = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0 and 'CELLS-OK' in r.stdout, r.stderr[-3000:]
+
+
+@pytest.mark.gpu
+def test_nearest_only_search_is_column_zero():
+    """Nearest-only mode (the up-sampling tables of the registration pipeline): one column, equal to column 0 of the
+    full sorted table incl. the rows without any support inside the radius, for int32 and int64 tables, with and
+    without a reused support grid."""
+    import torch
+    from lcrnet_b200 import ext, ops
+    g = torch.Generator().manual_seed(11)
+    sl = torch.tensor([700, 1300], dtype=torch.int64)
+    ql = torch.tensor([2500, 1800], dtype=torch.int64)
+    s = (torch.rand(int(sl.sum()), 3, generator=g) * 20).cuda()
+    q = (torch.rand(int(ql.sum()), 3, generator=g) * 24 - 2).cuda()          # some queries outside the support box
+    q[:50] = s[:50]                                                            # exact hits (d2 = 0)
+    ql_d, sl_d = ql.cuda(), sl.cuda()
+    for int32 in (True, False):
+        full = ops.radius_search(q, s, ql_d, sl_d, 1.7, 40, int32=int32)
+        near = ops.radius_search(q, s, ql_d, sl_d, 1.7, 40, int32=int32, nearest=True)
+        assert near.shape == (q.shape[0], 1) and near.dtype == full.dtype
+        assert torch.equal(near[:, 0], full[:, 0])
+        assert int((near[:, 0] == s.shape[0]).sum()) > 0                       # pads exist
+        grid = ext.SupportGrid(s, sl_d, 1.7, q.shape[0])
+        a = ops.radius_search(q, s, ql_d, sl_d, 1.7, 40, int32=int32, grid=grid)
+        b = ops.radius_search(q, s, ql_d, sl_d, 1.7, 40, int32=int32, grid=grid, nearest=True)
+        assert torch.equal(a, full) and torch.equal(b, near)
