@@ -488,7 +488,8 @@ def bench_descriptor(ctx, args, inp):
             'e2e': {'value': pairs_all / (total_e2e * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': inp.h2d_bytes,
                     'd2h_bytes_per_step': int(out_desc.numel() * 4 + out_dist.numel() * 4),
                     'ms_per_step': total_e2e / args.steps},
-            'gpu_launches': int(launches), 'clocks': clocks, '_profile': prof, '_sd': sd, '_desc0': desc[:2].cpu()}
+            'gpu_launches': int(launches), 'clocks': clocks, 'ms_steps': [round(x, 2) for x in ms],
+            'ms_steps_e2e': [round(x, 2) for x in ms_e2e], '_profile': prof, '_sd': sd, '_desc0': desc[:2].cpu()}
 
 
 def bench_pairs(ctx, args, inp):

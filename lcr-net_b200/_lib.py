@@ -153,8 +153,9 @@ class _Workspace:
         self._buf = {}
 
     def get(self, nbytes, device, slot=0):
-        key = (device.index if device.index is not None else torch.cuda.current_device(),
-               torch.cuda.current_stream(device).cuda_stream, slot)
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        key = (idx, _raw_stream(idx) if _raw_stream is not None else torch.cuda.current_stream(device).cuda_stream,
+               slot)
         b = self._buf.get(key)
         if b is None or b.numel() < nbytes:
             b = torch.empty(max(int(nbytes * 1.25), 1 << 20), dtype=torch.uint8, device=device)

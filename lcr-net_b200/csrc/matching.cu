@@ -6,6 +6,8 @@
 //   fine correspondences               modules/geotransformer/local_global_registration.py:49-92
 //   local-to-global registration       local_global_registration.py:140-202, registration/procrustes.py:6-73
 // SFU / latency-bound small problems: one CTA per problem, everything stays on the device.
+#include <string.h>
+
 #include "common.cuh"
 #include "kabsch.cuh"
 
@@ -290,6 +292,105 @@ patch_scores_kernel(const float* __restrict__ fa, int na, const int32_t* __restr
           make_float4(acc[i][h * 4 + 0] / div, acc[i][h * 4 + 1] / div, acc[i][h * 4 + 2] / div, acc[i][h * 4 + 3] / div);
     }
   }
+}
+
+// ------------------------------------------------------------------ the same product on the warp-level tensor path
+// 128 x 128 x 128 per patch pair with mma.sync.m16n8k8 TF32 and the 3xTF32 operand split of the GEMMs (hi = upper 19
+// bits, lo = x - hi; lo.hi + hi.lo + hi.hi, fp32 accumulate: fp32-class accuracy).  Both gathered operands stay in their
+// natural [point][channel] layout in shared memory (row.col fragments of A . B^T read rows of both); the row stride of
+// 68 floats puts the eight rows x four columns of a fragment load on 32 distinct banks.  8 warps, each a 64 x 32
+// output block; two 64-channel stages, two CTAs per SM.  (A 128-row tcgen05 tile per pair would need the gather to
+// write swizzled hi / lo operand tiles; the legacy tensor path already makes the kernel MMA-bound instead of
+// FFMA-bound: 2.2 -> see DESIGN.md.)
+constexpr int PSS = PCH + 4;
+__device__ __forceinline__ void ps_mma(float (&d)[4], const unsigned (&a)[4], unsigned b0, unsigned b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void ps_split(float x, unsigned& hi, unsigned& lo) {
+  hi = __float_as_uint(x) & 0xFFFFE000u;
+  lo = __float_as_uint(x - __uint_as_float(hi));
+}
+
+__global__ void __launch_bounds__(256, 2)
+patch_scores_mma_kernel(const float* __restrict__ fa, int na, const int32_t* __restrict__ knn_a,
+                        const int32_t* __restrict__ node_a, const float* __restrict__ fb, int nb,
+                        const int32_t* __restrict__ knn_b, const int32_t* __restrict__ node_b, float div,
+                        float* __restrict__ out) {
+  extern __shared__ __align__(16) float sp[];  // A [PK][PSS], B [PK][PSS]
+  float(*sa)[PSS] = reinterpret_cast<float(*)[PSS]>(sp);
+  float(*sb)[PSS] = reinterpret_cast<float(*)[PSS]>(sp + PK * PSS);
+  const int p = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int row0 = (warp & 1) * 64, col0 = (warp >> 1) * 32;
+  const int32_t* ka = knn_a + (size_t)node_a[p] * PK;
+  const int32_t* kb = knn_b + (size_t)node_b[p] * PK;
+  // staging: 16 threads per 64-channel half row, 8 rows per thread and operand
+  const int sr = tid >> 4, sc = (tid & 15) * 4;
+  float acc[4][4][4];
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+#pragma unroll
+      for (int e = 0; e < 4; e++) acc[i][j][e] = 0.f;
+#pragma unroll 1
+  for (int half = 0; half < PC / PCH; half++) {
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 va[8], vb[8];
+#pragma unroll
+    for (int it = 0; it < 8; it++) {           // all 16 loads in flight before the first store
+      const int ia = ka[sr + 16 * it], ib = kb[sr + 16 * it];     // (re-read per stage: L1 hits, 16 registers less)
+      va[it] = ia < na ? *reinterpret_cast<const float4*>(fa + (size_t)ia * PC + half * PCH + sc) : z;
+      vb[it] = ib < nb ? *reinterpret_cast<const float4*>(fb + (size_t)ib * PC + half * PCH + sc) : z;
+    }
+    if (half) __syncthreads();                 // the previous stage has been consumed
+#pragma unroll
+    for (int it = 0; it < 8; it++) {
+      *reinterpret_cast<float4*>(&sa[sr + 16 * it][sc]) = va[it];
+      *reinterpret_cast<float4*>(&sb[sr + 16 * it][sc]) = vb[it];
+    }
+    __syncthreads();
+#pragma unroll 2
+    for (int ks = 0; ks < PCH / 8; ks++) {
+      const int k0 = ks * 8 + t;
+      unsigned bh[4][2], bl[4][2];
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const float* r = &sb[col0 + 8 * j + g][k0];
+        ps_split(r[0], bh[j][0], bl[j][0]);
+        ps_split(r[4], bh[j][1], bl[j][1]);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const float* r0 = &sa[row0 + 16 * i + g][k0];
+        const float* r1 = r0 + 8 * PSS;
+        unsigned ah[4], al[4];
+        ps_split(r0[0], ah[0], al[0]);
+        ps_split(r1[0], ah[1], al[1]);
+        ps_split(r0[4], ah[2], al[2]);
+        ps_split(r1[4], ah[3], al[3]);
+        // three passes over the four n-tiles: consecutive MMAs never share an accumulator
+#pragma unroll
+        for (int j = 0; j < 4; j++) ps_mma(acc[i][j], al, bh[j][0], bh[j][1]);
+#pragma unroll
+        for (int j = 0; j < 4; j++) ps_mma(acc[i][j], ah, bl[j][0], bl[j][1]);
+#pragma unroll
+        for (int j = 0; j < 4; j++) ps_mma(acc[i][j], ah, bh[j][0], bh[j][1]);
+      }
+    }
+  }
+  float* o = out + (size_t)p * PK * PK;
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int r = row0 + 16 * i + g, c = col0 + 8 * j + 2 * t;
+      *reinterpret_cast<float2*>(o + (size_t)r * PK + c) = make_float2(acc[i][j][0] / div, acc[i][j][1] / div);
+      *reinterpret_cast<float2*>(o + (size_t)(r + 8) * PK + c) = make_float2(acc[i][j][2] / div, acc[i][j][3] / div);
+    }
 }
 
 // ================================================================== fine correspondences
@@ -845,11 +946,19 @@ extern "C" int lcr_patch_scores(const float* feats_a, int64_t n_a, const int32_t
   cudaStream_t stream = (cudaStream_t)stream_;
   LCR_REQUIRE(k == PK && channels == PC, "patch_scores: specialised to 128 points x 128 channels");
   if (n_pairs == 0) return LCR_OK;
-  const size_t smem = sizeof(float) * 2 * PCH * (PK + 4);
-  LCR_CUDA_TRY(cudaFuncSetAttribute(patch_scores_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   LcrProfScope prof("patch_scores", 2.0 * n_pairs * PK * PK * PC, 4.0 * n_pairs * (2.0 * PK * PC + PK * PK), stream);
-  patch_scores_kernel<<<n_pairs, 256, smem, stream>>>(feats_a, (int)n_a, knn_a, node_a, feats_b, (int)n_b, knn_b,
-                                                      node_b, sqrtf((float)channels), out);
+  static const bool simt = getenv("LCR_PATCH") && !strcmp(getenv("LCR_PATCH"), "simt");   // default: mma.sync 3xTF32
+  if (simt) {
+    const size_t smem = sizeof(float) * 2 * PCH * (PK + 4);
+    LCR_CUDA_TRY(cudaFuncSetAttribute(patch_scores_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    patch_scores_kernel<<<n_pairs, 256, smem, stream>>>(feats_a, (int)n_a, knn_a, node_a, feats_b, (int)n_b, knn_b,
+                                                        node_b, sqrtf((float)PC), out);
+  } else {
+    const size_t smem = sizeof(float) * 2 * PK * PSS;
+    LCR_CUDA_TRY(cudaFuncSetAttribute(patch_scores_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    patch_scores_mma_kernel<<<n_pairs, 256, smem, stream>>>(feats_a, (int)n_a, knn_a, node_a, feats_b, (int)n_b, knn_b,
+                                                            node_b, sqrtf((float)PC), out);
+  }
   LCR_LAUNCHED(1);
   LCR_CUDA_CHECK_LAUNCH();
   return LCR_OK;

@@ -272,13 +272,17 @@ class LearnableLogOptimalTransport(nn.Module):
         self.num_iterations = num_iterations
         self.register_parameter('alpha', nn.Parameter(torch.tensor(1.0)))
 
-    def forward(self, scores, row_masks=None, col_masks=None):
-        return P.sinkhorn(scores, row_masks, col_masks, self.alpha, self.num_iterations)
+    def forward(self, scores, row_masks=None, col_masks=None, out=None):
+        return P.sinkhorn(scores, row_masks, col_masks, self.alpha, self.num_iterations, out=out)
 
 
 # ------------------------------------------------------------------ the model
 class LCRNet(nn.Module):
     """model_family/LCRNet.py:25-321.  ``with_descriptor=False`` gives LCRNet_Matching (no NetVLAD head)."""
+
+    # True: also return the node / point transport plans ('_node_ot', '_point_ot'; parity tests) and allocate the
+    # point-level temporaries as ordinary tensors instead of workspace views
+    keep_intermediates = False
 
     def __init__(self, cfg, with_descriptor=True):
         super().__init__()
@@ -363,10 +367,14 @@ class LCRNet(nn.Module):
         total = patch_off_host[-1]
         patch_off = ops.host_to_device(torch.tensor(patch_off_host, dtype=torch.int32), dev)
         ci_g, cj_g, ci_l, cj_l, _, patch_pair = P.gather_coarse(oi, oj, os_, patch_off, node_st, total)
-        ms = P.patch_scores(feats_f, knn_g, ci_g, feats_f, knn_g, cj_g)               # LCRNet.py:231-233
+        # the two ~1 GB temporaries live in the per-stream workspace unless a caller wants to look at them
+        keep = self.keep_intermediates
+        ms = P.patch_scores(feats_f, knn_g, ci_g, feats_f, knn_g, cj_g,               # LCRNet.py:231-233
+                            out=None if keep else P.scratch((total, 128, 128), dev, 6))
         km_bool = knn_mask.bool()
         pkm, akm = km_bool[ci_g.long()], km_bool[cj_g.long()]
-        ot = self.optimal_transport(ms, pkm, akm)                                     # one launch, all patch pairs
+        ot = self.optimal_transport(ms, pkm, akm,                                     # one launch, all patch pairs
+                                    out=None if keep else P.scratch((total, 129, 129), dev, 7))
         corr = P.fine_correspondences(ot, knn_mask, ci_g, knn_mask, cj_g)
         ref_c, src_c = P.corr_points(corr, points_f, knn_g, ci_g, points_f, knn_g, cj_g)
         T = P.lgr_batched(ref_c, src_c, corr['score'], corr['pair'], corr['pair_off'], patch_pair, patch_off, n_pairs,
@@ -402,9 +410,11 @@ class LCRNet(nn.Module):
                 'pos_node_corr_knn_masks': pkm[t0:t1], 'anc_node_corr_knn_masks': akm[t0:t1],
                 'pos_corr_points': ref_c[c0:c1], 'anc_corr_points': src_c[c0:c1], 'corr_scores': corr['score'][c0:c1],
                 'estimated_transform': T[p],
-                '_node_ot': node_ot[p], '_point_ot': ot[t0:t1], '_corr_patch': corr_patch_local[c0:c1],
+                '_corr_patch': corr_patch_local[c0:c1],
                 '_corr_i': corr['i'][c0:c1], '_corr_j': corr['j'][c0:c1],
             }
+            if keep:
+                out['_node_ot'], out['_point_ot'] = node_ot[p], ot[t0:t1]
             if self.with_descriptor:
                 out['pos_feature_global'] = descriptors[a:a + 1]
                 out['anc_feature_global'] = descriptors[b:b + 1]

@@ -125,10 +125,24 @@ def point_to_node_partition(points, nodes, point_limit=128, int64=False):
     return owner, node_mask.bool(), knn, knn_mask.bool(), status
 
 
-def sinkhorn(scores, row_masks, col_masks, alpha, iters=100):
+def scratch(shape, device, slot):
+    """float32 tensor of ``shape`` carved from the grow-only per-(device, stream) workspace ``slot``: for the two
+    ~1 GB temporaries of the registration tail (patch scores, point-level transport plans of ~17 k patch pairs).
+    Asking the caching allocator for them every step made it split and re-grow its largest blocks for more than ten
+    forwards (sporadic 40-300 ms cudaMalloc stalls inside a step)."""
+    n = 1
+    for d in shape:
+        n *= int(d)
+    buf = _lib.workspace.get(4 * max(n, 1), device, slot=slot)
+    return buf[:4 * n].view(torch.float32).view(*shape)
+
+
+def sinkhorn(scores, row_masks, col_masks, alpha, iters=100, out=None):
     """learnable_sinkhorn.py:13-66: scores [B,M,N] -> [B,M+1,N+1]."""
     b, m, n = scores.shape
-    out = torch.empty((b, m + 1, n + 1), dtype=torch.float32, device=scores.device)
+    if out is None:
+        out = torch.empty((b, m + 1, n + 1), dtype=torch.float32, device=scores.device)
+    assert out.shape == (b, m + 1, n + 1) and out.is_contiguous()
     rm = None if row_masks is None else row_masks.to(torch.uint8).contiguous()
     cm = None if col_masks is None else col_masks.to(torch.uint8).contiguous()
     _lib.check(_L().lcr_sinkhorn(_lib.ptr(_f32c(scores)), b, m, n, _lib.ptr(rm), _lib.ptr(cm),
@@ -157,9 +171,11 @@ def coarse_matching(log_scores, defer=False):
     return oi[:p], oj[:p], os_[:p]
 
 
-def patch_scores(feats_a, knn_a, node_a, feats_b, knn_b, node_b):
+def patch_scores(feats_a, knn_a, node_a, feats_b, knn_b, node_b, out=None):
     p = node_a.shape[0]
-    out = torch.empty((p, 128, 128), dtype=torch.float32, device=feats_a.device)
+    if out is None:
+        out = torch.empty((p, 128, 128), dtype=torch.float32, device=feats_a.device)
+    assert out.shape == (p, 128, 128) and out.is_contiguous()
     _lib.check(_L().lcr_patch_scores(_lib.ptr(_f32c(feats_a)), feats_a.shape[0], _lib.ptr(knn_a), _lib.ptr(node_a),
                                      _lib.ptr(_f32c(feats_b)), feats_b.shape[0], _lib.ptr(knn_b), _lib.ptr(node_b), p,
                                      128, feats_a.shape[1], _lib.ptr(out), _s(feats_a)))

@@ -200,6 +200,7 @@ def pair_batch():
     limits = gdata.calibrate_neighbors_scans(scans[:2], 4, 0.3, 1.275, pre_voxel=0.3, scans_per_sample=2)
     sd = checkpoint.random_state_dict('lcrnet', 7351)
     net = lcrnet.create_model(lcrnet.default_cfg(limits)).eval()
+    net.keep_intermediates = True            # the node / point transport plans are compared below
     net.load_state_dict(sd, strict=True)
     net = net.cuda()
     d = gdata.scans_collate_fn_stack_mode(scans, 4, 0.3, 1.275, limits, pre_voxel=0.3, stack_size=2, int32=True,
