@@ -13,6 +13,8 @@ SHAPES = [  # (M, K, N, what)
     (361000, 256, 64, 'unary 256->64'), (130000, 512, 128, 'unary 512->128'), (46000, 1024, 256, 'unary 1024->256'),
     (46000, 256, 1024, 'unary 256->1024'), (130000, 256, 512, 'unary 256->512'), (130000, 128, 512, 'unary 128->512'),
     (909000, 64, 32, 'unary 64->32'), (909000, 32, 128, 'unary 32->128'),
+    (909000, 64, 128, 'unary 64->128'), (361000, 128, 256, 'unary 128->256'), (361000, 64, 256, 'unary 64->256'),
+    (361000, 128, 64, 'unary 128->64'), (130000, 128, 512, 'unary 128->512 (2 n-tiles)'),
 ]
 flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
 tot = 0.0
