@@ -91,7 +91,7 @@ constexpr int RB = 3;                                        // rows (columns) p
 constexpr int NG = PP / RB;                                  // 44 row (column) groups
 constexpr int kPatchThreads = 384;                           // 12 warps, 352 threads carry data
 constexpr int kPatchSFloats = 16644;                         // 129 * 129 rounded up to a multiple of 4
-constexpr size_t kPatchSmem = sizeof(float) * (kPatchSFloats + 4 * PV + 6 * PP);
+constexpr size_t kPatchSmem = sizeof(float) * (kPatchSFloats + 4 * PV + 6 * PP + 4);
 
 __device__ __forceinline__ int vec_slot(int x) { return PSEG * (x / PB) + x % PB; }   // x < 136
 
@@ -157,6 +157,7 @@ __global__ void __launch_bounds__(kPatchThreads, 1) sinkhorn_patch_kernel(Sinkho
   float* nu = mu + PP;
   float* log_mu = nu + PP;
   float* log_nu = log_mu + PP;
+  float* chg = log_nu + PP;            // [2] "a scaling changed in iteration it" flags (iteration numbers as bits)
   const int b = blockIdx.x, tid = threadIdx.x;
   const int g = tid >> 3, h = tid & (PH - 1);
   const bool active = g < NG;                    // 44 groups of 3 rows (columns)
@@ -183,6 +184,7 @@ __global__ void __launch_bounds__(kPatchThreads, 1) sinkhorn_patch_kernel(Sinkho
     u[i] = 0.f;
     v[i] = 0.f;
   }
+  if (tid < 2) chg[tid] = __int_as_float(-1);
   for (int e = tid; e < 2 * PV; e += kPatchThreads) {
     la[e] = 0.f;
     lb[e] = 0.f;
@@ -272,36 +274,58 @@ __global__ void __launch_bounds__(kPatchThreads, 1) sinkhorn_patch_kernel(Sinkho
       // tight loop over consecutive LIN iterations; leaves on the first out-of-band scaling (fail) or at the end
       const uint32_t la_s = (uint32_t)__cvta_generic_to_shared(la), lb_s = (uint32_t)__cvta_generic_to_shared(lb);
       const uint32_t seg_off = 4u * PSEG * (uint32_t)h, slot_off = 4u * (uint32_t)my_slot;
-      bool fail = false;
+      bool fail = false, fixed = false;
+      // Exact early exit: when an iteration reproduces BIT FOR BIT every scaling of the iteration two steps back
+      // (whose values still sit in the buffer it is about to overwrite), the sequence has entered a cycle of period
+      // 1 or 2 -- same inputs, same arithmetic -- and the state after the full iteration count is the current one or
+      // the previous one, by the parity of the iterations left: both are in shared memory.  Finishers that see a
+      // changed value store the iteration number into chg[it & 1]; the flag of iteration `it` is read after its
+      // second barrier and is rewritten two iterations (four barriers) later.
+      const uint32_t chg_s = (uint32_t)__cvta_generic_to_shared(chg);
       while (it < a.iters) {
         const uint32_t cur = 4u * PV * (uint32_t)p, nxt = 4u * PV * (uint32_t)(p ^ 1);
+        const uint32_t chg_it = chg_s + 4u * (uint32_t)(it & 1);
         bool bad;
         {
           float s[RB];
+          const float prev = lds32(la_s + nxt + slot_off);      // a of iteration it - 2
           dot_block(kr, lb_s + cur + seg_off, s);
           const float sum = h == 0 ? s[0] : h == 1 ? s[1] : s[2];
           const float an = my_mu > 0.f ? __fdividef(my_mu, sum) : 0.f;
           bad = my_mu > 0.f && !(an < kHi && an > kLo);
-          if (finisher) sts32(la_s + nxt + slot_off, an);
+          if (finisher) {
+            sts32(la_s + nxt + slot_off, an);
+            if (an != prev) sts32(chg_it, __int_as_float(it));
+          }
         }
         fail = __syncthreads_or(bad) != 0;
         if (fail) break;
         {
           float s[RB];
+          const float prev = lds32(lb_s + nxt + slot_off);
           dot_block(kc, la_s + nxt + seg_off, s);
           const float sum = h == 0 ? s[0] : h == 1 ? s[1] : s[2];
           const float bn = my_nu > 0.f ? __fdividef(my_nu, sum) : 0.f;
           bad = my_nu > 0.f && !(bn < kHi && bn > kLo);
-          if (finisher) sts32(lb_s + nxt + slot_off, bn);
+          if (finisher) {
+            sts32(lb_s + nxt + slot_off, bn);
+            if (bn != prev) sts32(chg_it, __int_as_float(it));
+          }
         }
         fail = __syncthreads_or(bad) != 0;
         if (fail) break;
+        fixed = __float_as_int(lds32(chg_it)) != it;
         p ^= 1;
         it++;
         streak++;
         n_lin++;
+        if (fixed) break;
       }
-      if (!fail) break;      // all iterations done
+      if (fixed) {               // the remaining iterations only alternate between the last two states
+        if ((a.iters - it) & 1) p ^= 1;
+        it = a.iters;
+      }
+      if (!fail) break;          // all iterations done
       // discard this iteration and absorb the previous (consistent) scalings into the potentials
       n_disc++;
       if (tid < PR) {
