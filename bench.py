@@ -551,7 +551,10 @@ def bench_pairs(ctx, args, inp):
            'config': {'workload': 'configs[2]: scan-pair registration (LCRNet full forward: descriptors + pose), batch '
                                   '%d pairs of 65536-point scans per step per GPU' % n_pairs,
                       'neighbor_limits': inp.limits, 'streams': args.pair_streams, 'cache': 'L2 flushed between timed steps',
-                      'weights': 'seeded random: correspondences are not meaningful, the work is'},
+                      'weights': 'seeded random: correspondences are not meaningful, the work is',
+                      'sinkhorn': '100 iterations as the reference; the point-level kernel leaves the loop when the '
+                                  'scalings repeat bit for bit with period 1 or 2 -- the output is identical to the full '
+                                  'count (tests/test_gpu_pair.py::test_point_sinkhorn_early_exit_is_exact)'},
            'e2e': {'value': pairs_all / (total_e2e * 1e-3), 'unit': 'pairs/s', 'h2d_bytes_per_step': inp.h2d_bytes,
                    'd2h_bytes_per_step': int(out_T.numel() * 4 + out_desc.numel() * 4), 'ms_per_step': total_e2e / steps},
            'gpu_launches': int(launches), 'mean_correspondences': float(np.mean(n_corr)),

@@ -290,6 +290,10 @@ int lcr_sinkhorn_stats(int64_t* out4, int reset);
  * whose shared-memory row slabs hold the plan, 4 / 8 force that cluster size.  Point-level (128 x 128) problems always
  * use the register-resident kernel. */
 void lcr_set_sinkhorn_cluster(int mode);
+/* Point-level kernel: 1 (default) stops the iteration as soon as every scaling reproduces, bit for bit, its value of
+ * two iterations before -- the sequence is then periodic and the result after `iters` iterations is known exactly
+ * (tests compare both settings bitwise); 0 always runs the full count. */
+void lcr_set_sinkhorn_early_exit(int on);
 size_t lcr_coarse_matching_ws_bytes(int rows, int cols);
 int lcr_coarse_matching(const float* log_scores, int rows, int cols, int32_t* out_i, int32_t* out_j,
                         float* out_scores, int32_t* out_count, void* ws, size_t ws_bytes, void* stream);

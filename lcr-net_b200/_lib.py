@@ -72,6 +72,7 @@ SIGNATURES = {
     'lcr_sinkhorn': (c_i32, [c_vp, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_i32, c_vp, c_vp]),
     'lcr_sinkhorn_stats': (c_i32, [ctypes.POINTER(c_i64), c_i32]),
     'lcr_set_sinkhorn_cluster': (None, [c_i32]),
+    'lcr_set_sinkhorn_early_exit': (None, [c_i32]),
     'lcr_coarse_matching_ws_bytes': (c_sz, [c_i32, c_i32]),
     'lcr_coarse_matching': (c_i32, [c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
     'lcr_patch_scores': (c_i32, [c_vp, c_i64, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp]),

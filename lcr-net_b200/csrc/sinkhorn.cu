@@ -20,6 +20,10 @@
 // Measured against an fp64 evaluation of the reference (tests/test_gpu_pair.py): 7e-6 .. 2e-5 absolute on the log
 // scores for score ranges up to +-100; the torch fp32 reference itself is 4e-5 .. 3e-4 away from fp64 there.
 //
+// Exact early exit (point level): a LIN iteration whose scalings all equal, bit for bit, those of two iterations before
+// has closed a cycle of period 1 or 2; the remaining iterations only replay it, so the loop stops and the final state is
+// picked by the parity of the iterations left (lcr_set_sinkhorn_early_exit(0) runs the full count: same bits).
+//
 // Kernels:
 //   sinkhorn_patch_kernel    the point-level problems (128 x 128 (+1), thousands per batch): K lives in REGISTERS in
 //                            row form and in column form (3 x 17 blocks per thread each); a LIN half-iteration is
@@ -42,6 +46,7 @@ struct SinkhornArgs {
   const float* alpha;        // device scalar
   float* out;                // [B, M+1, N+1]
   int M, N, iters;
+  int early_exit;            // 1: stop at a bitwise cycle of the scalings (exact), 0: always run `iters` iterations
 };
 
 // iteration statistics (debug / tuning): [0] LOG iterations, [1] LIN iterations, [2] discarded LIN iterations,
@@ -319,7 +324,8 @@ __global__ void __launch_bounds__(kPatchThreads, 1) sinkhorn_patch_kernel(Sinkho
         it++;
         streak++;
         n_lin++;
-        if (fixed) break;
+        if (fixed && a.early_exit) break;
+        fixed = false;
       }
       if (fixed) {               // the remaining iterations only alternate between the last two states
         if ((a.iters - it) & 1) p ^= 1;
@@ -978,6 +984,8 @@ int launch_sinkhorn_cluster(const SinkhornArgs& a, int batch, int rs, size_t sme
 
 // Node-level kernel selection: 0 single-CTA kernel, 1 (default) smallest cluster that fits, 4 / 8 that cluster size.
 // LCR_SINKHORN_CLUSTER sets the default; lcr_set_sinkhorn_cluster overrides it (tests).
+static int g_sinkhorn_early_exit = 1;
+extern "C" void lcr_set_sinkhorn_early_exit(int on) { g_sinkhorn_early_exit = on ? 1 : 0; }
 static int g_sinkhorn_cluster = -1;
 static int sinkhorn_cluster_mode() {
   if (g_sinkhorn_cluster < 0) g_sinkhorn_cluster = getenv("LCR_SINKHORN_CLUSTER") ? atoi(getenv("LCR_SINKHORN_CLUSTER")) : 1;
@@ -1004,7 +1012,7 @@ extern "C" int lcr_sinkhorn(const float* scores, int batch, int rows, int cols, 
   LCR_REQUIRE(batch >= 0 && rows >= 1 && cols >= 1 && iters >= 0, "sinkhorn: sizes");
   LCR_REQUIRE(scores && alpha && out, "sinkhorn: null pointer");
   if (batch == 0) return LCR_OK;
-  SinkhornArgs a{scores, row_mask, col_mask, alpha, out, rows, cols, iters};
+  SinkhornArgs a{scores, row_mask, col_mask, alpha, out, rows, cols, iters, g_sinkhorn_early_exit};
   const bool patch = rows == PN && cols == PN;
   LcrProfScope prof(patch ? "sinkhorn_point" : "sinkhorn_node", 4.0 * batch * (double)(rows + 1) * (cols + 1) * iters,
                     4.0 * batch * ((double)rows * cols + (double)(rows + 1) * (cols + 1)), stream);

@@ -162,6 +162,41 @@ def test_sinkhorn_vs_oracle(b, m, n, scale):
     print('   iterations per problem: LOG %.1f, LIN %.1f, discarded %.1f, absorptions %.1f' % tuple(x / b for x in st))
 
 
+def test_point_sinkhorn_early_exit_is_exact():
+    """The point-level kernel leaves the iteration when the scalings have entered a bitwise cycle of period 1 or 2
+    (sinkhorn.cu): the result must equal the full 100 iterations BIT FOR BIT, for odd and even iteration counts
+    (the parity of the remaining iterations selects which of the two states is final), and the exit must actually
+    trigger on well-conditioned problems."""
+    import ctypes
+    from lcrnet_b200 import _lib
+    from lcrnet_b200 import pair_ops as P
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(21)
+    s = torch.cat([torch.randn(6, 128, 128, generator=g) * 2, torch.randn(6, 128, 128, generator=g) * 0.3,
+                   torch.randn(4, 128, 128, generator=g) * 40]).cuda()
+    rm = (torch.rand(16, 128, generator=g) > 0.1).cuda()
+    cm = (torch.rand(16, 128, generator=g) > 0.1).cuda()
+    alpha = torch.tensor(0.7).cuda()
+    st = (ctypes.c_int64 * 4)()
+    try:
+        for iters in (100, 99, 37):
+            L.lcr_set_sinkhorn_early_exit(0)
+            L.lcr_sinkhorn_stats(st, 1)
+            full = P.sinkhorn(s, rm, cm, alpha, iters).clone()
+            L.lcr_sinkhorn_stats(st, 1)
+            n_full = st[0] + st[1]
+            L.lcr_set_sinkhorn_early_exit(1)
+            early = P.sinkhorn(s, rm, cm, alpha, iters)
+            L.lcr_sinkhorn_stats(st, 1)
+            assert torch.equal(full, early)
+            assert n_full == 16 * iters
+            if iters == 100:
+                print('iterations run with the early exit: %d of %d' % (st[0] + st[1], n_full))
+                assert st[0] + st[1] < n_full
+    finally:
+        L.lcr_set_sinkhorn_early_exit(1)
+
+
 @pytest.mark.parametrize('mode', [0, 4, 8])
 def test_node_sinkhorn_kernel_variants_agree(mode):
     """Node-level problems run on a thread-block cluster (row slabs of the plan in shared memory, column partials
