@@ -459,9 +459,9 @@ attention_tma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
 #pragma unroll
           for (int e = 0; e < 4; e++) {
             const float x = live ? xs[e] : 0.f;
-            const float h = rn_tf32(x);
+            const float h = trunc_tf32(x);
             Vhi[sub * 1024 + sw_off(c + e, kc)] = h;
-            Vlo[sub * 1024 + sw_off(c + e, kc)] = rn_tf32(x - h);
+            Vlo[sub * 1024 + sw_off(c + e, kc)] = x - h;
           }
         }
       }
@@ -492,9 +492,9 @@ attention_tma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         for (int e = 0; e < 32; e++) {
           const float p = fast_exp(__uint_as_float(sr[c0 + e]) - m_new);
           psum += p;
-          const float h = rn_tf32(p);
+          const float h = trunc_tf32(p);       // the tensor core truncates its operands: hi + lo = p exactly
           hi[e] = __float_as_uint(h);
-          lo[e] = __float_as_uint(rn_tf32(p - h));
+          lo[e] = __float_as_uint(p - h);
         }
         st_tmem32(tmem_phi + lane_base + c0, hi);
         st_tmem32(tmem_plo + lane_base + c0, lo);
