@@ -752,7 +752,7 @@ __global__ void __launch_bounds__(kClThreads, 1) sinkhorn_cluster_kernel(Sinkhor
       float* a_new = la + (p ^ 1) * rs;
       float* b_new = lb + (p ^ 1) * Cs;
       const float* b_cur = lb + p * Cs;
-      bool bad = false;
+      bool bad = false, chg = false;                // chg: a scaling differs from its value two iterations back
       {
         float bc[kClChunks];                        // this lane's columns of the current scalings
 #pragma unroll
@@ -784,11 +784,12 @@ __global__ void __launch_bounds__(kClThreads, 1) sinkhorn_cluster_kernel(Sinkhor
               an = __fdividef(m_, sum);
               bad |= !(an < kHi && an > kLo);
             }
+            chg |= an != a_new[i];                  // (a_new still holds the scaling of iteration it - 2)
             a_new[i] = an;
           }
         }
       }
-      const int row_bad = __syncthreads_or(bad);
+      const int row_bad = (__syncthreads_or(bad) ? 1 : 0) | (__syncthreads_or(chg) ? 2 : 0);
       for (int j = tid; j < C; j += nt) {           // thread per column over the slab's rows
         float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
         int i = 0;
@@ -806,6 +807,7 @@ __global__ void __launch_bounds__(kClThreads, 1) sinkhorn_cluster_kernel(Sinkhor
       if (tid < CL) peer_flags[tid][(x & 1) * CL + rank] = row_bad;
       cluster.sync();
       bad = false;
+      chg = false;
       for (int j = tid; j < C; j += nt) {
         float sum = 0.f;
 #pragma unroll
@@ -816,17 +818,26 @@ __global__ void __launch_bounds__(kClThreads, 1) sinkhorn_cluster_kernel(Sinkhor
           bn = __fdividef(n_, sum);
           bad |= !(bn < kHi && bn > kLo);
         }
+        chg |= bn != b_new[j];
         b_new[j] = bn;
       }
 #pragma unroll
-      for (int r = 0; r < CL; r++) bad |= fl[r] != 0;
+      for (int r = 0; r < CL; r++) {
+        bad |= (fl[r] & 1) != 0;
+        chg |= (fl[r] & 2) != 0;
+      }
       const bool fail = __syncthreads_or(bad) != 0;
+      const bool moving = __syncthreads_or(chg) != 0;       // identical on every rank (replicated inputs)
       x++;
       if (!fail) {
         p ^= 1;
         it++;
         streak++;
         n_lin++;
+        if (!moving && a.early_exit) {   // period-1 / period-2 cycle: exact early exit (see the point-level kernel)
+          if ((a.iters - it) & 1) p ^= 1;
+          it = a.iters;
+        }
         continue;
       }
       n_disc++;

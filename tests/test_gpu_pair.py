@@ -193,6 +193,19 @@ def test_point_sinkhorn_early_exit_is_exact():
             if iters == 100:
                 print('iterations run with the early exit: %d of %d' % (st[0] + st[1], n_full))
                 assert st[0] + st[1] < n_full
+        # the node-level cluster kernel has the same exit (the flags travel with the DSMEM exchange)
+        sn = (torch.randn(3, 210, 190, generator=g) * 0.5).cuda()
+        rn = (torch.arange(210)[None, :] < torch.tensor([[210], [150], [201]])).cuda()
+        cn = (torch.arange(190)[None, :] < torch.tensor([[170], [190], [33]])).cuda()
+        for iters in (100, 63):
+            L.lcr_set_sinkhorn_early_exit(0)
+            full = P.sinkhorn(sn, rn, cn, alpha, iters).clone()
+            L.lcr_sinkhorn_stats(st, 1)
+            L.lcr_set_sinkhorn_early_exit(1)
+            early = P.sinkhorn(sn, rn, cn, alpha, iters)
+            L.lcr_sinkhorn_stats(st, 1)
+            assert torch.equal(full, early)
+            print('node level, %d iterations: %d run with the early exit' % (3 * iters, st[0] + st[1]))
     finally:
         L.lcr_set_sinkhorn_early_exit(1)
 
