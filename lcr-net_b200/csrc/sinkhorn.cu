@@ -293,7 +293,7 @@ __global__ void __launch_bounds__(kPatchThreads, 1) sinkhorn_patch_kernel(Sinkho
         bool bad;
         {
           float s[RB];
-          const float prev = lds32(la_s + nxt + slot_off);      // a of iteration it - 2
+          const float prev = finisher ? lds32(la_s + nxt + slot_off) : 0.f;      // a of iteration it - 2
           dot_block(kr, lb_s + cur + seg_off, s);
           const float sum = h == 0 ? s[0] : h == 1 ? s[1] : s[2];
           const float an = my_mu > 0.f ? __fdividef(my_mu, sum) : 0.f;
@@ -307,7 +307,7 @@ __global__ void __launch_bounds__(kPatchThreads, 1) sinkhorn_patch_kernel(Sinkho
         if (fail) break;
         {
           float s[RB];
-          const float prev = lds32(lb_s + nxt + slot_off);
+          const float prev = finisher ? lds32(lb_s + nxt + slot_off) : 0.f;
           dot_block(kc, la_s + nxt + seg_off, s);
           const float sum = h == 0 ? s[0] : h == 1 ? s[1] : s[2];
           const float bn = my_nu > 0.f ? __fdividef(my_nu, sum) : 0.f;
